@@ -1,0 +1,93 @@
+/* TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+ *
+ * Ensemble driver for the CPU oracle: one independent solver call per
+ * trajectory, spread over host threads (pthreads, dynamic chunks of 8) -- the C
+ * equivalent of the numba prange loop the reference's README (:60-67) recommends
+ * for ensembles.
+ */
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stddef.h>
+#include <unistd.h>
+
+#include "oracle.h"
+
+typedef struct {
+    int solver;
+    oracle_rhs_fn f;
+    long B;
+    int neq;
+    const double *u0;
+    long u0_stride;
+    const void *data;
+    long data_stride;
+    int nt;
+    const double *teval;
+    double *usol;
+    double rtol, atol;
+    int mxstep, exit_on_warning;
+    int *success, *counters;
+    atomic_long next;
+} job_t;
+
+static void *worker(void *arg)
+{
+    job_t *j = (job_t *)arg;
+    for (;;) {
+        long b0 = atomic_fetch_add(&j->next, 8), b1 = b0 + 8;
+        if (b0 >= j->B)
+            break;
+        if (b1 > j->B)
+            b1 = j->B;
+        for (long b = b0; b < b1; b++) {
+            const double *u0b = j->u0 + b * j->u0_stride;
+            void *db = (void *)((const char *)j->data + b * j->data_stride);
+            double *out = j->usol + (size_t)b * j->nt * j->neq;
+            int ok = 0;
+            if (j->solver == 0) {
+                oracle_dop853_stats st;
+                oracle_dop853(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
+                              j->mxstep, &ok, &st);
+                if (j->counters) {
+                    int *c = j->counters + b * ORACLE_NCOUNTERS;
+                    c[0] = st.nstep, c[1] = st.nfcn, c[2] = st.naccpt, c[3] = st.nrejct;
+                    c[4] = st.nevent, c[5] = st.idid, c[6] = st.rows, c[7] = 0;
+                }
+            } else {
+                oracle_lsoda_stats st;
+                oracle_lsoda(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
+                             j->mxstep, &ok, j->exit_on_warning, &st);
+                if (j->counters) {
+                    int *c = j->counters + b * ORACLE_NCOUNTERS;
+                    c[0] = st.nst, c[1] = st.nfe, c[2] = st.nje, c[3] = st.nswitch;
+                    c[4] = st.nqu, c[5] = st.istate, c[6] = st.rows, c[7] = st.meth;
+                }
+            }
+            j->success[b] = ok;
+        }
+    }
+    return 0;
+}
+
+int oracle_solve_batch(int solver, oracle_rhs_fn f, long B, int neq, const double *u0,
+                       long u0_stride, const void *data, long data_stride, int nt,
+                       const double *teval, double *usol, double rtol, double atol,
+                       int mxstep, int exit_on_warning, int *success, int *counters,
+                       int nthreads)
+{
+    job_t j = {solver, f,    B,    neq,  u0,     u0_stride,       data,    data_stride,
+               nt,     teval, usol, rtol, atol,   mxstep, exit_on_warning, success, counters, 0};
+    pthread_t th[256];
+    if (nthreads <= 0)
+        nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (nthreads > 256)
+        nthreads = 256;
+    if (nthreads < 1)
+        nthreads = 1;
+    for (int i = 1; i < nthreads; i++)
+        pthread_create(&th[i], 0, worker, &j);
+    worker(&j);
+    for (int i = 1; i < nthreads; i++)
+        pthread_join(th[i], 0);
+    return nthreads;
+}

@@ -1,0 +1,123 @@
+"""ctypes bindings of the CPU oracle (oracle/liboracle.so) and, when it was built,
+of the compiled reference LSODA (oracle/_ref/*.so).  Test infrastructure only."""
+import ctypes as ct
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+REFSRC = "/root/reference/src/LSODA.cpp"
+
+
+class LsodaStats(ct.Structure):
+    _fields_ = [(k, ct.c_int) for k in
+                "nst nfe nje nswitch nqu meth istate rows nattempt nhnil".split()] + \
+               [("tn", ct.c_double), ("hu", ct.c_double)]
+
+
+class Dop853Stats(ct.Structure):
+    _fields_ = [(k, ct.c_int) for k in
+                "nfcn nstep naccpt nrejct nevent idid rows pad_".split()] + \
+               [("hlast", ct.c_double), ("xlast", ct.c_double)]
+
+
+def _build():
+    if not os.path.exists(os.path.join(ODIR, "liboracle.so")):
+        subprocess.check_call(["make", "-C", ODIR, ])
+    if os.path.exists(REFSRC) and not os.path.exists(os.path.join(ODIR, "_ref", "libref_probe.so")):
+        subprocess.check_call(["make", "-C", ODIR, "ref", ])
+
+
+_build()
+lib = ct.CDLL(os.path.join(ODIR, "liboracle.so"))
+lib.oracle_builtin_rhs.restype = ct.c_void_p
+lib.oracle_builtin_rhs.argtypes = [ct.c_char_p]
+_probe_path = os.path.join(ODIR, "_ref", "libref_probe.so")
+_ref_path = os.path.join(ODIR, "_ref", "liblsoda.so")
+ref_probe = ct.CDLL(_probe_path) if os.path.exists(_probe_path) else None
+ref_lib = ct.CDLL(_ref_path) if os.path.exists(_ref_path) else None
+HAVE_REF = ref_probe is not None
+
+
+def _p(a):
+    return a.ctypes.data_as(ct.c_void_p)
+
+
+def builtin_rhs(name):
+    ptr = lib.oracle_builtin_rhs(name.encode())
+    assert ptr, name
+    return ptr
+
+
+def _prep(u0, t_eval, data):
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    te = np.ascontiguousarray(t_eval, dtype=np.float64)
+    data = np.ascontiguousarray(data)
+    us = np.full((len(te), len(u0)), np.nan)
+    return u0, te, data, us
+
+
+def lsoda(fptr, u0, t_eval, data, rtol=1e-3, atol=1e-6, mxstep=10000, exit_on_warning=False):
+    u0, te, data, us = _prep(u0, t_eval, data)
+    ok = ct.c_int(999)
+    st = LsodaStats()
+    lib.oracle_lsoda(ct.c_void_p(fptr), len(u0), _p(u0), _p(data), len(te), _p(te), _p(us),
+                     ct.c_double(rtol), ct.c_double(atol), int(mxstep), ct.byref(ok),
+                     int(exit_on_warning), ct.byref(st))
+    return us, ok.value == 1, st
+
+
+def dop853(fptr, u0, t_eval, data, rtol=1e-3, atol=1e-6, mxstep=10000):
+    u0, te, data, us = _prep(u0, t_eval, data)
+    ok = ct.c_int(999)
+    st = Dop853Stats()
+    lib.oracle_dop853(ct.c_void_p(fptr), len(u0), _p(u0), _p(data), len(te), _p(te), _p(us),
+                      ct.c_double(rtol), ct.c_double(atol), int(mxstep), ct.byref(ok),
+                      ct.byref(st))
+    return us, ok.value == 1, st
+
+
+def ref_lsoda(fptr, u0, t_eval, data, rtol=1e-3, atol=1e-6, mxstep=10000,
+              exit_on_warning=False):
+    """The compiled reference, driven like src/wrapper.cpp drives it, plus counters:
+    [nst, nfe, nje, nswitch, nqu, istate, rows, meth]."""
+    u0, te, data, us = _prep(u0, t_eval, data)
+    ok = ct.c_int(999)
+    st = (ct.c_int * 8)()
+    ref_probe.ref_lsoda_stats(ct.c_void_p(fptr), len(u0), _p(u0), _p(data), len(te), _p(te),
+                              _p(us), ct.c_double(rtol), ct.c_double(atol), int(mxstep),
+                              ct.byref(ok), int(exit_on_warning), st)
+    return us, ok.value == 1, list(st)
+
+
+def ref_lsoda_wrapper(fptr, u0, t_eval, data, rtol=1e-3, atol=1e-6, mxstep=10000,
+                      exit_on_warning=False):
+    """The reference's own extern "C" entry point (src/wrapper.cpp:10)."""
+    u0, te, data, us = _prep(u0, t_eval, data)
+    ok = ct.c_int(999)
+    ref_lib.lsoda_wrapper(ct.c_void_p(fptr), len(u0), _p(u0), _p(data), len(te), _p(te), _p(us),
+                          ct.c_double(rtol), ct.c_double(atol), int(mxstep), ct.byref(ok),
+                          int(exit_on_warning))
+    return us, ok.value == 1
+
+
+def solve_batch(solver, fptr, u0, t_eval, data, rtol, atol, mxstep=10000,
+                exit_on_warning=False, nthreads=0):
+    """solver: 'dop853' | 'lsoda'.  u0 [B,n] or [n]; data [B,p] or [p]."""
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    te = np.ascontiguousarray(t_eval, dtype=np.float64)
+    B = u0.shape[0] if u0.ndim == 2 else data.shape[0]
+    n = u0.shape[-1]
+    us = np.full((B, len(te), n), np.nan)
+    ok = np.zeros(B, dtype=np.int32)
+    cnt = np.zeros((B, 8), dtype=np.int32)
+    lib.oracle_solve_batch.restype = ct.c_int
+    lib.oracle_solve_batch(0 if solver == "dop853" else 1, ct.c_void_p(fptr), ct.c_long(B), n,
+                           _p(u0), ct.c_long(n if u0.ndim == 2 else 0), _p(data),
+                           ct.c_long(data.shape[-1] * 8 if data.ndim == 2 else 0), len(te),
+                           _p(te), _p(us), ct.c_double(rtol), ct.c_double(atol), int(mxstep),
+                           int(exit_on_warning), _p(ok), _p(cnt), int(nthreads))
+    return us, ok == 1, cnt

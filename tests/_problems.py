@@ -1,0 +1,90 @@
+"""Problem definitions shared by the tests: the reference's own examples.
+
+Each problem has the Python right-hand side exactly as the reference writes it
+(so numba produces the same IEEE operations for the CPU cfunc and, through
+numba.cuda, for the device function), the initial state, parameters and output
+grid.  Sources: README.md:26-37, tests/test_numbalsoda.py:5-20,
+benchmark/benchmark_lorenz.py:9-31, benchmark/benchmark_robber.py:8-32,
+tests/test_exit_on_warning.py:12-30 (all under /root/reference)."""
+import numpy as np
+
+
+def lv_rhs(t, u, du, p):
+    du[0] = u[0] - u[0] * u[1]
+    du[1] = u[0] * u[1] - u[1] * p[0]
+
+
+def lorenz_rhs(t, u, du, p):
+    sigma = p[0]
+    rho = p[1]
+    beta = p[2]
+    x = u[0]
+    y = u[1]
+    z = u[2]
+    du[0] = sigma * (y - x)
+    du[1] = x * (rho - z) - y
+    du[2] = x * y - beta * z
+
+
+def robertson_rhs(t, u, du, p):
+    k1 = p[0]
+    k2 = p[1]
+    k3 = p[2]
+    du[0] = -k1 * u[0] + k3 * u[1] * u[2]
+    du[1] = k1 * u[0] - k2 * u[1] ** 2 - k3 * u[1] * u[2]
+    du[2] = k2 * u[1] ** 2
+
+
+def growth_rhs(t, u, du, p):
+    # tests/test_exit_on_warning.py:13-14
+    du[0] = p[0] * u[0] * np.sin(t)
+
+
+PROBLEMS = {
+    # name: (rhs, builtin name in oracle/rhs_builtin.c, u0, data, t_eval, rtol, atol)
+    "lv_test": (lv_rhs, "lotka_volterra", [5.0, 0.8], [1.0], np.linspace(0.0, 10.0, 11), 1e-8, 1e-8),
+    "lv_readme": (lv_rhs, "lotka_volterra", [5.0, 0.8], [1.0], np.linspace(0.0, 50.0, 1000), 1e-3, 1e-6),
+    "robertson": (robertson_rhs, "robertson", [1.0, 0.0, 0.0], [0.04, 3e7, 1e4],
+                  np.linspace(0.0, 1e5, 100), 1e-8, 1e-8),
+    "lorenz": (lorenz_rhs, "lorenz", [1.0, 0.0, 0.0], [10.0, 28.0, 8.0 / 3.0],
+               np.linspace(0.0, 100.0, 1001), 1e-8, 1e-8),
+    "lorenz_short": (lorenz_rhs, "lorenz", [1.0, 0.0, 0.0], [10.0, 28.0, 8.0 / 3.0],
+                     np.linspace(0.0, 10.0, 101), 1e-8, 1e-8),
+}
+
+
+def problem(name):
+    rhs, builtin, u0, data, te, rtol, atol = PROBLEMS[name]
+    return dict(rhs=rhs, builtin=builtin, u0=np.array(u0, dtype=np.float64),
+                data=np.array(data, dtype=np.float64), t_eval=np.asarray(te, dtype=np.float64),
+                rtol=rtol, atol=atol)
+
+
+_cfuncs = {}
+
+
+def cfunc_address(rhs):
+    """numba @cfunc(lsoda_sig) address of a Python RHS (kept alive in a cache)."""
+    import numba as nb
+    from numba import types
+    if rhs not in _cfuncs:
+        sig = types.void(types.double, types.CPointer(types.double),
+                         types.CPointer(types.double), types.CPointer(types.double))
+        _cfuncs[rhs] = nb.cfunc(sig)(rhs)
+    return _cfuncs[rhs].address
+
+
+def lorenz_sweep(B, seed=0):
+    """sigma~U(9,11), rho~U(20,36), beta~U(2,3.33)."""
+    rng = np.random.default_rng(seed)
+    p = np.empty((B, 3))
+    p[:, 0] = rng.uniform(9.0, 11.0, B)
+    p[:, 1] = rng.uniform(20.0, 36.0, B)
+    p[:, 2] = rng.uniform(2.0, 3.33, B)
+    return p
+
+
+def robertson_sweep(B, seed=0):
+    """[0.04, 3e7, 1e4] * 10^U(-0.5, 0.5)."""
+    rng = np.random.default_rng(seed)
+    return np.array([0.04, 3e7, 1e4]) * 10.0 ** rng.uniform(-0.5, 0.5, (B, 3))
