@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the batched-ODE hot path (BASELINE.json metric: trajectories/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--impl reference]
+
+A "step" is one pass of the solver over one ensemble of synthetic inputs:
+  lorenz_dop853   (default; BASELINE.json configs[1], SURVEY.md 8d "C2")
+                  Lorenz n=3 parameter sweep, DOP853, t_eval = linspace(0,100,1001),
+                  rtol = atol = 1e-8, 2^20 trajectories per GPU
+  robertson_lsoda (configs[2], "C3") Robertson n=3, LSODA, t_eval = linspace(0,1e5,100),
+                  rtol = atol = 1e-8, 2^20 trajectories per GPU
+Multi-GPU: one process per GPU (torchrun), the ensemble is sharded by trajectory, no
+data-path collective; `value` = trajectories of all ranks / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs and outputs resident
+in HBM (CUDA events on the launch stream); `e2e` is the same workload through the
+numbalsoda-compatible host API (pinned host buffers, H2D + D2H inside the timed
+region).  `--impl reference` times the reference's CPU implementation of the path on
+the host cores on a bounded sample (oracle/_ref when it compiled -- LSODA --, else the
+oracle port -- DOP853, whose reference is Fortran).
+"""
+import argparse
+import ctypes as ct
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    "lorenz_dop853": dict(solver="dop853", rhs="lorenz", n=3, p=3, u0=[1.0, 0.0, 0.0],
+                          t_eval=(0.0, 100.0, 1001), rtol=1e-8, atol=1e-8, mxstep=10000,
+                          batch=1 << 20, config="BASELINE.json configs[1] (SURVEY 8d C2)"),
+    "robertson_lsoda": dict(solver="lsoda", rhs="robertson", n=3, p=3, u0=[1.0, 0.0, 0.0],
+                            t_eval=(0.0, 1.0e5, 100), rtol=1e-8, atol=1e-8, mxstep=10000,
+                            batch=1 << 20, config="BASELINE.json configs[2] (SURVEY 8d C3)"),
+}
+
+
+def sweep(name, B, seed):
+    import _problems as pr
+    return pr.lorenz_sweep(B, seed) if name == "lorenz" else pr.robertson_sweep(B, seed)
+
+
+# ---------------------------------------------------------------- algorithmic FLOPs
+def dop853_flops(cnt, n, f_rhs, nt):
+    """per attempted step 157n + 37 + 11 F; accepted + F; event step
+    + 153n + 6 + 3 F; per output row 14n + 3; start-up 2 F + 12 n.  cnt = [B,8]."""
+    nstep = cnt[:, 0].astype(np.float64)
+    naccpt = cnt[:, 2].astype(np.float64)
+    nevent = cnt[:, 4].astype(np.float64)
+    rows = cnt[:, 6].astype(np.float64)
+    fl = nstep * (157 * n + 37 + 11 * f_rhs) + naccpt * f_rhs + \
+        nevent * (153 * n + 6 + 3 * f_rhs) + rows * (14 * n + 3) + (2 * f_rhs + 12 * n)
+    return float(fl.sum())
+
+
+def lsoda_flops(cnt, n, f_rhs, nt):
+    """SURVEY.md 8(d), LSODA: counted from nst / nfe / nje with the mean order taken
+    as nqu (upper estimate of the per-step bookkeeping is avoided: only the terms
+    that scale with the counters are included)."""
+    nst = cnt[:, 0].astype(np.float64)
+    nfe = cnt[:, 1].astype(np.float64)
+    nje = cnt[:, 2].astype(np.float64)
+    nq = np.maximum(cnt[:, 4].astype(np.float64), 1.0)
+    rows = cnt[:, 6].astype(np.float64)
+    per_step = 3 * n + (n + 1) + n * nq * (nq + 1) / 2 + n + 2 * n * (nq + 1) + (n + 1) + 25 + \
+        (3 * n + 30) / (nq + 1)
+    per_fe = f_rhs + 2 * n * n + 8 * n + 10
+    per_je = (2 * n * n + 4 * n) + (2 * n * n + n) + n + (2.0 / 3.0) * n ** 3 + 0.5 * n * n
+    fl = nst * per_step + nfe * per_fe + nje * per_je + rows * (n * (3 * nq + 1) + 2)
+    return float(fl.sum())
+
+
+F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6}
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 8:
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        pw = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- peaks
+def measured_peaks():
+    out = {"hbm_gbs": 6650.0, "hbm_source": "fallback (B200_PROFILING.md)"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            out["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"])
+            out["hbm_source"] = "MEASURED_PEAKS.json (of measured)"
+        except Exception:
+            pass
+    return out
+
+
+def fp64_peak():
+    """DFMA-chain microbenchmark (tools/fp64_peak.cu) run now on this GPU; falls back
+    to the value recorded under profiles/."""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    try:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        return float(j["fp64_tflops"]), "tools/fp64_peak DFMA chains, measured in this run", j
+    except Exception:
+        p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+        if os.path.exists(p):
+            j = json.load(open(p))
+            return float(j["fp64_tflops"]), "profiles/fp64_peak.json (earlier run on this pool)", j
+        return 37.2, "nominal 148 SM x 64 lanes x 2 x 1.965 GHz (not measured)", None
+
+
+# ---------------------------------------------------------------- CPU arm
+def cpu_arm(wl, budget_s, seed=0):
+    """The reference's CPU path on the host cores, bounded sample.  Returns
+    (traj_per_s, cores, kind, sample description, seconds)."""
+    import _oracle as orc
+    cores = os.cpu_count() or 1
+    te = np.linspace(*wl["t_eval"][:2], wl["t_eval"][2])
+    u0 = np.array(wl["u0"])
+    f = orc.builtin_rhs(wl["rhs"])
+    use_ref = wl["solver"] == "lsoda" and orc.ref_probe is not None
+
+    def run(P):
+        B = len(P)
+        if use_ref:
+            us = np.empty((B, len(te), wl["n"]))
+            ok = np.zeros(B, dtype=np.int32)
+            orc.ref_probe.ref_lsoda_batch.restype = ct.c_int
+            t0 = time.perf_counter()
+            with open(os.devnull, "w") as dn:
+                fd = os.dup(2)
+                os.dup2(dn.fileno(), 2)  # the reference prints warnings to stderr
+                try:
+                    orc.ref_probe.ref_lsoda_batch(
+                        ct.c_void_p(f), ct.c_long(B), wl["n"], u0.ctypes.data_as(ct.c_void_p),
+                        ct.c_long(0), P.ctypes.data_as(ct.c_void_p), ct.c_long(P.shape[1] * 8),
+                        len(te), te.ctypes.data_as(ct.c_void_p), us.ctypes.data_as(ct.c_void_p),
+                        ct.c_double(wl["rtol"]), ct.c_double(wl["atol"]), wl["mxstep"], 0,
+                        ok.ctypes.data_as(ct.c_void_p), 0)
+                finally:
+                    os.dup2(fd, 2)
+                    os.close(fd)
+            return time.perf_counter() - t0
+        t0 = time.perf_counter()
+        orc.solve_batch(wl["solver"], f, u0, te, P, wl["rtol"], wl["atol"], wl["mxstep"])
+        return time.perf_counter() - t0
+
+    probe = sweep(wl["rhs"], 4 * cores, seed)
+    t = run(probe)
+    per = max(t / len(probe), 1e-7)
+    B = int(min(wl["batch"], max(8 * cores, budget_s / per)))
+    P = sweep(wl["rhs"], B, seed)
+    t = run(P)
+    kind = "reference" if use_ref else "port"
+    what = ("oracle/_ref (unmodified reference LSODA.cpp + wrapper.cpp, g++ -O3)" if use_ref else
+            "oracle port (C restatement; the reference's DOP853 is Fortran, no compiler here)")
+    sample = "%d trajectories of the same sweep (seed %d), %s, %d threads" % (B, seed, what, cores)
+    return B / t, cores, kind, sample, t
+
+
+# ---------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lorenz_dop853", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="trajectories per GPU (default 2^20)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strict", action="store_true", help="FMA contraction off (parity mode)")
+    a = ap.parse_args()
+    wl = dict(WORKLOADS[a.workload])
+    if a.batch:
+        wl["batch"] = a.batch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"workload": "%s: %s n=%d sweep, %s, t_eval=linspace(%g,%g,%d), rtol=atol=%g, "
+                       "%d trajectories per GPU" % (a.workload, wl["rhs"], wl["n"], wl["solver"],
+                                                    *wl["t_eval"], wl["rtol"], wl["batch"]),
+           "reference_config": wl["config"], "trajectories_per_gpu": wl["batch"],
+           "sharding": "by trajectory, no collective",
+           "l2": "outputs (%.1f GB per step) exceed L2; inputs re-read per step are %d MB; "
+                 "a 256 MB buffer is rewritten between timed steps to flush L2"
+                 % (wl["batch"] * wl["t_eval"][2] * wl["n"] * 8 / 1e9,
+                    wl["batch"] * wl["p"] * 8 >> 20)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for _ in range(a.warmup):
+            cpu_arm(wl, 1.0)
+        info = None
+        for _ in range(max(a.steps, 1)):
+            info = cpu_arm(wl, 8.0)
+            vals.append(info)
+        B_s = sum(float(v[0]) * v[4] for v in vals)
+        T_s = sum(v[4] for v in vals)
+        v = B_s / T_s
+        line = {"impl": "reference", "metric": "trajectories/s", "value": v, "unit": "traj/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * T_s / max(a.steps, 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg,
+                "cpu_baseline": {"value": v, "unit": "traj/s", "cores": info[1], "kind": info[2],
+                                 "sample": info[3]},
+                "e2e": {"value": v, "unit": "traj/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import numbalsoda_b200 as nb
+    from numbalsoda_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, n, nt = wl["batch"], wl["n"], wl["t_eval"][2]
+    solver = _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
+    h = nb.get_handle(nb.builtin(wl["rhs"]), solver, n, strict=a.strict)
+    Ph = sweep(wl["rhs"], B, seed=rank)  # every rank integrates its own shard of the sweep
+    teh = np.linspace(*wl["t_eval"][:2], nt)
+    P = torch.tensor(Ph, device=dev)
+    u0 = torch.tensor(wl["u0"], dtype=torch.float64, device=dev)
+    te = torch.tensor(teh, device=dev)
+    usol = torch.empty((B, nt, n), dtype=torch.float64, device=dev)
+    ok = torch.zeros(B, dtype=torch.int32, device=dev)
+    cnt = torch.zeros((B, 8), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        args = [h.ptr, B, n, u0.data_ptr(), 0, P.data_ptr(), wl["p"] * 8, wl["p"], nt,
+                te.data_ptr(), usol.data_ptr(), wl["rtol"], wl["atol"], wl["mxstep"],
+                ok.data_ptr(), cnt.data_ptr()]
+        if solver == _lib.DOP853:
+            rc = _lib.lib.b200ode_dop853_batched_device(*args, ct.c_void_p(stream.cuda_stream))
+        else:
+            rc = _lib.lib.b200ode_lsoda_batched_device(*args, 0, ct.c_void_p(stream.cuda_stream))
+        _lib.check(rc)
+
+    peak_tf, peak_src, peak_raw = (None, None, None)
+    if rank == 0:
+        peak_tf, peak_src, peak_raw = fp64_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 0)):
+        step()
+        flush.fill_(1)
+    launches0 = h.kernel_info()["launches"]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(a.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(a.steps):
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+        flush.fill_(k & 0xFF)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = h.kernel_info()["launches"] - launches0
+    ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    dev_s = sum(ms) / 1e3
+    if world > 1:
+        t = torch.tensor([dev_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s_max = float(t.item())
+    else:
+        dev_s_max = dev_s
+    n_ok = int((ok == 1).sum().item())
+    value = world * B * a.steps / dev_s_max
+
+    # ---- end to end through the numbalsoda-compatible host API, pinned host buffers
+    e2e = None
+    if not a.no_e2e:
+        Pp = torch.from_numpy(Ph).pin_memory()
+        u0p = torch.tensor(wl["u0"], dtype=torch.float64).pin_memory()
+        tep = torch.from_numpy(teh).pin_memory()
+        usolp = torch.empty((B, nt, n), dtype=torch.float64).pin_memory()
+        okp = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def e2e_step():
+            args = [h.ptr, B, n, u0p.data_ptr(), 0, Pp.data_ptr(), wl["p"] * 8, wl["p"], nt,
+                    tep.data_ptr(), usolp.data_ptr(), wl["rtol"], wl["atol"], wl["mxstep"],
+                    okp.data_ptr(), None]
+            if solver == _lib.DOP853:
+                rc = _lib.lib.b200ode_dop853_batched(*args, local)
+            else:
+                rc = _lib.lib.b200ode_lsoda_batched(*args, 0, local)
+            _lib.check(rc)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(a.steps, 3))
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        te2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([te2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te2e = float(t.item())
+        e2e = {"value": world * B * ke / te2e, "unit": "traj/s",
+               "h2d_bytes_per_step": int(Ph.nbytes + teh.nbytes + 24),
+               "d2h_bytes_per_step": int(B * nt * n * 8 + B * 4),
+               "steps": ke, "ms_per_step": 1e3 * te2e / ke,
+               "api": "b200ode_%s_batched (host pointers, pinned)" % wl["solver"]}
+        del usolp
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cnt_h = cnt.cpu().numpy()
+    flops = (dop853_flops if wl["solver"] == "dop853" else lsoda_flops)(cnt_h, n, F_RHS[wl["rhs"]], nt)
+    per_launch_s = dev_s / a.steps
+    achieved_tf = flops / per_launch_s / 1e12
+    peaks = measured_peaks()
+    out_bytes = B * (nt * n * 8 + (n + wl["p"]) * 8 + 4)
+    roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+            "kernel": "b200ode_%s_kernel" % wl["solver"],
+            "flops_per_launch": flops, "flops_per_trajectory": flops / B,
+            "flop_count": "algorithmic, SURVEY.md 8(d) formulas x per-trajectory counters",
+            "peak_source": peak_src,
+            "hbm": {"achieved_gbs": out_bytes / per_launch_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                    "frac": out_bytes / per_launch_s / 1e9 / peaks["hbm_gbs"],
+                    "bytes_per_launch": out_bytes, "peak_source": peaks["hbm_source"]},
+            "roofline_traj_per_s_per_gpu": min(peak_tf * 1e12 / (flops / B),
+                                               peaks["hbm_gbs"] * 1e9 / (out_bytes / B))
+            if peak_tf else None}
+    line = {"metric": "trajectories/s", "value": value, "unit": "traj/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s_max / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "mode": "strict" if a.strict else "fast (FMA)",
+            "success_fraction": n_ok / B, "wall_s_timed_region": t_wall,
+            "mean_steps_per_trajectory": float(cnt_h[:, 0].mean()),
+            "roofline": roof, "clocks": clocks, "gpu_launches": launches,
+            "kernel_info": h.kernel_info()}
+    if e2e:
+        line["e2e"] = e2e
+    if not a.no_cpu:
+        v, cores, kind, sample, secs = cpu_arm(wl, 12.0)
+        line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": kind,
+                                "sample": sample, "seconds": secs}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

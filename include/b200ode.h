@@ -1,0 +1,133 @@
+/* libb200ode -- C ABI of the B200-native batched ODE integrator.
+ *
+ * This is the drop-in boundary for the reference's two native entry points
+ *
+ *   void lsoda_wrapper (rhs, neq, u0, data, nt, teval, usol, rtol, atol, mxstep,
+ *                       success, exit_on_warning)   src/wrapper.cpp:10-13
+ *   void dop853_wrapper(rhs, neq, u0, data, nt, teval, usol, rtol, atol, mxstep,
+ *                       success)                    src/dop853_c_interface.f90:75-87
+ *
+ * (ctypes prototypes: numbalsoda/driver.py:22-26, numbalsoda/driver_dop853.py:17-21).
+ * The argument meaning, the [nt,neq] row layout of usol, the 1/0 success flag and
+ * the failure semantics of those two functions are kept; two things change because
+ * the solver now runs on the GPU:
+ *
+ *   - `rhs` cannot be an x86 function pointer.  The right-hand side is handed over
+ *     once, as device code (LTO-IR / PTX produced by numba.cuda or nvcc, or the name
+ *     of a built-in problem) and linked into the solver kernels: b200ode_link_rhs()
+ *     returns a handle that takes the place of the function pointer;
+ *   - every array gains a leading ensemble dimension B: u0[B,neq] (or one shared
+ *     u0[neq]), data[B] records (or one shared record), usol[B,nt,neq], success[B].
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return 0 on
+ * success and a negative B200ODE_E* code otherwise; b200ode_last_error() gives the
+ * message of the last failure on the calling thread.
+ */
+#ifndef B200ODE_H
+#define B200ODE_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ODE_VERSION 100
+
+/* solver */
+#define B200ODE_DOP853 0 /* replaces dop853_wrapper, src/dop853_c_interface.f90:75 */
+#define B200ODE_LSODA 1  /* replaces lsoda_wrapper,  src/wrapper.cpp:10 */
+
+/* kind of right-hand-side image passed to b200ode_link_rhs() */
+#define B200ODE_IMG_LTOIR 0   /* NVVM LTO-IR, e.g. numba.cuda.compile(..., output='ltoir') */
+#define B200ODE_IMG_PTX 1     /* PTX text (not inlined: slower, state spills to local memory) */
+#define B200ODE_IMG_FATBIN 2  /* nvcc -gencode arch=compute_100a,code=lto_100a -fatbin */
+#define B200ODE_IMG_BUILTIN 3 /* image = name of a built-in problem: "lorenz", "robertson",
+                                 "lotka_volterra", "brusselator1d" */
+
+/* flags of b200ode_link_rhs() */
+#define B200ODE_STRICT_FP 1u /* no FMA contraction anywhere: arithmetic identical to the
+                                reference's x86-64 build (parity mode).  Default (0) lets
+                                the compiler fuse multiply-adds (throughput mode). */
+
+/* error codes */
+#define B200ODE_EINVAL -1  /* bad argument */
+#define B200ODE_ELINK -2   /* nvJitLink failed (message has the linker log) */
+#define B200ODE_ECUDA -3   /* CUDA driver error */
+#define B200ODE_ENODEV -4  /* no CUDA driver / device: there is NO CPU fallback */
+#define B200ODE_ENOSYS -5  /* unsupported combination (e.g. neq out of range) */
+
+#define B200ODE_NCOUNTERS 8
+/* counters[b*8 + k], optional per-trajectory statistics:
+ *   dop853: nstep, nfcn, naccpt, nrejct, nevent, idid, rows written, 0
+ *           (dop853_module.f90:141-164 `info`; idid as :340-347)
+ *   lsoda : nst, nfe, nje, method switches, nqu, istate, rows written, meth
+ *           (LSODA.h:128; istate as LSODA.cpp:782-976)                         */
+
+typedef struct b200ode_rhs_s* b200ode_rhs_t;
+
+/* The right-hand side  void f(double t, double* u, double* du, void* data)
+ * (numbalsoda/driver.py:8-11, src/LSODA.h:32) must be a device function named
+ * `b200ode_user_rhs` with C linkage taking (double, double*, double*, double*);
+ * a 64-bit dummy return value (what numba's C ABI emits) is allowed.
+ * Links it with the solver kernels for systems of `neq` equations; needs no GPU. */
+int b200ode_link_rhs(int solver, int neq, const void* image, size_t size, int kind,
+                     unsigned flags, b200ode_rhs_t* out);
+void b200ode_rhs_free(b200ode_rhs_t rhs);
+/* The linked sm_100a cubin (for inspection: cuobjdump -sass / -res-usage). */
+int b200ode_rhs_cubin(b200ode_rhs_t rhs, const void** cubin, size_t* size);
+
+/* Batched dop853_wrapper.  Host pointers; copies inputs to `device`, integrates all
+ * B trajectories there and copies usol / success (/ counters) back.
+ *   u0        [B,neq] with u0_stride = neq, or one shared [neq] with u0_stride = 0
+ *   data      data_stride > 0: B records of data_stride bytes, one per trajectory;
+ *             data_stride < 0: one record of -data_stride bytes shared by all;
+ *             data_stride = 0: one shared record of np doubles.
+ *             np = number of leading doubles of a record the RHS may read through
+ *             its `p` argument from registers (<= 16), or -1 to pass the record's
+ *             device address unchanged (any size / layout, e.g. a C struct)
+ *   usol      [B,nt,neq]; rows a failed trajectory did not reach are left untouched,
+ *             as in the reference (np.empty memory there)
+ *   success   [B], 1 or 0 exactly like the reference's *success
+ *   counters  [B,8] or NULL                                                     */
+int b200ode_dop853_batched(b200ode_rhs_t rhs, long long B, int neq, const double* u0,
+                           long long u0_stride, const void* data, long long data_stride,
+                           int np, int nt, const double* teval, double* usol, double rtol,
+                           double atol, int mxstep, int* success, int* counters, int device);
+
+/* Batched lsoda_wrapper; same conventions, plus exit_on_warning (wrapper.cpp:13). */
+int b200ode_lsoda_batched(b200ode_rhs_t rhs, long long B, int neq, const double* u0,
+                          long long u0_stride, const void* data, long long data_stride,
+                          int np, int nt, const double* teval, double* usol, double rtol,
+                          double atol, int mxstep, int* success, int* counters,
+                          int exit_on_warning, int device);
+
+/* Device-resident variants: every pointer is a device pointer on the current
+ * device of the calling thread; `stream` is a CUstream / cudaStream_t (NULL = default
+ * stream).  Asynchronous: returns after enqueueing.  Nothing is copied. */
+int b200ode_dop853_batched_device(b200ode_rhs_t rhs, long long B, int neq, const double* u0,
+                                  long long u0_stride, const void* data,
+                                  long long data_stride, int np, int nt, const double* teval,
+                                  double* usol, double rtol, double atol, int mxstep,
+                                  int* success, int* counters, void* stream);
+int b200ode_lsoda_batched_device(b200ode_rhs_t rhs, long long B, int neq, const double* u0,
+                                 long long u0_stride, const void* data,
+                                 long long data_stride, int np, int nt, const double* teval,
+                                 double* usol, double rtol, double atol, int mxstep,
+                                 int* success, int* counters, int exit_on_warning,
+                                 void* stream);
+
+/* Launch geometry and resource usage of the kernel behind `rhs` on the current
+ * device: info = {registers/thread, local bytes/thread, static smem bytes,
+ * threads/block, blocks/SM, SM count, grid size of the last launch, kernel launches
+ * so far}. */
+int b200ode_kernel_info(b200ode_rhs_t rhs, int info[8]);
+
+int b200ode_device_count(void);
+const char* b200ode_last_error(void);
+int b200ode_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,9 @@
+"""numbalsoda_b200: B200-native batched lsoda / dop853 behind numbalsoda's API
+(reference numbalsoda/__init__.py:1-2)."""
+from .driver import lsoda_sig, lsoda, address_as_void_pointer
+from .driver_dop853 import dop853
+from .rhs import builtin, register, get_handle
+from ._lib import B200OdeError
+
+__all__ = ["lsoda_sig", "lsoda", "dop853", "address_as_void_pointer", "builtin", "register",
+           "get_handle", "B200OdeError"]

@@ -1,0 +1,124 @@
+"""Shared host logic of lsoda() / dop853(): argument normalisation, batching by
+array rank, the call into libb200ode, sharding over the GPUs of one box."""
+import ctypes as ct
+import threading
+
+import numpy as np
+
+from . import _lib, rhs as _rhs
+
+
+def _as_f64(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.float64:
+        # the reference only passes the buffer address (driver.py:37): a non-float64
+        # array is silently reinterpreted there; here it is an error
+        raise TypeError("%s must be float64 (got %s)" % (name, a.dtype))
+    return np.ascontiguousarray(a)
+
+
+def _data_layout(data, B_hint):
+    """-> (buffer, batched, record_bytes, np_staged)"""
+    data = np.ascontiguousarray(data)
+    if data.dtype == np.float64:
+        if data.ndim == 2:
+            p = data.shape[1]
+            return data, True, p * 8, (p if p <= 16 else -1)
+        if data.ndim == 1:
+            p = data.shape[0]
+            return data, False, p * 8, (p if p <= 16 else -1)
+        raise ValueError("data must be [p] or [B,p]")
+    # record arrays (passing_data_to_rhs_function.ipynb): opaque bytes, passed by address
+    if data.ndim == 0:
+        return data.reshape(1), False, data.dtype.itemsize, -1
+    if data.ndim == 1 and B_hint is not None and data.shape[0] == B_hint:
+        return data, True, data.dtype.itemsize, -1
+    return data, False, data.nbytes, -1
+
+
+def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning=False,
+          strict=False, device=None, counters=False):
+    u0 = _as_f64(u0, "u0")
+    t_eval = _as_f64(t_eval, "t_eval")
+    if data is None:
+        data = np.array([0.0], np.float64)
+    if u0.ndim not in (1, 2) or t_eval.ndim != 1:
+        raise ValueError("u0 must be [n] or [B,n]; t_eval must be [nt]")
+    batched_u0 = u0.ndim == 2
+    data_arr = np.asarray(data)
+    B_hint = u0.shape[0] if batched_u0 else (data_arr.shape[0] if data_arr.ndim == 2 else None)
+    dbuf, batched_data, rec, nps = _data_layout(data, B_hint)
+    if batched_u0 and batched_data and dbuf.shape[0] != u0.shape[0]:
+        raise ValueError("u0 has %d trajectories but data has %d" % (u0.shape[0], dbuf.shape[0]))
+    batched = batched_u0 or batched_data
+    B = u0.shape[0] if batched_u0 else (dbuf.shape[0] if batched_data else 1)
+    n = u0.shape[-1]
+    nt = t_eval.shape[0]
+    handle = _rhs.get_handle(funcptr, solver, n, strict=strict)
+    usol = np.empty((B, nt, n), dtype=np.float64)
+    ok = np.full(B, 999, dtype=np.int32)
+    cnt = np.zeros((B, _lib.NCOUNTERS), dtype=np.int32) if counters else None
+
+    devices = _device_list(device)
+
+    def run(dev, b0, b1):
+        nb = b1 - b0
+        if nb <= 0:
+            return
+        u0p = u0[b0:b1] if batched_u0 else u0
+        dp = dbuf[b0:b1] if batched_data else dbuf
+        args = [handle.ptr, nb, n, u0p.ctypes.data, n if batched_u0 else 0, dp.ctypes.data,
+                rec if batched_data else -rec, nps, nt, t_eval.ctypes.data,
+                usol[b0:b1].ctypes.data, float(rtol), float(atol), int(mxstep),
+                ok[b0:b1].ctypes.data, cnt[b0:b1].ctypes.data if counters else None]
+        if solver == _lib.DOP853:
+            rc = _lib.lib.b200ode_dop853_batched(*args, dev)
+        else:
+            rc = _lib.lib.b200ode_lsoda_batched(*args, int(bool(exit_on_warning)), dev)
+        _lib.check(rc)
+
+    if len(devices) == 1 or B < 2 * len(devices):
+        run(devices[0], 0, B)
+    else:
+        # trajectories are independent: contiguous shards, one host thread per GPU,
+        # no inter-GPU communication
+        bounds = shard_bounds(B, len(devices))
+        errs = []
+
+        def work(i):
+            try:
+                run(devices[i], bounds[i], bounds[i + 1])
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(devices))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if errs:
+            raise errs[0]
+    success = ok == 1
+    if not batched:
+        out = (usol[0], bool(success[0]))
+        return out + ((cnt[0],) if counters else ())
+    return (usol, success) + ((cnt,) if counters else ())
+
+
+def shard_bounds(B, parts):
+    """Contiguous, balanced shard boundaries: part i owns [bounds[i], bounds[i+1])."""
+    base, extra = divmod(B, parts)
+    bounds = [0]
+    for i in range(parts):
+        bounds.append(bounds[-1] + base + (1 if i < extra else 0))
+    return bounds
+
+
+def _device_list(device):
+    if device is None:
+        return [0]
+    if device == "all":
+        n = _lib.lib.b200ode_device_count()
+        if n < 1:
+            raise _lib.B200OdeError("no CUDA device: numbalsoda_b200 has no CPU fallback")
+        return list(range(n))
+    if isinstance(device, (list, tuple)):
+        return [int(d) for d in device]
+    return [int(device)]

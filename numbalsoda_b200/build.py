@@ -1,0 +1,104 @@
+"""Build libb200ode.so in-tree (numbalsoda_b200/libb200ode.so).
+
+  1. nvcc compiles every solver kernel for sm_100a to LTO-IR fatbins, one per
+     system size (-DB200_NEQ=n), and the built-in right-hand sides;
+  2. the fatbins are embedded into the shared library (.incbin);
+  3. g++ compiles the host side (CUDA driver API through dlopen, nvJitLink linked
+     statically so that a different libnvJitLink already loaded in the process --
+     torch bundles 12.8 -- cannot be picked up by mistake).
+
+Run:  python -m numbalsoda_b200.build [--force]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libb200ode.so")
+CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+NVCC = os.path.join(CUDA, "bin", "nvcc")
+
+ARCH = ["-gencode", "arch=compute_100a,code=lto_100a"]
+NVCC_FLAGS = ["-O3", "-lineinfo", "-rdc=true", "-fatbin", "-std=c++17"]
+
+SOLVERS = {
+    # name: (source, sizes)
+    "dop853": ("dop853_kernel.cu", list(range(1, 9))),
+    "lsoda": ("lsoda_kernel.cu", list(range(1, 9))),
+}
+BUILTIN_RHS = ["lotka_volterra", "lorenz", "robertson", "brusselator1d"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    images = []
+    for name, (src, sizes) in SOLVERS.items():
+        srcp = os.path.join(CSRC, src)
+        if not os.path.exists(srcp):
+            continue
+        for n in sizes:
+            out = os.path.join(OBJ, "%s_n%d.fatbin" % (name, n))
+            if force or _newer(out, [srcp] + headers):
+                log = _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_NEQ=%d" % n, "-o", out, srcp])
+                if verbose and log.strip():
+                    print(log)
+            images.append(("%s_n%d" % (name, n), out))
+    srcp = os.path.join(CSRC, "rhs_builtin.cu")
+    for r in BUILTIN_RHS:
+        out = os.path.join(OBJ, "rhs_%s.fatbin" % r)
+        if force or _newer(out, [srcp]):
+            _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_RHS_%s" % r.upper(), "-o", out, srcp])
+        images.append(("rhs_" + r, out))
+
+    asm = os.path.join(OBJ, "embedded_images.S")
+    lines = ['    .section .rodata', '']
+    for i, (name, path) in enumerate(images):
+        lines += ['    .balign 16', 'b200img_%d_begin:' % i, '    .incbin "%s"' % path,
+                  'b200img_%d_end:' % i, 'b200img_%d_name:' % i, '    .asciz "%s"' % name, '']
+    lines += ['    .section .data.rel.ro,"aw"', '    .balign 8',
+              '    .globl b200ode_embedded_images', 'b200ode_embedded_images:']
+    for i in range(len(images)):
+        lines += ['    .quad b200img_%d_name' % i, '    .quad b200img_%d_begin' % i,
+                  '    .quad b200img_%d_end' % i]
+    lines += ['    .globl b200ode_embedded_count', '    .balign 4', 'b200ode_embedded_count:',
+              '    .long %d' % len(images), '    .section .note.GNU-stack,"",@progbits', '']
+    new_asm = "\n".join(lines)
+    if not os.path.exists(asm) or open(asm).read() != new_asm:
+        open(asm, "w").write(new_asm)
+
+    cxx = shutil.which("g++") or "g++"
+    deps = [p for _, p in images] + [asm, os.path.join(CSRC, "b200ode.cpp"),
+                                     os.path.join(CSRC, "b200ode_launch.h"),
+                                     os.path.join(os.path.dirname(HERE), "include", "b200ode.h")]
+    if force or _newer(LIB, deps):
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-s", "-Wl,--gc-sections",
+               "-Wall", "-Wextra", "-I" + os.path.join(CUDA, "include"),
+               "-o", LIB, os.path.join(CSRC, "b200ode.cpp"), asm,
+               "-Wl,--exclude-libs,ALL", "-L" + os.path.join(CUDA, "lib64"),
+               "-l:libnvJitLink_static.a", "-l:libnvptxcompiler_static.a", "-ldl", "-lpthread", "-lrt"]
+        log = _run(cmd)
+        if verbose and log.strip():
+            print(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

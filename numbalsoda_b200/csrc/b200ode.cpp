@@ -1,0 +1,548 @@
+// libb200ode.so -- host side of the C ABI declared in include/b200ode.h.
+//
+// What the reference does in-process on the CPU (one LSODA / dop853 object per
+// call, src/wrapper.cpp:15, src/dop853_c_interface.f90:96) happens here on the GPU:
+//   b200ode_link_rhs()        nvJitLink: solver LTO-IR (embedded, built by nvcc for
+//                             sm_100a) + the user's RHS LTO-IR -> one cubin
+//   b200ode_*_batched_device  cuLaunchKernel on caller-owned device buffers
+//   b200ode_*_batched         the same behind host buffers (chunked, copies overlapped)
+// The CUDA driver is loaded with dlopen at first use so that the library itself
+// loads (and links RHS images) on machines without a GPU; there is no CPU solver
+// in here: without a device every solve call fails with B200ODE_ENODEV.
+#include "../../include/b200ode.h"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvJitLink.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b200ode_launch.h"
+
+// ---------------------------------------------------------------- embedded images
+struct B200EmbeddedImage {
+    const char* name;
+    const unsigned char* begin;
+    const unsigned char* end;
+};
+extern "C" const B200EmbeddedImage b200ode_embedded_images[];  // embedded_images.S/.c
+extern "C" const int b200ode_embedded_count;
+
+static const B200EmbeddedImage* find_image(const std::string& name)
+{
+    for (int i = 0; i < b200ode_embedded_count; i++)
+        if (name == b200ode_embedded_images[i].name) return &b200ode_embedded_images[i];
+    return nullptr;
+}
+
+// ---------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+extern "C" const char* b200ode_last_error(void) { return g_err.c_str(); }
+extern "C" int b200ode_version(void) { return B200ODE_VERSION; }
+
+// ---------------------------------------------------------------- CUDA driver (dlopen)
+#define DRV_FUNCS(X)                                                                        \
+    X(cuInit) X(cuDeviceGet) X(cuDeviceGetCount) X(cuDeviceGetAttribute)                    \
+    X(cuDevicePrimaryCtxRetain) X(cuCtxSetCurrent) X(cuCtxGetCurrent) X(cuCtxGetDevice)     \
+    X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuFuncGetAttribute)      \
+    X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuLaunchKernel) X(cuMemAlloc_v2)       \
+    X(cuMemFree_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)      \
+    X(cuStreamCreate) X(cuStreamDestroy_v2) X(cuStreamSynchronize) X(cuStreamWaitEvent)     \
+    X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord) X(cuEventSynchronize)            \
+    X(cuGetErrorString) X(cuMemGetInfo_v2)
+
+struct Driver {
+    void* lib = nullptr;
+    bool ok = false;
+#define X(f) decltype(&::f) f = nullptr;
+    DRV_FUNCS(X)
+#undef X
+};
+static Driver g_drv;
+static std::once_flag g_drv_once;
+
+static void load_driver()
+{
+    g_drv.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_drv.lib) return;
+    bool all = true;
+#define X(f)                                                      \
+    g_drv.f = reinterpret_cast<decltype(&::f)>(dlsym(g_drv.lib, #f)); \
+    if (!g_drv.f) all = false;
+    DRV_FUNCS(X)
+#undef X
+    if (!all) return;
+    if (g_drv.cuInit(0) != CUDA_SUCCESS) return;
+    g_drv.ok = true;
+}
+static bool driver()
+{
+    std::call_once(g_drv_once, load_driver);
+    return g_drv.ok;
+}
+static int cu_fail(CUresult r, const char* what)
+{
+    const char* s = nullptr;
+    if (g_drv.cuGetErrorString) g_drv.cuGetErrorString(r, &s);
+    return fail(B200ODE_ECUDA, "%s: CUDA error %d (%s)", what, (int)r, s ? s : "?");
+}
+#define CU(call)                                        \
+    do {                                                \
+        CUresult r_ = g_drv.call;                       \
+        if (r_ != CUDA_SUCCESS) return cu_fail(r_, #call); \
+    } while (0)
+
+extern "C" int b200ode_device_count(void)
+{
+    if (!driver()) return 0;
+    int n = 0;
+    if (g_drv.cuDeviceGetCount(&n) != CUDA_SUCCESS) return 0;
+    return n;
+}
+
+// ---------------------------------------------------------------- handle
+static const int kThreads = 128;  // matches __launch_bounds__ of the kernels
+static const int kCounterSlots = 64;
+
+struct PerDevice {
+    CUcontext ctx = nullptr;
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;      // parameters staged in registers (np >= 0)
+    CUfunction fn_ptr = nullptr;  // data record passed by address (np < 0)
+    CUdeviceptr next = 0;  // kCounterSlots work-queue heads
+    int regs = 0, local_bytes = 0, smem = 0, blocks_per_sm = 0, sms = 0;
+};
+
+struct b200ode_rhs_s {
+    int solver = 0, neq = 0;
+    unsigned flags = 0;
+    std::vector<char> cubin;
+    std::mutex mu;
+    std::map<int, PerDevice> dev;
+    std::atomic<unsigned> slot{0};
+    std::atomic<int> launches{0};
+    int last_grid = 0;
+};
+
+static const char* kernel_name(int solver)
+{
+    return solver == B200ODE_DOP853 ? "b200ode_dop853_kernel" : "b200ode_lsoda_kernel";
+}
+
+extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t size, int kind,
+                                unsigned flags, b200ode_rhs_t* out)
+{
+    if (!out) return fail(B200ODE_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (solver != B200ODE_DOP853 && solver != B200ODE_LSODA)
+        return fail(B200ODE_EINVAL, "unknown solver %d", solver);
+    if (neq < 1) return fail(B200ODE_EINVAL, "neq = %d", neq);
+    if (!image) return fail(B200ODE_EINVAL, "image is NULL");
+    char name[64];
+    snprintf(name, sizeof name, "%s_n%d", solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq);
+    const B200EmbeddedImage* solver_img = find_image(name);
+    if (!solver_img)
+        return fail(B200ODE_ENOSYS, "no %s kernel was built for neq = %d (image %s missing)",
+                    solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq, name);
+
+    const void* rhs_data = image;
+    size_t rhs_size = size;
+    nvJitLinkInputType rhs_type = NVJITLINK_INPUT_LTOIR;
+    switch (kind) {
+    case B200ODE_IMG_LTOIR: rhs_type = NVJITLINK_INPUT_LTOIR; break;
+    case B200ODE_IMG_PTX: rhs_type = NVJITLINK_INPUT_PTX; break;
+    case B200ODE_IMG_FATBIN: rhs_type = NVJITLINK_INPUT_FATBIN; break;
+    case B200ODE_IMG_BUILTIN: {
+        std::string n = std::string("rhs_") + static_cast<const char*>(image);
+        const B200EmbeddedImage* r = find_image(n);
+        if (!r) return fail(B200ODE_EINVAL, "unknown built-in right-hand side '%s'",
+                            static_cast<const char*>(image));
+        rhs_data = r->begin;
+        rhs_size = (size_t)(r->end - r->begin);
+        rhs_type = NVJITLINK_INPUT_FATBIN;
+        break;
+    }
+    default: return fail(B200ODE_EINVAL, "unknown image kind %d", kind);
+    }
+    if (rhs_size == 0) return fail(B200ODE_EINVAL, "empty right-hand-side image");
+
+    std::vector<const char*> opts = {"-arch=sm_100a", "-lto", "-O3", "-lineinfo"};
+    if (flags & B200ODE_STRICT_FP) opts.push_back("-fma=0");
+    nvJitLinkHandle h;
+    nvJitLinkResult r = nvJitLinkCreate(&h, (uint32_t)opts.size(), opts.data());
+    if (r != NVJITLINK_SUCCESS) return fail(B200ODE_ELINK, "nvJitLinkCreate failed (%d)", (int)r);
+    auto log_and_fail = [&](const char* what, nvJitLinkResult rr) {
+        size_t n = 0;
+        std::string log;
+        if (nvJitLinkGetErrorLogSize(h, &n) == NVJITLINK_SUCCESS && n > 1) {
+            log.resize(n);
+            nvJitLinkGetErrorLog(h, &log[0]);
+        }
+        nvJitLinkDestroy(&h);
+        return fail(B200ODE_ELINK, "%s failed (%d): %s", what, (int)rr, log.c_str());
+    };
+    r = nvJitLinkAddData(h, NVJITLINK_INPUT_FATBIN, solver_img->begin,
+                         (size_t)(solver_img->end - solver_img->begin), name);
+    if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(solver)", r);
+    r = nvJitLinkAddData(h, rhs_type, rhs_data, rhs_size, "b200ode_user_rhs");
+    if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(rhs)", r);
+    r = nvJitLinkComplete(h);
+    if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkComplete", r);
+    size_t n = 0;
+    r = nvJitLinkGetLinkedCubinSize(h, &n);
+    if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkGetLinkedCubinSize", r);
+    b200ode_rhs_s* H = new b200ode_rhs_s;
+    H->solver = solver;
+    H->neq = neq;
+    H->flags = flags;
+    H->cubin.resize(n);
+    r = nvJitLinkGetLinkedCubin(h, H->cubin.data());
+    if (r != NVJITLINK_SUCCESS) {
+        delete H;
+        return log_and_fail("nvJitLinkGetLinkedCubin", r);
+    }
+    nvJitLinkDestroy(&h);
+    *out = H;
+    return 0;
+}
+
+extern "C" void b200ode_rhs_free(b200ode_rhs_t H)
+{
+    if (!H) return;
+    if (g_drv.ok) {
+        for (auto& kv : H->dev) {
+            g_drv.cuCtxSetCurrent(kv.second.ctx);
+            if (kv.second.next) g_drv.cuMemFree_v2(kv.second.next);
+            if (kv.second.mod) g_drv.cuModuleUnload(kv.second.mod);
+        }
+    }
+    delete H;
+}
+
+extern "C" int b200ode_rhs_cubin(b200ode_rhs_t H, const void** cubin, size_t* size)
+{
+    if (!H || !cubin || !size) return fail(B200ODE_EINVAL, "NULL argument");
+    *cubin = H->cubin.data();
+    *size = H->cubin.size();
+    return 0;
+}
+
+// Make `device`'s primary context current on this thread (shared with the CUDA
+// runtime and torch) and load the module there once.
+static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
+{
+    if (!driver())
+        return fail(B200ODE_ENODEV, "CUDA driver (libcuda.so.1) not available: this library has "
+                                    "no CPU fallback");
+    CUdevice dev;
+    if (device < 0) {
+        CUcontext cur = nullptr;
+        CU(cuCtxGetCurrent(&cur));
+        if (!cur) {
+            device = 0;
+        } else {
+            CU(cuCtxGetDevice(&dev));
+            device = (int)dev;
+        }
+    }
+    std::lock_guard<std::mutex> lk(H->mu);
+    PerDevice& P = H->dev[device];
+    if (!P.ctx) {
+        CU(cuDeviceGet(&dev, device));
+        CU(cuDevicePrimaryCtxRetain(&P.ctx, dev));
+    }
+    CU(cuCtxSetCurrent(P.ctx));
+    if (!P.mod) {
+        CU(cuDeviceGet(&dev, device));
+        CU(cuModuleLoadData(&P.mod, H->cubin.data()));
+        CU(cuModuleGetFunction(&P.fn, P.mod, kernel_name(H->solver)));
+        CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
+                               (std::string(kernel_name(H->solver)) + "_ptr").c_str()));
+        CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
+        CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
+        CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, kThreads, 0));
+        CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+        CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
+        if (P.blocks_per_sm < 1) P.blocks_per_sm = 1;
+    }
+    *out = &P;
+    return 0;
+}
+
+static int check_args(b200ode_rhs_t H, int solver, long long B, int neq, const void* u0,
+                      const void* data, int np, int nt, const void* teval, const void* usol,
+                      const void* success)
+{
+    if (!H) return fail(B200ODE_EINVAL, "rhs handle is NULL");
+    if (H->solver != solver)
+        return fail(B200ODE_EINVAL, "rhs handle was linked for the other solver");
+    if (neq != H->neq)
+        return fail(B200ODE_EINVAL, "neq = %d but the handle was linked for neq = %d", neq, H->neq);
+    if (B < 0 || nt < 1) return fail(B200ODE_EINVAL, "B = %lld, nt = %d", B, nt);
+    if (np > B200ODE_NPMAX)
+        return fail(B200ODE_EINVAL, "np = %d exceeds %d; pass np = -1 to hand the record's "
+                                    "address to the right-hand side instead", np, B200ODE_NPMAX);
+    if (B > 0 && (!u0 || !teval || !usol || !success || (!data && np != 0)))
+        return fail(B200ODE_EINVAL, "NULL array argument");
+    return 0;
+}
+
+// Enqueue one ensemble on `stream`; all pointers are device pointers.
+static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, CUstream stream)
+{
+    if (args_in.B == 0) return 0;
+    B200OdeLaunch args = args_in;
+    unsigned slot = H->slot.fetch_add(1) % kCounterSlots;
+    CUdeviceptr next = P->next + slot * sizeof(unsigned long long);
+    CU(cuMemsetD8Async(next, 0, sizeof(unsigned long long), stream));
+    args.next = reinterpret_cast<unsigned long long*>(next);
+    long long want = (args.B + kThreads - 1) / kThreads;
+    long long resident = (long long)P->sms * P->blocks_per_sm;
+    int grid = (int)std::min(want, resident);
+    void* params[] = {&args};
+    CU(cuLaunchKernel(args.np >= 0 ? P->fn : P->fn_ptr, grid, 1, 1, kThreads, 1, 1, 0, stream, params, nullptr));
+    H->last_grid = grid;
+    H->launches++;
+    return 0;
+}
+
+static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const double* u0,
+                        long long u0_stride, const void* data, long long data_stride, int np,
+                        int nt, const double* teval, double* usol, double rtol, double atol,
+                        int mxstep, int* success, int* counters, int exit_on_warning,
+                        void* stream)
+{
+    int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
+    if (rc) return rc;
+    PerDevice* P;
+    rc = device_state(H, -1, &P);
+    if (rc) return rc;
+    B200OdeLaunch a;
+    memset(&a, 0, sizeof a);
+    a.B = B;
+    a.u0 = u0;
+    a.u0_stride = u0_stride;
+    a.data = static_cast<const char*>(data);
+    a.data_stride = data_stride;
+    a.np = np;
+    a.nt = nt;
+    a.t_eval = teval;
+    a.usol = usol;
+    a.rtol = rtol;
+    a.atol = atol;
+    a.mxstep = mxstep;
+    a.exit_on_warning = exit_on_warning;
+    a.success = success;
+    a.counters = counters;
+    return launch(H, P, a, static_cast<CUstream>(stream));
+}
+
+extern "C" int b200ode_dop853_batched_device(b200ode_rhs_t H, long long B, int neq,
+                                             const double* u0, long long u0_stride,
+                                             const void* data, long long data_stride, int np,
+                                             int nt, const double* teval, double* usol,
+                                             double rtol, double atol, int mxstep,
+                                             int* success, int* counters, void* stream)
+{
+    return solve_device(B200ODE_DOP853, H, B, neq, u0, u0_stride, data, data_stride, np, nt,
+                        teval, usol, rtol, atol, mxstep, success, counters, 0, stream);
+}
+
+extern "C" int b200ode_lsoda_batched_device(b200ode_rhs_t H, long long B, int neq,
+                                            const double* u0, long long u0_stride,
+                                            const void* data, long long data_stride, int np,
+                                            int nt, const double* teval, double* usol,
+                                            double rtol, double atol, int mxstep, int* success,
+                                            int* counters, int exit_on_warning, void* stream)
+{
+    return solve_device(B200ODE_LSODA, H, B, neq, u0, u0_stride, data, data_stride, np, nt,
+                        teval, usol, rtol, atol, mxstep, success, counters, exit_on_warning,
+                        stream);
+}
+
+// ---------------------------------------------------------------- host-buffer path
+namespace {
+struct DevBuf {
+    CUdeviceptr p = 0;
+    ~DevBuf() { if (p && g_drv.ok) g_drv.cuMemFree_v2(p); }
+    int alloc(size_t n) { CU(cuMemAlloc_v2(&p, n ? n : 1)); return 0; }
+};
+struct Stream {
+    CUstream s = nullptr;
+    ~Stream() { if (s && g_drv.ok) g_drv.cuStreamDestroy_v2(s); }
+    int create() { CU(cuStreamCreate(&s, CU_STREAM_NON_BLOCKING)); return 0; }
+};
+struct Event {
+    CUevent e = nullptr;
+    ~Event() { if (e && g_drv.ok) g_drv.cuEventDestroy_v2(e); }
+    int create() { CU(cuEventCreate(&e, CU_EVENT_DISABLE_TIMING)); return 0; }
+};
+}  // namespace
+
+// The ensemble is processed in chunks of trajectories with two output buffers:
+// while chunk c integrates, the rows of chunk c-1 travel back over PCIe.
+static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const double* u0,
+                      long long u0_stride, const void* data, long long data_stride, int np,
+                      int nt, const double* teval, double* usol, double rtol, double atol,
+                      int mxstep, int* success, int* counters, int exit_on_warning, int device)
+{
+    int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
+    if (rc) return rc;
+    if (device < 0) return fail(B200ODE_EINVAL, "device = %d", device);
+    if (B == 0) return 0;
+    // dop853: nmax <= 0 is rejected before any work (dop853_module.f90:243-246)
+    if (solver == B200ODE_DOP853 && mxstep <= 0) {
+        for (long long b = 0; b < B; b++) success[b] = 0;
+        if (counters) {
+            memset(counters, 0, sizeof(int) * B200ODE_NCOUNTERS * (size_t)B);
+            for (long long b = 0; b < B; b++) counters[b * B200ODE_NCOUNTERS + 5] = -1;
+        }
+        return 0;
+    }
+    PerDevice* P;
+    rc = device_state(H, device, &P);
+    if (rc) return rc;
+
+    const size_t row_bytes = sizeof(double) * (size_t)nt * (size_t)neq;
+    size_t free_b = 0, total_b = 0;
+    CU(cuMemGetInfo_v2(&free_b, &total_b));
+    size_t target = std::min<size_t>((size_t)2 << 30, free_b / 4);
+    long long chunk = (long long)std::max<size_t>(1, target / std::max<size_t>(row_bytes, 1));
+    // keep every SM busy within a chunk where the ensemble allows it
+    chunk = std::max<long long>(chunk, std::min<long long>(B, (long long)P->sms * P->blocks_per_sm * kThreads));
+    chunk = std::min(chunk, B);
+    // record size: |data_stride| bytes, or np doubles when data_stride == 0
+    const size_t rec = data_stride != 0 ? (size_t)(data_stride > 0 ? data_stride : -data_stride)
+                                        : (size_t)(np > 0 ? np * 8 : 0);
+
+    Stream sk, sc;
+    if ((rc = sk.create()) || (rc = sc.create())) return rc;
+    DevBuf d_te, d_u0, d_data, d_usol[2], d_ok[2], d_cnt[2];
+    Event ev_kernel[2], ev_copied[2];
+    if ((rc = d_te.alloc(sizeof(double) * nt))) return rc;
+    if ((rc = d_u0.alloc(sizeof(double) * neq * (size_t)(u0_stride ? B : 1)))) return rc;
+    const size_t data_bytes = data ? (data_stride > 0 ? (size_t)data_stride * (size_t)B : rec) : 0;
+    if ((rc = d_data.alloc(data_bytes))) return rc;
+    const int nbuf = chunk < B ? 2 : 1;
+    for (int i = 0; i < nbuf; i++) {
+        if ((rc = d_usol[i].alloc(row_bytes * (size_t)chunk))) return rc;
+        if ((rc = d_ok[i].alloc(sizeof(int) * (size_t)chunk))) return rc;
+        if (counters && (rc = d_cnt[i].alloc(sizeof(int) * B200ODE_NCOUNTERS * (size_t)chunk))) return rc;
+        if ((rc = ev_kernel[i].create()) || (rc = ev_copied[i].create())) return rc;
+    }
+    CU(cuMemcpyHtoDAsync_v2(d_te.p, teval, sizeof(double) * nt, sk.s));
+    if (u0_stride) {
+        // gather rows if the caller's stride is wider than neq
+        if (u0_stride == neq) {
+            CU(cuMemcpyHtoDAsync_v2(d_u0.p, u0, sizeof(double) * neq * (size_t)B, sk.s));
+        } else {
+            for (long long b = 0; b < B; b++)
+                CU(cuMemcpyHtoDAsync_v2(d_u0.p + sizeof(double) * neq * (size_t)b,
+                                        u0 + b * u0_stride, sizeof(double) * neq, sk.s));
+        }
+    } else {
+        CU(cuMemcpyHtoDAsync_v2(d_u0.p, u0, sizeof(double) * neq, sk.s));
+    }
+    if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data.p, data, data_bytes, sk.s));
+
+    long long nchunks = (B + chunk - 1) / chunk;
+    auto copy_back = [&](long long c) -> int {
+        int i = (int)(c % nbuf);
+        long long b0 = c * chunk, nb = std::min(chunk, B - b0);
+        CU(cuStreamWaitEvent(sc.s, ev_kernel[i].e, 0));
+        CU(cuMemcpyDtoHAsync_v2(usol + (size_t)b0 * nt * neq, d_usol[i].p, row_bytes * (size_t)nb, sc.s));
+        CU(cuMemcpyDtoHAsync_v2(success + b0, d_ok[i].p, sizeof(int) * (size_t)nb, sc.s));
+        if (counters)
+            CU(cuMemcpyDtoHAsync_v2(counters + b0 * B200ODE_NCOUNTERS, d_cnt[i].p,
+                                    sizeof(int) * B200ODE_NCOUNTERS * (size_t)nb, sc.s));
+        CU(cuEventRecord(ev_copied[i].e, sc.s));
+        return 0;
+    };
+    for (long long c = 0; c < nchunks; c++) {
+        int i = (int)(c % nbuf);
+        long long b0 = c * chunk, nb = std::min(chunk, B - b0);
+        if (c >= nbuf) CU(cuStreamWaitEvent(sk.s, ev_copied[i].e, 0));
+        B200OdeLaunch a;
+        memset(&a, 0, sizeof a);
+        a.B = nb;
+        a.u0 = reinterpret_cast<const double*>(d_u0.p) + (u0_stride ? (size_t)b0 * neq : 0);
+        a.u0_stride = u0_stride ? neq : 0;
+        a.data = reinterpret_cast<const char*>(d_data.p) + (data_stride > 0 ? (size_t)b0 * data_stride : 0);
+        a.data_stride = data_stride > 0 ? data_stride : 0;
+        a.np = np;
+        a.nt = nt;
+        a.t_eval = reinterpret_cast<const double*>(d_te.p);
+        a.usol = reinterpret_cast<double*>(d_usol[i].p);
+        a.rtol = rtol;
+        a.atol = atol;
+        a.mxstep = mxstep;
+        a.exit_on_warning = exit_on_warning;
+        a.success = reinterpret_cast<int*>(d_ok[i].p);
+        a.counters = counters ? reinterpret_cast<int*>(d_cnt[i].p) : nullptr;
+        if ((rc = launch(H, P, a, sk.s))) return rc;
+        CU(cuEventRecord(ev_kernel[i].e, sk.s));
+        if (c >= 1 && (rc = copy_back(c - 1))) return rc;
+    }
+    if ((rc = copy_back(nchunks - 1))) return rc;
+    CU(cuStreamSynchronize(sc.s));
+    CU(cuStreamSynchronize(sk.s));
+    return 0;
+}
+
+extern "C" int b200ode_dop853_batched(b200ode_rhs_t H, long long B, int neq, const double* u0,
+                                      long long u0_stride, const void* data,
+                                      long long data_stride, int np, int nt,
+                                      const double* teval, double* usol, double rtol,
+                                      double atol, int mxstep, int* success, int* counters,
+                                      int device)
+{
+    return solve_host(B200ODE_DOP853, H, B, neq, u0, u0_stride, data, data_stride, np, nt,
+                      teval, usol, rtol, atol, mxstep, success, counters, 0, device);
+}
+
+extern "C" int b200ode_lsoda_batched(b200ode_rhs_t H, long long B, int neq, const double* u0,
+                                     long long u0_stride, const void* data,
+                                     long long data_stride, int np, int nt, const double* teval,
+                                     double* usol, double rtol, double atol, int mxstep,
+                                     int* success, int* counters, int exit_on_warning,
+                                     int device)
+{
+    return solve_host(B200ODE_LSODA, H, B, neq, u0, u0_stride, data, data_stride, np, nt, teval,
+                      usol, rtol, atol, mxstep, success, counters, exit_on_warning, device);
+}
+
+extern "C" int b200ode_kernel_info(b200ode_rhs_t H, int info[8])
+{
+    if (!H || !info) return fail(B200ODE_EINVAL, "NULL argument");
+    PerDevice* P;
+    int rc = device_state(H, -1, &P);
+    if (rc) return rc;
+    info[0] = P->regs;
+    info[1] = P->local_bytes;
+    info[2] = P->smem;
+    info[3] = kThreads;
+    info[4] = P->blocks_per_sm;
+    info[5] = P->sms;
+    info[6] = H->last_grid;
+    info[7] = H->launches.load();
+    return 0;
+}

@@ -1,0 +1,27 @@
+/* Kernel argument block shared by the host library (b200ode.cpp) and the device
+ * code (b200ode_device.cuh).  Plain C, fixed layout. */
+#ifndef B200ODE_LAUNCH_H
+#define B200ODE_LAUNCH_H
+
+#define B200ODE_NPMAX 16        /* parameters staged into registers per trajectory */
+#define B200ODE_NCOUNTERS_DEV 8 /* ints per trajectory in the counters array */
+
+typedef struct B200OdeLaunch {
+    long long B;              /* trajectories in this launch */
+    const double* u0;         /* [B,n] (u0_stride = n) or [n] shared (u0_stride = 0) */
+    long long u0_stride;      /* in doubles */
+    const char* data;         /* B records of data_stride bytes, or one shared record */
+    long long data_stride;    /* in bytes; 0 = shared */
+    int np;                   /* doubles per record staged in registers; < 0: pass the pointer */
+    int nt;
+    const double* t_eval;     /* [nt] */
+    double* usol;             /* [B,nt,n], the reference's row layout per trajectory */
+    double rtol, atol;
+    int mxstep;
+    int exit_on_warning;      /* lsoda only */
+    int* success;             /* [B] 1 / 0, as the reference's *success */
+    int* counters;            /* [B,8] or null */
+    unsigned long long* next; /* work queue head (zeroed before the launch) */
+} B200OdeLaunch;
+
+#endif

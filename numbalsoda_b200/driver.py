@@ -1,0 +1,41 @@
+"""lsoda(): GPU drop-in for numbalsoda.lsoda (reference numbalsoda/driver.py:28-43).
+
+Same positional arguments and keyword defaults.  With `u0[n]` and `data[p]` it
+returns `(usol[nt,n], success)` like the reference; a 2-D `u0[B,n]` and/or
+`data[B,p]` selects the ensemble path and returns `(usol[B,nt,n], success[B])`.
+"""
+import numpy as np
+
+from . import _lib
+from ._solve import solve
+
+try:
+    from numba import types as _types
+    # reference numbalsoda/driver.py:8-11
+    lsoda_sig = _types.void(_types.double, _types.CPointer(_types.double),
+                            _types.CPointer(_types.double), _types.CPointer(_types.double))
+except Exception:  # numba absent: built-in right-hand sides still work
+    lsoda_sig = None
+
+
+def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, atol=1.0e-6,
+          mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False):
+    """Integrate with the LSODA kernel on the GPU.
+
+    funcptr: address of a numba @cfunc(lsoda_sig) (as in the reference), the cfunc, the
+    Python function, or numbalsoda_b200.builtin(name).
+    Extra keyword-only arguments: strict (FMA contraction off: bit-for-bit the CPU
+    arithmetic), device (index, list of indices or "all"), counters (also return
+    [nst, nfe, nje, nswitch, nqu, istate, rows, meth] per trajectory)."""
+    return solve(_lib.LSODA, funcptr, u0, t_eval, data, rtol, atol, mxstep,
+                 exit_on_warning=exit_on_warning, strict=strict, device=device,
+                 counters=counters)
+
+
+def address_as_void_pointer(addr):
+    """The reference offers this numba intrinsic (driver.py:45-53) to hand a struct
+    with embedded host pointers to the RHS.  Host pointers cannot be dereferenced on
+    the device; pass flat float64 data or a plain record array instead."""
+    raise NotImplementedError(
+        "address_as_void_pointer: data records with embedded host pointers are not "
+        "supported on the GPU; pass float64[p] / float64[B,p] or a numpy record array")

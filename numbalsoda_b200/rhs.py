@@ -1,0 +1,135 @@
+"""Right-hand sides: from the reference's `funcptr` contract to device code.
+
+The reference passes `funcptr = cfunc.address`, the address of x86 machine code
+(README.md:24-33, numbalsoda/driver.py:37).  That code cannot run on the GPU, so
+the same Python function is compiled a second time, by numba.cuda, into LTO-IR
+and linked into the solver kernels (libb200ode: b200ode_link_rhs).  Accepted
+spellings of the right-hand side:
+
+  * the integer address of a numba `@cfunc(lsoda_sig)` (what the reference takes):
+    the CFunc object is found again among the live objects and its Python function
+    recompiled;
+  * the CFunc object itself, or the plain Python function `rhs(t, u, du, p)`;
+  * `builtin("lorenz")` etc.: device code shipped inside libb200ode.
+"""
+import ctypes as ct
+import gc
+import threading
+
+from . import _lib
+
+_lock = threading.Lock()
+_handles = {}     # (key, solver, neq, flags) -> RhsHandle
+_by_address = {}  # cfunc address -> python function
+
+
+class Builtin:
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return "builtin(%r)" % self.name
+
+
+def builtin(name):
+    """A right-hand side compiled into libb200ode (lorenz, robertson, lotka_volterra,
+    brusselator1d)."""
+    return Builtin(name)
+
+
+class RhsHandle:
+    """A linked (solver kernel + right-hand side) module; owns the C handle."""
+
+    def __init__(self, ptr, solver, neq, flags, origin):
+        self.ptr, self.solver, self.neq, self.flags, self.origin = ptr, solver, neq, flags, origin
+
+    def cubin(self):
+        p, n = ct.c_void_p(), ct.c_size_t()
+        _lib.check(_lib.lib.b200ode_rhs_cubin(self.ptr, ct.byref(p), ct.byref(n)))
+        return ct.string_at(p, n.value)
+
+    def kernel_info(self):
+        info = (ct.c_int * 8)()
+        _lib.check(_lib.lib.b200ode_kernel_info(self.ptr, ct.byref(info)))
+        keys = ["registers", "local_bytes", "static_smem", "threads_per_block", "blocks_per_sm",
+                "sm_count", "last_grid", "launches"]
+        return dict(zip(keys, list(info)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib.b200ode_rhs_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def register(cfunc):
+    """Remember the Python function behind a numba CFunc (optional: lookups by
+    address also scan the live objects)."""
+    _by_address[cfunc.address] = cfunc._pyfunc
+    return cfunc
+
+
+def _pyfunc_from_address(addr):
+    if addr in _by_address:
+        return _by_address[addr]
+    from numba.core.ccallback import CFunc
+    for obj in gc.get_objects():
+        if isinstance(obj, CFunc):
+            try:
+                _by_address[obj.address] = obj._pyfunc
+            except Exception:
+                pass
+    if addr in _by_address:
+        return _by_address[addr]
+    raise ValueError(
+        "funcptr %#x is not the address of a live numba @cfunc: the GPU solver needs the "
+        "Python source of the right-hand side to compile it for the device; pass the cfunc "
+        "object or the Python function instead" % addr)
+
+
+def compile_ltoir(pyfunc):
+    """numba.cuda: Python rhs(t, u, du, p) -> LTO-IR of `b200ode_user_rhs`."""
+    from numba import cuda, types
+    sig = (types.double, types.CPointer(types.double), types.CPointer(types.double),
+           types.CPointer(types.double))
+    code, _ = cuda.compile(pyfunc, sig, device=True, abi="c",
+                           abi_info={"abi_name": "b200ode_user_rhs"}, output="ltoir", cc=(9, 0))
+    return bytes(code)
+
+
+def get_handle(rhs, solver, neq, strict=False):
+    """Link (once per right-hand side, solver, size and mode) and return the handle."""
+    flags = _lib.STRICT_FP if strict else 0
+    if isinstance(rhs, RhsHandle):
+        return rhs
+    if isinstance(rhs, Builtin):
+        key, origin = ("builtin", rhs.name), rhs
+    else:
+        if isinstance(rhs, int):
+            rhs = _pyfunc_from_address(rhs)
+        elif hasattr(rhs, "_pyfunc") and hasattr(rhs, "address"):
+            rhs = rhs._pyfunc
+        if not callable(rhs):
+            raise TypeError("right-hand side must be a cfunc address, a cfunc, a Python function "
+                            "or builtin(name); got %r" % (rhs,))
+        key, origin = ("py", rhs), rhs
+    k = (key, solver, neq, flags)
+    with _lock:
+        h = _handles.get(k)
+        if h is not None:
+            return h
+        out = ct.c_void_p()
+        if isinstance(origin, Builtin):
+            name = origin.name.encode()
+            rc = _lib.lib.b200ode_link_rhs(solver, neq, name, len(name), _lib.IMG_BUILTIN, flags,
+                                           ct.byref(out))
+        else:
+            img = compile_ltoir(origin)
+            rc = _lib.lib.b200ode_link_rhs(solver, neq, img, len(img), _lib.IMG_LTOIR, flags,
+                                           ct.byref(out))
+        _lib.check(rc)
+        h = RhsHandle(out, solver, neq, flags, origin)
+        _handles[k] = h
+        return h

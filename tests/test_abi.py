@@ -1,0 +1,102 @@
+"""The C-ABI library loads without a GPU and exports what include/b200ode.h declares;
+linking a right-hand side (nvJitLink, CPU-only work) produces an sm_100a cubin whose
+solver state lives in registers; solving without a device fails loudly."""
+import ctypes as ct
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _problems as pr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200ode.h")).read()
+    return sorted(set(re.findall(r"\b(b200ode_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from numbalsoda_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(_lib.lib, n), n
+    _lib.lib.b200ode_version.restype = ct.c_int
+    assert _lib.lib.b200ode_version() == 100
+
+
+def test_link_errors_are_reported():
+    from numbalsoda_b200 import _lib
+    out = ct.c_void_p()
+    rc = _lib.lib.b200ode_link_rhs(0, 3, b"nope", 4, _lib.IMG_BUILTIN, 0, ct.byref(out))
+    assert rc == -1 and b"unknown built-in" in _lib.lib.b200ode_last_error()
+    rc = _lib.lib.b200ode_link_rhs(0, 4096, b"lorenz", 6, _lib.IMG_BUILTIN, 0, ct.byref(out))
+    assert rc == -5
+    rc = _lib.lib.b200ode_link_rhs(0, 3, b"garbage", 7, _lib.IMG_LTOIR, 0, ct.byref(out))
+    assert rc == -2 and not out.value
+
+
+@pytest.mark.parametrize("solver", ["dop853"])
+@pytest.mark.parametrize("strict", [False, True])
+def test_link_builtin_and_numba_rhs(solver, strict):
+    import numbalsoda_b200 as nb
+    from numbalsoda_b200 import _lib
+    sid = _lib.DOP853 if solver == "dop853" else _lib.LSODA
+    for rhs in (nb.builtin("lorenz"), pr.lorenz_rhs):
+        h = nb.get_handle(rhs, sid, 3, strict=strict)
+        cubin = h.cubin()
+        assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
+        assert nb.get_handle(rhs, sid, 3, strict=strict) is h  # cached
+
+
+def test_linked_kernel_keeps_state_in_registers(tmp_path):
+    """cuobjdump on the linked cubin: no local-memory spills, no stack, the user RHS
+    inlined (no CALL to b200ode_user_rhs survives)."""
+    import numbalsoda_b200 as nb
+    from numbalsoda_b200 import _lib
+    h = nb.get_handle(pr.lorenz_rhs, _lib.DOP853, 3)
+    f = tmp_path / "k.cubin"
+    f.write_bytes(h.cubin())
+    res = subprocess.run(["cuobjdump", "-res-usage", str(f)], capture_output=True, text=True).stdout
+    m = re.search(r"Function b200ode_dop853_kernel:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", res)
+    assert m, res
+    regs, stack, shared, local = map(int, m.groups())
+    assert stack == 0 and local == 0 and regs <= 255
+    sass = subprocess.run(["cuobjdump", "-sass", str(f)], capture_output=True, text=True).stdout
+    assert "b200ode_user_rhs" not in sass
+    assert "DFMA" in sass
+
+
+def test_cfunc_address_is_resolved():
+    import numba
+    import numbalsoda_b200 as nb
+    from numbalsoda_b200 import _lib
+    cf = numba.cfunc(nb.lsoda_sig)(pr.lv_rhs)
+    h = nb.get_handle(cf.address, _lib.DOP853, 2)
+    assert h.origin is pr.lv_rhs
+    with pytest.raises(ValueError):
+        nb.get_handle(0x1234, _lib.DOP853, 2)
+
+
+def test_no_cpu_fallback():
+    import numbalsoda_b200 as nb
+    from numbalsoda_b200 import _lib
+    if _lib.lib.b200ode_device_count() > 0:
+        pytest.skip("a device is present")
+    with pytest.raises(nb.B200OdeError, match="no CPU fallback"):
+        nb.dop853(nb.builtin("lorenz"), np.array([1.0, 0, 0]), np.linspace(0, 1, 5),
+                  np.array([10.0, 28.0, 8 / 3]))
+
+
+def test_shard_bounds():
+    from numbalsoda_b200._solve import shard_bounds
+    for B in (0, 1, 7, 8, 1000, 2 ** 20 + 3):
+        for parts in (1, 2, 3, 8):
+            b = shard_bounds(B, parts)
+            assert b[0] == 0 and b[-1] == B and len(b) == parts + 1
+            sizes = np.diff(b)
+            assert sizes.min() >= 0 and sizes.max() - sizes.min() <= 1

@@ -1,0 +1,183 @@
+"""Parity of the CUDA DOP853 path (through the C ABI / numbalsoda-compatible
+driver) with the CPU oracle on the same inputs.  strict=True links the kernels
+with FMA contraction disabled: the arithmetic is then the reference's, so states
+are compared bit-for-bit and the step counters must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as orc
+import _problems as pr
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "dop853_oracle.npz"))
+CASES = ["lv_test", "lv_readme", "lorenz_short", "lorenz"]
+
+
+def _nb():
+    import numbalsoda_b200 as nb
+    return nb
+
+
+def _cnt(st):
+    return [st.nstep, st.nfcn, st.naccpt, st.nrejct, st.nevent, st.idid, st.rows, 0]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("kind", ["builtin", "numba"])
+def test_single_trajectory_strict_bitwise(name, kind):
+    nb = _nb()
+    p = pr.problem(name)
+    rhs = nb.builtin(p["builtin"]) if kind == "builtin" else p["rhs"]
+    us, ok, cnt = nb.dop853(rhs, p["u0"], p["t_eval"], p["data"], p["rtol"], p["atol"],
+                            strict=True, counters=True)
+    ref, okr, st = orc.dop853(orc.builtin_rhs(p["builtin"]), p["u0"], p["t_eval"], p["data"],
+                              p["rtol"], p["atol"])
+    assert ok == okr
+    assert list(cnt) == _cnt(st)
+    assert np.array_equal(us, ref)
+    assert np.array_equal(us, GOLD[name + "/usol"])
+    assert list(cnt[:7]) == list(GOLD[name + "/counters"])
+
+
+def test_reference_known_answer():
+    # /root/reference/tests/test_numbalsoda.py:22-31, through the drop-in driver
+    nb = _nb()
+    p = pr.problem("lv_test")
+    import numba
+    cf = numba.cfunc(nb.lsoda_sig)(p["rhs"])
+    usol, success = nb.dop853(cf.address, p["u0"], p["t_eval"], p["data"], rtol=1e-8, atol=1e-8)
+    assert success
+    assert usol.shape == (11, 2)
+    assert np.all(np.isclose(usol[-1], np.array([0.38583246250193476, 4.602012234037773])))
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_lorenz_sweep_against_oracle(strict):
+    """Config C2's parameter sweep (short horizon: Lorenz is chaotic)."""
+    nb = _nb()
+    B = 1000
+    P = pr.lorenz_sweep(B)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 5, 51)
+    us, ok, cnt = nb.dop853(nb.builtin("lorenz"), u0, te, P, 1e-8, 1e-8, strict=strict,
+                            counters=True)
+    ref, okr, cr = orc.solve_batch("dop853", orc.builtin_rhs("lorenz"), u0, te, P, 1e-8, 1e-8)
+    assert ok.all() and okr.all() and us.shape == (B, 51, 3)
+    if strict:
+        assert np.array_equal(cnt[:, :7], cr[:, :7])
+        assert np.array_equal(us, ref)
+    else:
+        # fused multiply-adds change the last bits only: north_star's bound is 10*rtol
+        rel = np.abs(us - ref) / (np.abs(ref) + 1e-8 / 1e-8 * 1e-8 + 1.0)
+        assert rel.max() <= 10 * 1e-8
+        assert np.abs(cnt[:, 0].astype(float) - cr[:, 0]).max() <= 3
+
+
+def test_batched_u0_and_shared_data():
+    nb = _nb()
+    rng = np.random.default_rng(5)
+    B = 257
+    u0 = np.array([5.0, 0.8]) * rng.uniform(0.5, 1.5, (B, 2))
+    te = np.linspace(0, 10, 31)
+    d = np.array([1.3])
+    us, ok, cnt = nb.dop853(nb.builtin("lotka_volterra"), u0, te, d, 1e-7, 1e-9, strict=True,
+                            counters=True)
+    ref, okr, cr = orc.solve_batch("dop853", orc.builtin_rhs("lotka_volterra"), u0, te, d,
+                                   1e-7, 1e-9)
+    assert ok.all() and np.array_equal(us, ref) and np.array_equal(cnt[:, :7], cr[:, :7])
+
+
+def test_failures_and_edge_cases():
+    nb = _nb()
+    f = nb.builtin("lotka_volterra")
+    fo = orc.builtin_rhs("lotka_volterra")
+    u0 = np.array([5.0, 0.8])
+    d = np.array([1.0])
+    te = np.linspace(0, 10, 11)
+    # nmax <= 0 (dop853_module.f90:243-246) and nmax exhausted (:539)
+    for mx in (0, -3, 20, 51):
+        us, ok, cnt = nb.dop853(f, u0, te, d, 1e-8, 1e-8, mxstep=mx, strict=True, counters=True)
+        ref, okr, st = orc.dop853(fo, u0, te, d, 1e-8, 1e-8, mxstep=mx)
+        assert ok == okr, mx
+        assert cnt[5] == st.idid and cnt[6] == st.rows
+        assert np.array_equal(us[:st.rows], ref[:st.rows])
+    # a batch in which only some trajectories fail
+    P = np.array([[1.0], [1.0], [1.0]])
+    U = np.array([[5.0, 0.8], [50.0, 8.0], [5.0, 0.8]])
+    us, ok, cnt = nb.dop853(f, U, te, P, 1e-8, 1e-8, mxstep=60, strict=True, counters=True)
+    ref, okr, cr = orc.solve_batch("dop853", fo, U, te, P, 1e-8, 1e-8, mxstep=60)
+    assert list(ok) == list(okr) and not ok.all() and ok.any()
+    for b in range(3):
+        r = cr[b, 6]
+        assert np.array_equal(us[b, :r], ref[b, :r])
+    # nt = 1 -> h = 0 -> idid = -3; decreasing t_eval -> success without rows
+    us, ok, cnt = nb.dop853(f, u0, np.array([0.0]), d, 1e-8, 1e-8, counters=True)
+    assert not ok and cnt[5] == -3
+    us, ok, cnt = nb.dop853(f, u0, np.linspace(10, 0, 5), d, 1e-8, 1e-8, counters=True)
+    assert ok and cnt[6] == 0
+    # rows inside one step and duplicates
+    te2 = np.array([0.0, 1e-4, 1e-4, 2e-4, 1.0])
+    us, ok = nb.dop853(f, u0, te2, d, 1e-8, 1e-8, strict=True)
+    ref, _, _ = orc.dop853(fo, u0, te2, d, 1e-8, 1e-8)
+    assert ok and np.array_equal(us, ref)
+
+
+def test_overflowing_trial_step_recovers():
+    nb = _nb()
+    te = np.linspace(0, 40, 5)
+    d = np.array([0.04, 3e7, 1e4])
+    us, ok, cnt = nb.dop853(nb.builtin("robertson"), np.array([1.0, 0, 0]), te, d, 1e-8, 1e-8,
+                            mxstep=100000, strict=True, counters=True)
+    ref, okr, st = orc.dop853(orc.builtin_rhs("robertson"), np.array([1.0, 0, 0]), te, d, 1e-8,
+                              1e-8, mxstep=100000)
+    assert ok and okr and list(cnt) == _cnt(st) and np.array_equal(us, ref)
+
+
+def test_full_size_properties():
+    """BASELINE config C2 at reduced B but full horizon: every trajectory succeeds,
+    row 0 is u0 exactly, rows are finite, and an ensemble solved in one launch equals
+    the same trajectories solved in two launches (order / lane independence)."""
+    nb = _nb()
+    B = 4096
+    P = pr.lorenz_sweep(B)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 100, 1001)
+    us, ok = nb.dop853(nb.builtin("lorenz"), u0, te, P, 1e-8, 1e-8)
+    assert ok.all() and np.isfinite(us).all()
+    assert np.array_equal(us[:, 0, :], np.broadcast_to(u0, (B, 3)))
+    perm = np.random.default_rng(0).permutation(B)
+    us2, ok2 = nb.dop853(nb.builtin("lorenz"), u0, te, P[perm], 1e-8, 1e-8)
+    assert np.array_equal(us2, us[perm])
+    ref, okr, st = orc.dop853(orc.builtin_rhs("lorenz"), u0, te, P[17], 1e-8, 1e-8)
+    # fast mode on a chaotic system: compare the early part only
+    assert np.abs(us[17, :100] - ref[:100]).max() < 1e-6
+
+
+def test_device_resident_entry_point():
+    """b200ode_dop853_batched_device on torch-owned device memory and stream."""
+    import ctypes as ct
+    import torch
+    nb = _nb()
+    from numbalsoda_b200 import _lib
+    B, nt = 512, 41
+    P = torch.tensor(pr.lorenz_sweep(B), device="cuda")
+    u0 = torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64, device="cuda")
+    te = torch.linspace(0, 4, nt, dtype=torch.float64, device="cuda")
+    usol = torch.empty((B, nt, 3), dtype=torch.float64, device="cuda")
+    ok = torch.zeros(B, dtype=torch.int32, device="cuda")
+    h = nb.get_handle(nb.builtin("lorenz"), _lib.DOP853, 3, strict=True)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        rc = _lib.lib.b200ode_dop853_batched_device(
+            h.ptr, B, 3, u0.data_ptr(), 0, P.data_ptr(), 24, 3, nt, te.data_ptr(),
+            usol.data_ptr(), 1e-8, 1e-8, 10000, ok.data_ptr(), None, ct.c_void_p(s.cuda_stream))
+    _lib.check(rc)
+    s.synchronize()
+    ref, okr, _ = orc.solve_batch("dop853", orc.builtin_rhs("lorenz"), np.array([1.0, 0, 0]),
+                                  te.cpu().numpy(), P.cpu().numpy(), 1e-8, 1e-8)
+    assert bool((ok == 1).all()) and np.array_equal(usol.cpu().numpy(), ref)
+    info = h.kernel_info()
+    assert info["local_bytes"] == 0 and info["launches"] >= 1
