@@ -123,6 +123,12 @@ int b200ode_lsoda_batched_device(b200ode_rhs_t rhs, long long B, int neq, const 
  * so far}. */
 int b200ode_kernel_info(b200ode_rhs_t rhs, int info[8]);
 
+/* Self test: out[i] = device pow(x[i], y) for device arrays of n doubles.  The solvers'
+ * step-size controllers must reproduce the host libm pow bit-for-bit (the reference
+ * calls it at dop853_module.f90:618,:817 and LSODA.cpp:1229,:1983-2113). */
+int b200ode_selftest_pow(const double* x_dev, double y, double* out_dev, long long n,
+                         void* stream);
+
 int b200ode_device_count(void);
 const char* b200ode_last_error(void);
 int b200ode_version(void);

@@ -24,6 +24,24 @@ NVCC = os.path.join(CUDA, "bin", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=lto_100a"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-rdc=true", "-fatbin", "-std=c++17"]
 
+# __launch_bounds__(128, MINBLOCKS): register budget per system size (blocks of 128
+# threads that must fit one SM); chosen so that ptxas does not spill (checked by
+# tests/test_abi.py on the linked cubin).
+MINBLOCKS = {"dop853": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1}}
+THREADS = {"dop853": {n: 128 for n in range(1, 9)}}
+# DOP853 dense-output queue: records per warp (dop853_kernel.cu); 64 = single inlined
+# drain site; sized so that MINBLOCKS blocks fit the 227 KB of shared memory.
+QCAP = {1: 63, 2: 63, 3: 63, 4: 63, 5: 63, 6: 63, 7: 63, 8: 63}
+
+
+def _smem_ok(n, mb, qcap):
+    return mb * 4 * (4 + 11 * n) * qcap * 8 <= 227 * 1024
+
+
+for _n in QCAP:
+    while not _smem_ok(_n, MINBLOCKS["dop853"][_n], QCAP[_n]) and QCAP[_n] > 36:
+        QCAP[_n] -= 4
+
 SOLVERS = {
     # name: (source, sizes)
     "dop853": ("dop853_kernel.cu", list(range(1, 9))),
@@ -56,8 +74,14 @@ def build(force=False, verbose=False):
             continue
         for n in sizes:
             out = os.path.join(OBJ, "%s_n%d.fatbin" % (name, n))
-            if force or _newer(out, [srcp] + headers):
-                log = _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_NEQ=%d" % n, "-o", out, srcp])
+            if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
+                mb = int(os.environ.get("B200ODE_MINBLOCKS", MINBLOCKS.get(name, {}).get(n, 1)))
+                qc = int(os.environ.get("B200ODE_QCAP", QCAP.get(n, 48)))
+                ni = int(os.environ.get("B200ODE_DRAIN_NOINLINE", "0"))
+                th = int(os.environ.get("B200ODE_THREADS", THREADS.get(name, {}).get(n, 128)))
+                log = _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_NEQ=%d" % n, "-DB200_QCAP=%d" % qc,
+                                                          "-DB200_MINBLOCKS=%d" % mb, "-DB200_DRAIN_NOINLINE=%d" % ni, "-DB200_THREADS=%d" % th,
+                                                          "-o", out, srcp])
                 if verbose and log.strip():
                     print(log)
             images.append(("%s_n%d" % (name, n), out))
@@ -67,6 +91,14 @@ def build(force=False, verbose=False):
         if force or _newer(out, [srcp]):
             _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_RHS_%s" % r.upper(), "-o", out, srcp])
         images.append(("rhs_" + r, out))
+
+    # self-test kernels: a plain sm_100a cubin (no LTO link needed)
+    srcp = os.path.join(CSRC, "selftest_kernel.cu")
+    out = os.path.join(OBJ, "selftest.cubin")
+    if force or _newer(out, [srcp] + headers):
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-cubin",
+              "-std=c++17", "-o", out, srcp])
+    images.append(("selftest", out))
 
     asm = os.path.join(OBJ, "embedded_images.S")
     lines = ['    .section .rodata', '']

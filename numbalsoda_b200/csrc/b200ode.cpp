@@ -62,9 +62,9 @@ extern "C" int b200ode_version(void) { return B200ODE_VERSION; }
 #define DRV_FUNCS(X)                                                                        \
     X(cuInit) X(cuDeviceGet) X(cuDeviceGetCount) X(cuDeviceGetAttribute)                    \
     X(cuDevicePrimaryCtxRetain) X(cuCtxSetCurrent) X(cuCtxGetCurrent) X(cuCtxGetDevice)     \
-    X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuFuncGetAttribute)      \
+    X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuFuncGetAttribute) X(cuFuncSetAttribute)      \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuLaunchKernel) X(cuMemAlloc_v2)       \
-    X(cuMemFree_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)      \
+    X(cuMemFree_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)      \
     X(cuStreamCreate) X(cuStreamDestroy_v2) X(cuStreamSynchronize) X(cuStreamWaitEvent)     \
     X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord) X(cuEventSynchronize)            \
     X(cuGetErrorString) X(cuMemGetInfo_v2)
@@ -119,7 +119,6 @@ extern "C" int b200ode_device_count(void)
 }
 
 // ---------------------------------------------------------------- handle
-static const int kThreads = 128;  // matches __launch_bounds__ of the kernels
 static const int kCounterSlots = 64;
 
 struct PerDevice {
@@ -129,6 +128,9 @@ struct PerDevice {
     CUfunction fn_ptr = nullptr;  // data record passed by address (np < 0)
     CUdeviceptr next = 0;  // kCounterSlots work-queue heads
     int regs = 0, local_bytes = 0, smem = 0, blocks_per_sm = 0, sms = 0;
+    int dyn_smem = 0;  // dynamic shared memory per block
+    int qcap = 0;      // dop853: records per warp queue
+    int threads = B200ODE_THREADS;  // threads per block the image was built for
 };
 
 struct b200ode_rhs_s {
@@ -276,12 +278,33 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         CU(cuModuleGetFunction(&P.fn, P.mod, kernel_name(H->solver)));
         CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
                                (std::string(kernel_name(H->solver)) + "_ptr").c_str()));
+        CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
         CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
         CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
         CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
-        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, kThreads, 0));
+        if (H->solver == B200ODE_DOP853) {
+            // ask the image for its queue geometry
+            CUfunction cfg;
+            CU(cuModuleGetFunction(&cfg, P.mod, "b200ode_dop853_config"));
+            int* d_cfg = reinterpret_cast<int*>(P.next);  // scratch: 32 bytes of the slots
+            void* cp[] = {&d_cfg};
+            CU(cuLaunchKernel(cfg, 1, 1, 1, 1, 1, 1, 0, nullptr, cp, nullptr));
+            int cfgv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            CU(cuMemcpyDtoH_v2(cfgv, P.next, sizeof cfgv));
+            if (cfgv[0] < 32 || cfgv[1] != B200ODE_DOP853_QFIELDS(H->neq) || cfgv[3] != H->neq)
+                return fail(B200ODE_ECUDA, "dop853 image reports an inconsistent queue geometry");
+            P.qcap = cfgv[0];
+            P.threads = cfgv[4];
+            if (P.threads < 32 || P.threads > 1024 || P.threads % 32)
+                return fail(B200ODE_ECUDA, "dop853 image reports %d threads per block", P.threads);
+            P.dyn_smem = ((P.threads / 32) * cfgv[1] * cfgv[0] + 4) * (int)sizeof(double);
+        }
+        if (P.dyn_smem > 48 * 1024) {
+            CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));
+            CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));
+        }
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
         CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
-        CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
         if (P.blocks_per_sm < 1) P.blocks_per_sm = 1;
     }
     *out = &P;
@@ -315,11 +338,12 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
     CUdeviceptr next = P->next + slot * sizeof(unsigned long long);
     CU(cuMemsetD8Async(next, 0, sizeof(unsigned long long), stream));
     args.next = reinterpret_cast<unsigned long long*>(next);
+    const int kThreads = P->threads;
     long long want = (args.B + kThreads - 1) / kThreads;
     long long resident = (long long)P->sms * P->blocks_per_sm;
     int grid = (int)std::min(want, resident);
     void* params[] = {&args};
-    CU(cuLaunchKernel(args.np >= 0 ? P->fn : P->fn_ptr, grid, 1, 1, kThreads, 1, 1, 0, stream, params, nullptr));
+    CU(cuLaunchKernel(args.np >= 0 ? P->fn : P->fn_ptr, grid, 1, 1, kThreads, 1, 1, (unsigned)P->dyn_smem, stream, params, nullptr));
     H->last_grid = grid;
     H->launches++;
     return 0;
@@ -428,7 +452,7 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     size_t target = std::min<size_t>((size_t)2 << 30, free_b / 4);
     long long chunk = (long long)std::max<size_t>(1, target / std::max<size_t>(row_bytes, 1));
     // keep every SM busy within a chunk where the ensemble allows it
-    chunk = std::max<long long>(chunk, std::min<long long>(B, (long long)P->sms * P->blocks_per_sm * kThreads));
+    chunk = std::max<long long>(chunk, std::min<long long>(B, (long long)P->sms * P->blocks_per_sm * P->threads));
     chunk = std::min(chunk, B);
     // record size: |data_stride| bytes, or np doubles when data_stride == 0
     const size_t rec = data_stride != 0 ? (size_t)(data_stride > 0 ? data_stride : -data_stride)
@@ -530,6 +554,33 @@ extern "C" int b200ode_lsoda_batched(b200ode_rhs_t H, long long B, int neq, cons
                       usol, rtol, atol, mxstep, success, counters, exit_on_warning, device);
 }
 
+// ---------------------------------------------------------------- self test
+extern "C" int b200ode_selftest_pow(const double* x_dev, double y, double* out_dev, long long n,
+                                    void* stream)
+{
+    if (!driver())
+        return fail(B200ODE_ENODEV, "CUDA driver (libcuda.so.1) not available");
+    const B200EmbeddedImage* img = find_image("selftest");
+    if (!img) return fail(B200ODE_ENOSYS, "selftest image missing");
+    CUcontext cur = nullptr;
+    CU(cuCtxGetCurrent(&cur));
+    if (!cur) {
+        CUdevice dev;
+        CU(cuDeviceGet(&dev, 0));
+        CU(cuDevicePrimaryCtxRetain(&cur, dev));
+        CU(cuCtxSetCurrent(cur));
+    }
+    CUmodule mod;
+    CUfunction fn;
+    CU(cuModuleLoadData(&mod, img->begin));
+    CU(cuModuleGetFunction(&fn, mod, "b200ode_selftest_pow_kernel"));
+    void* params[] = {&x_dev, &y, &out_dev, &n};
+    CU(cuLaunchKernel(fn, 1184, 1, 1, 256, 1, 1, 0, static_cast<CUstream>(stream), params, nullptr));
+    CU(cuStreamSynchronize(static_cast<CUstream>(stream)));
+    CU(cuModuleUnload(mod));
+    return 0;
+}
+
 extern "C" int b200ode_kernel_info(b200ode_rhs_t H, int info[8])
 {
     if (!H || !info) return fail(B200ODE_EINVAL, "NULL argument");
@@ -538,8 +589,8 @@ extern "C" int b200ode_kernel_info(b200ode_rhs_t H, int info[8])
     if (rc) return rc;
     info[0] = P->regs;
     info[1] = P->local_bytes;
-    info[2] = P->smem;
-    info[3] = kThreads;
+    info[2] = P->smem + P->dyn_smem;
+    info[3] = P->threads;
     info[4] = P->blocks_per_sm;
     info[5] = P->sms;
     info[6] = H->last_grid;

@@ -6,6 +6,12 @@
 #define B200ODE_NPMAX 16        /* parameters staged into registers per trajectory */
 #define B200ODE_NCOUNTERS_DEV 8 /* ints per trajectory in the counters array */
 
+/* DOP853 dense-output queue (dop853_kernel.cu): per warp, QCAP records of QFIELDS
+ * doubles in dynamic shared memory.  QCAP is a build-time choice of each kernel image
+ * (the host asks the image: b200ode_dop853_config). */
+#define B200ODE_DOP853_QFIELDS(n) (4 + 11 * (n))
+#define B200ODE_THREADS 128 /* threads per block of every solver kernel */
+
 typedef struct B200OdeLaunch {
     long long B;              /* trajectories in this launch */
     const double* u0;         /* [B,n] (u0_stride = n) or [n] shared (u0_stride = 0) */

@@ -7,15 +7,23 @@
 // link time (strict mode) the results are bit-identical to the CPU path; what is
 // new is the organisation:
 //
-//  * thread-per-trajectory, state (y, k1..k10, y1 = 12n doubles) and the dense
-//    output coefficients (8n) live in registers; the user's right-hand side is
-//    inlined by link-time optimisation (see b200ode_device.cuh);
+//  * thread-per-trajectory: the state (y, k1..k10, y1 = 12n doubles) lives in
+//    registers and the user's right-hand side is inlined by link-time
+//    optimisation (b200ode_device.cuh);
 //  * a persistent grid pulls trajectories from a global work counter: a lane that
-//    finishes its trajectory immediately starts the next one inside the same
-//    step loop, so the adaptive-step imbalance between trajectories costs idle
-//    lanes only at the very end of the launch;
+//    finishes its trajectory starts the next one inside the same step loop, so
+//    the adaptive-step imbalance between trajectories costs idle lanes only at
+//    the very end of the launch;
+//  * dense output is decoupled from stepping.  Only ~1/3 of the accepted steps
+//    contain a t_eval point, but in a warp of 32 trajectories almost every
+//    iteration has *some* lane in that case, so doing the 3 extra stages and the
+//    interpolation in line ran that code on every iteration at ~9 active lanes
+//    (ncu, profiles/r1_dop853_notes.md).  Instead a lane whose step passed output
+//    times pushes the step's stage values (4+11n doubles) into a per-warp queue in
+//    shared memory and goes on stepping; when 32 records are queued the whole
+//    warp pops one record per lane and does the dense-output work fully converged;
 //  * the t_eval rows of a trajectory are consecutive in memory ([B,nt,n] layout of
-//    the reference's usol), so each lane streams its rows sequentially and the
+//    the reference's usol), so rows stream out sequentially per trajectory and the
 //    L2 merges them into full-sector HBM writes.
 #include "b200ode_device.cuh"
 #include "b200ode_pow.cuh"
@@ -29,16 +37,208 @@
 #define DP_FAC1 0.333                    // :56
 #define DP_FAC2 6.0                      // :59
 
+#ifndef B200_QCAP
+#define B200_QCAP 64
+#endif
+#ifndef B200_MINBLOCKS
+#define B200_MINBLOCKS 1
+#endif
+#ifndef B200_THREADS
+#define B200_THREADS 128
+#endif
+#define QCAP B200_QCAP                    // records per warp queue (>= 32)
+#define QF B200ODE_DOP853_QFIELDS(N)      // doubles per record
+#define FULL 0xffffffffu
+// The queue is drained at the top of an iteration as soon as fewer than 32 slots are
+// free (one iteration can push at most 32 records), 32 records at a time.  With
+// QCAP = 63 every drain is a full warp; smaller queues trade drain efficiency
+// (QCAP - 31 .. 32 lanes busy) for shared memory.
+#define QDRAIN_AT (QCAP - 31 < 32 ? QCAP - 31 : 32)
+#ifndef B200_DRAIN_NOINLINE
+#define B200_DRAIN_NOINLINE 0
+#endif
+#if B200_DRAIN_NOINLINE
+#define DRAIN_INLINE __noinline__
+#else
+#define DRAIN_INLINE __forceinline__
+#endif
+
 // gfortran's MAX/MIN ignore a NaN operand, exactly like fmax/fmin (DMNMX).
 __device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b); }
 
-struct Dop853Rhs {
-    double* p;
-    __device__ __forceinline__ void operator()(double t, double* u, double* du) const {
-        b200ode_user_rhs(t, u, du, p);
+// Record layout in the queue, field-major: q[field * QCAP + slot].
+//   0: x (xold)   1: h (hout)   2: trajectory index   3: row range (lo | hi << 32)
+//   4 + v*N + i : vector v, component i; v = 0 y, 1 ynew(k5), 2 k1, 3 f(xph,ynew),
+//                 4..8 k6..k10, 9 k11 (stored in k2), 10 k12 (stored in k3)
+#define QV(v, i) (4 + (v) * N + (i))
+
+// Dense output for `m` queued steps, one per lane: dp86co module :657-705 (the 8n
+// continuous-output coefficients and the three extra stages) followed by solout
+// (c_interface :60-68) with contd8 (module :861-869).
+template <bool STAGED>
+__device__ DRAIN_INLINE void dop853_drain(const char* data, long long data_stride, int np_,
+                                          const double* __restrict__ te, double* usol, int nt,
+                                          const double* q, int qhead, int m)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane >= m) return;
+    int slot = qhead + lane;
+    if (slot >= QCAP) slot -= QCAP;
+    const double* r = q + slot;
+    const double x = r[0 * QCAP], h = r[1 * QCAP];
+    const long long b = __double_as_longlong(r[2 * QCAP]);
+    const unsigned long long rows = (unsigned long long)__double_as_longlong(r[3 * QCAP]);
+    int row = (int)(rows & 0xffffffffu);
+    const int row_end = (int)(rows >> 32);
+    // Parameters of the record's trajectory (the queue holds steps of other lanes).
+    double pl[STAGED ? B200ODE_NPMAX : 1];
+    double* pp;
+    const double* pg = reinterpret_cast<const double*>(data + b * data_stride);
+    if (STAGED) {
+#pragma unroll
+        for (int j = 0; j < B200ODE_NPMAX; j++) pl[j] = (j < np_) ? pg[j] : 0.0;
+        pp = pl;
+    } else {
+        pp = const_cast<double*>(pg);
     }
-};
+    // The stage vectors are consumed one at a time, in the order in which the
+    // reference's sums run over them (k1, k6..k10, k11, k12, then f(xph,ynew)), so
+    // every partial sum below is a prefix of the corresponding source expression:
+    //   c4..c7 : cont(4n..8n) = d_1*k1 + d_6*k6 + ... + d_12*k3          module :668-679
+    //   s14    : a141*k1 + a147*k7 + ... + a1412*k3 + a1413*k4          module :682-683
+    //   s15    : a151*k1 + a156*k6 + ... + a1513*k4 (+ a1514*k14)       module :685-686
+    //   s16    : a161*k1 + a166*k6 + ... + a1613*k4 (+ ...)             module :688-689
+    // and only 13 vectors are live at once instead of 20.
+    double c0[N], c1[N], c2[N], c3[N], c4[N], c5[N], c6[N], c7[N], s14[N], s15[N], s16[N];
+    double kv[N], k4[N], y1[N];
+    FOR_N {
+        c0[i] = r[QV(0, i) * QCAP];                    // y
+        const double ydiff = r[QV(1, i) * QCAP] - c0[i];  // ynew - y
+        c1[i] = ydiff;
+        kv[i] = r[QV(2, i) * QCAP];                    // k1
+        k4[i] = r[QV(3, i) * QCAP];                    // f(xph, ynew)
+        const double bspl = h * kv[i] - ydiff;
+        c2[i] = bspl;
+        c3[i] = ydiff - h * k4[i] - bspl;
+        c4[i] = DP_D4_1 * kv[i];
+        c5[i] = DP_D5_1 * kv[i];
+        c6[i] = DP_D6_1 * kv[i];
+        c7[i] = DP_D7_1 * kv[i];
+        s14[i] = DP_A14_1 * kv[i];
+        s15[i] = DP_A15_1 * kv[i];
+        s16[i] = DP_A16_1 * kv[i];
+    }
+    FOR_N {
+        kv[i] = r[QV(4, i) * QCAP];  // k6
+        c4[i] = c4[i] + DP_D4_6 * kv[i];
+        c5[i] = c5[i] + DP_D5_6 * kv[i];
+        c6[i] = c6[i] + DP_D6_6 * kv[i];
+        c7[i] = c7[i] + DP_D7_6 * kv[i];
+        s15[i] = s15[i] + DP_A15_6 * kv[i];
+        s16[i] = s16[i] + DP_A16_6 * kv[i];
+    }
+    FOR_N {
+        kv[i] = r[QV(5, i) * QCAP];  // k7
+        c4[i] = c4[i] + DP_D4_7 * kv[i];
+        c5[i] = c5[i] + DP_D5_7 * kv[i];
+        c6[i] = c6[i] + DP_D6_7 * kv[i];
+        c7[i] = c7[i] + DP_D7_7 * kv[i];
+        s14[i] = s14[i] + DP_A14_7 * kv[i];
+        s15[i] = s15[i] + DP_A15_7 * kv[i];
+        s16[i] = s16[i] + DP_A16_7 * kv[i];
+    }
+    FOR_N {
+        kv[i] = r[QV(6, i) * QCAP];  // k8
+        c4[i] = c4[i] + DP_D4_8 * kv[i];
+        c5[i] = c5[i] + DP_D5_8 * kv[i];
+        c6[i] = c6[i] + DP_D6_8 * kv[i];
+        c7[i] = c7[i] + DP_D7_8 * kv[i];
+        s14[i] = s14[i] + DP_A14_8 * kv[i];
+        s15[i] = s15[i] + DP_A15_8 * kv[i];
+        s16[i] = s16[i] + DP_A16_8 * kv[i];
+    }
+    FOR_N {
+        kv[i] = r[QV(7, i) * QCAP];  // k9
+        c4[i] = c4[i] + DP_D4_9 * kv[i];
+        c5[i] = c5[i] + DP_D5_9 * kv[i];
+        c6[i] = c6[i] + DP_D6_9 * kv[i];
+        c7[i] = c7[i] + DP_D7_9 * kv[i];
+        s14[i] = s14[i] + DP_A14_9 * kv[i];
+        s16[i] = s16[i] + DP_A16_9 * kv[i];
+    }
+    FOR_N {
+        kv[i] = r[QV(8, i) * QCAP];  // k10
+        c4[i] = c4[i] + DP_D4_10 * kv[i];
+        c5[i] = c5[i] + DP_D5_10 * kv[i];
+        c6[i] = c6[i] + DP_D6_10 * kv[i];
+        c7[i] = c7[i] + DP_D7_10 * kv[i];
+        s14[i] = s14[i] + DP_A14_10 * kv[i];
+    }
+    FOR_N {
+        kv[i] = r[QV(9, i) * QCAP];  // k11
+        c4[i] = c4[i] + DP_D4_11 * kv[i];
+        c5[i] = c5[i] + DP_D5_11 * kv[i];
+        c6[i] = c6[i] + DP_D6_11 * kv[i];
+        c7[i] = c7[i] + DP_D7_11 * kv[i];
+        s14[i] = s14[i] + DP_A14_11 * kv[i];
+        s15[i] = s15[i] + DP_A15_11 * kv[i];
+    }
+    FOR_N {
+        kv[i] = r[QV(10, i) * QCAP];  // k12
+        c4[i] = c4[i] + DP_D4_12 * kv[i];
+        c5[i] = c5[i] + DP_D5_12 * kv[i];
+        c6[i] = c6[i] + DP_D6_12 * kv[i];
+        c7[i] = c7[i] + DP_D7_12 * kv[i];
+        s14[i] = s14[i] + DP_A14_12 * kv[i];
+        s15[i] = s15[i] + DP_A15_12 * kv[i];
+    }
+    // the next three function evaluations, module :682-691, and the final
+    // preparation, module :693-703: cont = h*(cont + d_13*k4 + d_14*k14 + d_15*k15 + d_16*k16)
+    FOR_N {
+        y1[i] = c0[i] + h * (s14[i] + DP_A14_13 * k4[i]);
+        s15[i] = s15[i] + DP_A15_13 * k4[i];
+        s16[i] = s16[i] + DP_A16_13 * k4[i];
+        c4[i] = c4[i] + DP_D4_13 * k4[i];
+        c5[i] = c5[i] + DP_D5_13 * k4[i];
+        c6[i] = c6[i] + DP_D6_13 * k4[i];
+        c7[i] = c7[i] + DP_D7_13 * k4[i];
+    }
+    b200ode_user_rhs(x + DP_C14 * h, y1, kv, pp);  // k14
+    FOR_N {
+        y1[i] = c0[i] + h * (s15[i] + DP_A15_14 * kv[i]);
+        s16[i] = s16[i] + DP_A16_14 * kv[i];
+        c4[i] = c4[i] + DP_D4_14 * kv[i];
+        c5[i] = c5[i] + DP_D5_14 * kv[i];
+        c6[i] = c6[i] + DP_D6_14 * kv[i];
+        c7[i] = c7[i] + DP_D7_14 * kv[i];
+    }
+    b200ode_user_rhs(x + DP_C15 * h, y1, kv, pp);  // k15
+    FOR_N {
+        y1[i] = c0[i] + h * (s16[i] + DP_A16_15 * kv[i]);
+        c4[i] = c4[i] + DP_D4_15 * kv[i];
+        c5[i] = c5[i] + DP_D5_15 * kv[i];
+        c6[i] = c6[i] + DP_D6_15 * kv[i];
+        c7[i] = c7[i] + DP_D7_15 * kv[i];
+    }
+    b200ode_user_rhs(x + DP_C16 * h, y1, kv, pp);  // k16
+    FOR_N {
+        c4[i] = h * (c4[i] + DP_D4_16 * kv[i]);
+        c5[i] = h * (c5[i] + DP_D5_16 * kv[i]);
+        c6[i] = h * (c6[i] + DP_D6_16 * kv[i]);
+        c7[i] = h * (c7[i] + DP_D7_16 * kv[i]);
+    }
+    // solout rows [row, row_end): xold = x, hout = h
+    double* out = usol + ((size_t)b * (size_t)nt + (size_t)row) * N;
+    for (; row < row_end; row++, out += N) {
+        const double s = (te[row] - x) / h;
+        const double s1 = 1.0 - s;
+        FOR_N {
+            double conpar = c4[i] + s * (c5[i] + s1 * (c6[i] + s * c7[i]));
+            out[i] = c0[i] + s * (c1[i] + s1 * (c2[i] + s * (c3[i] + s1 * conpar)));
+        }
+    }
+}
 
 // STAGED: the first L.np doubles of the trajectory's data record are copied into
 // registers once and the right-hand side reads them there; otherwise it receives
@@ -46,276 +246,314 @@ struct Dop853Rhs {
 template <bool STAGED>
 __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
 {
+    extern __shared__ double b200_smem[];
+    const int lane = threadIdx.x & 31;
+    double* q = b200_smem + (size_t)(threadIdx.x >> 5) * (QF * QCAP);
+    int qhead = 0, qcount = 0;  // warp-uniform
+    // t_eval is shared by the whole ensemble, so the integration span is the same for
+    // every trajectory: dop853_wrapper's t = teval(1), tout = teval(nt) (c_interface
+    // :122-123), dop853's hmax = xend - x (module :431-432, :519) and dp86co's posneg
+    // (module :507).  Kept in shared memory (4 doubles per block) to save registers.
+    double* span = b200_smem + (size_t)(B200_THREADS / 32) * (QF * QCAP);
+    if (threadIdx.x == 0) {
+        const double x0 = L.t_eval[0], xe = L.t_eval[L.nt - 1];
+        span[0] = x0;
+        span[1] = xe;
+        span[2] = fabs(xe - x0);
+        span[3] = copysign(1.0, xe - x0);
+    }
+    __syncthreads();
+#define SPAN_X0 span[0]
+#define SPAN_XEND span[1]
+#define SPAN_HMAX span[2]
+#define SPAN_POSNEG span[3]
+
     double y[N], y1[N], k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], k8[N], k9[N], k10[N];
     double pl[STAGED ? B200ODE_NPMAX : 1];
-    Dop853Rhs f;
-    double x = 0.0, xend = 0.0, h = 0.0, hmax = 0.0, posneg = 1.0, xout = 0.0;
-    int nstep = 0, nfcn = 0, naccpt = 0, nrejct = 0, nevent = 0, row = 0;
-    bool last = false, reject = false;
-    long long b = -1;
-    double* out = nullptr;
+    double* pp = pl;
+    double x = 0.0, h = 0.0, xout = 0.0, xout2 = 0.0;
+    int nstep = 0, naccpt = 0, nrejct = 0, nevent = 0, row = 0;
+    // lane state bits (one register instead of three predicates kept across the loop)
+    enum : unsigned { F_LAST = 1u, F_REJECT = 2u, F_EXHAUSTED = 4u };
+    unsigned flags = 0;
+    int b = -1;  // trajectory index of this lane, -1 = idle
 
     const double rtol = L.rtol, atol = L.atol;
-    const double facc1 = 1.0 / DP_FAC1;     // module :505
-    const double facc2 = 1.0 / DP_FAC2;     // module :506
+    const double facc1 = 1.0 / DP_FAC1;  // module :505
+    const double facc2 = 1.0 / DP_FAC2;  // module :506
     const int nt = L.nt;
     const double* __restrict__ te = L.t_eval;
 
     for (;;) {
-        if (b < 0) {
+        if (b < 0 && !(flags & F_EXHAUSTED)) {
             // ---- take the next trajectory: dop853_wrapper (c_interface :98-124),
             //      dop853 (module :396-438), dp86co prologue (module :502-534)
-            b = b200ode_fetch(L.next);
-            if (b >= L.B) break;
-            const double* u0 = L.u0 + b * L.u0_stride;
-            FOR_N y[i] = u0[i];
-            const double* pg = reinterpret_cast<const double*>(L.data + b * L.data_stride);
-            if (STAGED) {
-#pragma unroll
-                for (int j = 0; j < B200ODE_NPMAX; j++) pl[j] = (j < L.np) ? pg[j] : 0.0;
-                f.p = pl;
+            const long long bn = b200ode_fetch(L.next);
+            if (bn >= L.B) {
+                flags |= F_EXHAUSTED;
             } else {
-                f.p = const_cast<double*>(pg);
-            }
-            out = L.usol + (size_t)b * (size_t)nt * N;
-            x = te[0];
-            xend = te[nt - 1];
-            hmax = xend - x;
-            posneg = copysign(1.0, xend - x);
-            last = false;
-            reject = false;
-            nstep = naccpt = nrejct = nevent = 0;
-            f(x, y, k1);
-            hmax = fabs(hmax);
-            {
-                // hinit, module :745-823 (itol = 0, iord = 8)
-                double dnf = 0.0, dny = 0.0;
-                FOR_N {
-                    double sk = atol + rtol * fabs(y[i]);
-                    double q = k1[i] / sk;
-                    dnf = dnf + q * q;
-                    q = y[i] / sk;
-                    dny = dny + q * q;
+                b = (int)bn;
+                const double* u0 = L.u0 + (long long)b * L.u0_stride;
+                FOR_N y[i] = u0[i];
+                const double* pg = reinterpret_cast<const double*>(L.data + (long long)b * L.data_stride);
+                if (STAGED) {
+#pragma unroll
+                    for (int j = 0; j < B200ODE_NPMAX; j++) pl[j] = (j < L.np) ? pg[j] : 0.0;
+                    pp = pl;
+                } else {
+                    pp = const_cast<double*>(pg);
                 }
-                double hh;
-                if (dnf <= 1.0e-10 || dny <= 1.0e-10) hh = 1.0e-6;
-                else hh = sqrt(dny / dnf) * 0.01;
-                hh = fmin_(hh, hmax);
-                hh = copysign(fabs(hh), posneg);
-                FOR_N y1[i] = y[i] + hh * k1[i];
-                f(x + hh, y1, k2);
-                double der2 = 0.0;
-                FOR_N {
-                    double sk = atol + rtol * fabs(y[i]);
-                    double q = (k2[i] - k1[i]) / sk;
-                    der2 = der2 + q * q;
+                x = SPAN_X0;
+                const double hmax = SPAN_HMAX, posneg = SPAN_POSNEG;
+                flags = 0;
+                nstep = naccpt = nrejct = nevent = 0;
+                b200ode_user_rhs(x, y, k1, pp);
+                {
+                    // hinit, module :745-823 (itol = 0, iord = 8)
+                    double dnf = 0.0, dny = 0.0;
+                    FOR_N {
+                        double sk = atol + rtol * fabs(y[i]);
+                        double qq = k1[i] / sk;
+                        dnf = dnf + qq * qq;
+                        qq = y[i] / sk;
+                        dny = dny + qq * qq;
+                    }
+                    double hh;
+                    if (dnf <= 1.0e-10 || dny <= 1.0e-10) hh = 1.0e-6;
+                    else hh = sqrt(dny / dnf) * 0.01;
+                    hh = fmin_(hh, hmax);
+                    hh = copysign(fabs(hh), posneg);
+                    FOR_N y1[i] = y[i] + hh * k1[i];
+                    b200ode_user_rhs(x + hh, y1, k2, pp);
+                    double der2 = 0.0;
+                    FOR_N {
+                        double sk = atol + rtol * fabs(y[i]);
+                        double qq = (k2[i] - k1[i]) / sk;
+                        der2 = der2 + qq * qq;
+                    }
+                    der2 = sqrt(der2) / hh;
+                    double der12 = fmax_(fabs(der2), sqrt(dnf));
+                    double h1;
+                    if (der12 <= 1.0e-15) h1 = fmax_(1.0e-6, fabs(hh) * 1.0e-3);
+                    else h1 = b200ode_pow_eighth(0.01 / der12);
+                    hh = fmin_(fmin_(100.0 * fabs(hh), h1), hmax);
+                    h = copysign(fabs(hh), posneg);
                 }
-                der2 = sqrt(der2) / hh;
-                double der12 = fmax_(fabs(der2), sqrt(dnf));
-                double h1;
-                if (der12 <= 1.0e-15) h1 = fmax_(1.0e-6, fabs(hh) * 1.0e-3);
-                else h1 = b200ode_pow_eighth(0.01 / der12);
-                hh = fmin_(fmin_(100.0 * fabs(hh), h1), hmax);
-                h = copysign(fabs(hh), posneg);
+                xout = te[0];  // first solout call, c_interface :56-58
+                xout2 = nt > 1 ? te[1] : 0.0;  // te[row + 1], loaded one event ahead
+                row = 0;
             }
-            nfcn = 2;
-            xout = te[0];  // first solout call, c_interface :56-58
-            row = 0;
+        }
+
+        // ---- dense output for queued steps, converged across the warp
+        const unsigned active = __ballot_sync(FULL, b >= 0);
+        if (qcount >= QDRAIN_AT || (active == 0 && qcount > 0)) {
+            const int m = qcount < 32 ? qcount : 32;
+            dop853_drain<STAGED>(L.data, L.data_stride, L.np, te, L.usol, nt, q, qhead, m);
+            qhead += m;
+            if (qhead >= QCAP) qhead -= QCAP;
+            qcount -= m;
+            __syncwarp();
+        }
+        if (active == 0) {
+            if (qcount == 0) break;
+            continue;
         }
 
         // ---- one attempted step, dp86co module :537-731
         int idid = 0;
-        if (nstep > L.mxstep) {
-            idid = -2;  // module :539
-        } else if (0.1 * fabs(h) <= fabs(x) * DP_UROUND) {
-            idid = -3;  // module :546
-        } else {
-            if ((x + 1.01 * h - xend) * posneg > 0.0) {  // module :554-557
-                h = xend - x;
-                last = true;
-            }
-            nstep++;
-            // the twelve stages, module :561-587
-            FOR_N y1[i] = y[i] + h * DP_A2_1 * k1[i];
-            f(x + DP_C2 * h, y1, k2);
-            FOR_N y1[i] = y[i] + h * (DP_A3_1 * k1[i] + DP_A3_2 * k2[i]);
-            f(x + DP_C3 * h, y1, k3);
-            FOR_N y1[i] = y[i] + h * (DP_A4_1 * k1[i] + DP_A4_3 * k3[i]);
-            f(x + DP_C4 * h, y1, k4);
-            FOR_N y1[i] = y[i] + h * (DP_A5_1 * k1[i] + DP_A5_3 * k3[i] + DP_A5_4 * k4[i]);
-            f(x + DP_C5 * h, y1, k5);
-            FOR_N y1[i] = y[i] + h * (DP_A6_1 * k1[i] + DP_A6_4 * k4[i] + DP_A6_5 * k5[i]);
-            f(x + DP_C6 * h, y1, k6);
-            FOR_N y1[i] = y[i] + h * (DP_A7_1 * k1[i] + DP_A7_4 * k4[i] + DP_A7_5 * k5[i] +
-                                      DP_A7_6 * k6[i]);
-            f(x + DP_C7 * h, y1, k7);
-            FOR_N y1[i] = y[i] + h * (DP_A8_1 * k1[i] + DP_A8_4 * k4[i] + DP_A8_5 * k5[i] +
-                                      DP_A8_6 * k6[i] + DP_A8_7 * k7[i]);
-            f(x + DP_C8 * h, y1, k8);
-            FOR_N y1[i] = y[i] + h * (DP_A9_1 * k1[i] + DP_A9_4 * k4[i] + DP_A9_5 * k5[i] +
-                                      DP_A9_6 * k6[i] + DP_A9_7 * k7[i] + DP_A9_8 * k8[i]);
-            f(x + DP_C9 * h, y1, k9);
-            FOR_N y1[i] = y[i] + h * (DP_A10_1 * k1[i] + DP_A10_4 * k4[i] + DP_A10_5 * k5[i] +
-                                      DP_A10_6 * k6[i] + DP_A10_7 * k7[i] + DP_A10_8 * k8[i] +
-                                      DP_A10_9 * k9[i]);
-            f(x + DP_C10 * h, y1, k10);
-            FOR_N y1[i] = y[i] + h * (DP_A11_1 * k1[i] + DP_A11_4 * k4[i] + DP_A11_5 * k5[i] +
-                                      DP_A11_6 * k6[i] + DP_A11_7 * k7[i] + DP_A11_8 * k8[i] +
-                                      DP_A11_9 * k9[i] + DP_A11_10 * k10[i]);
-            f(x + DP_C11 * h, y1, k2);
-            const double xph = x + h;
-            FOR_N y1[i] = y[i] + h * (DP_A12_1 * k1[i] + DP_A12_4 * k4[i] + DP_A12_5 * k5[i] +
-                                      DP_A12_6 * k6[i] + DP_A12_7 * k7[i] + DP_A12_8 * k8[i] +
-                                      DP_A12_9 * k9[i] + DP_A12_10 * k10[i] +
-                                      DP_A12_11 * k2[i]);
-            f(xph, y1, k3);
-            nfcn += 11;
-            FOR_N {
-                k4[i] = DP_B1 * k1[i] + DP_B6 * k6[i] + DP_B7 * k7[i] + DP_B8 * k8[i] +
-                        DP_B9 * k9[i] + DP_B10 * k10[i] + DP_B11 * k2[i] + DP_B12 * k3[i];
-                k5[i] = y[i] + h * k4[i];
-            }
-            // error estimation, module :591-616
-            double err = 0.0, err2 = 0.0;
-            FOR_N {
-                double sk = atol + rtol * fmax_(fabs(y[i]), fabs(k5[i]));
-                double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
-                double q = erri / sk;
-                err2 = err2 + q * q;
-                erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] +
-                       DP_ER9 * k9[i] + DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
-                q = erri / sk;
-                err = err + q * q;
-            }
-            double deno = err + 0.01 * err2;
-            if (deno <= 0.0) deno = 1.0;
-            err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
-            // step size controller, module :618-623 (facold**beta == 1 for beta = 0)
-            const double fac11 = b200ode_pow_eighth(err);
-            double fac = fac11 / 1.0;
-            fac = fmax_(facc2, fmin_(facc1, fac / DP_SAFE));
-            double hnew = h / fac;
-            if (err <= 1.0) {
-                // ---- accepted, module :625-722
-                // (facold = max(err, 1e-4), module :626, is dead: beta = 0)
-                naccpt++;
-                f(xph, k5, k4);
-                nfcn++;
-                // (the stiffness detector, module :631-655, only prints: iprint /= 0)
-                const bool event = (xout <= xph);  // iout == 3, module :657
-                if (event) {
-                    double c0[N], c1[N], c2[N], c3[N], c4[N], c5[N], c6[N], c7[N];
-                    nevent++;
-                    FOR_N {
-                        c0[i] = y[i];
-                        double ydiff = k5[i] - y[i];
-                        c1[i] = ydiff;
-                        double bspl = h * k1[i] - ydiff;
-                        c2[i] = bspl;
-                        c3[i] = ydiff - h * k4[i] - bspl;
-                        c4[i] = DP_D4_1 * k1[i] + DP_D4_6 * k6[i] + DP_D4_7 * k7[i] +
-                                DP_D4_8 * k8[i] + DP_D4_9 * k9[i] + DP_D4_10 * k10[i] +
-                                DP_D4_11 * k2[i] + DP_D4_12 * k3[i];
-                        c5[i] = DP_D5_1 * k1[i] + DP_D5_6 * k6[i] + DP_D5_7 * k7[i] +
-                                DP_D5_8 * k8[i] + DP_D5_9 * k9[i] + DP_D5_10 * k10[i] +
-                                DP_D5_11 * k2[i] + DP_D5_12 * k3[i];
-                        c6[i] = DP_D6_1 * k1[i] + DP_D6_6 * k6[i] + DP_D6_7 * k7[i] +
-                                DP_D6_8 * k8[i] + DP_D6_9 * k9[i] + DP_D6_10 * k10[i] +
-                                DP_D6_11 * k2[i] + DP_D6_12 * k3[i];
-                        c7[i] = DP_D7_1 * k1[i] + DP_D7_6 * k6[i] + DP_D7_7 * k7[i] +
-                                DP_D7_8 * k8[i] + DP_D7_9 * k9[i] + DP_D7_10 * k10[i] +
-                                DP_D7_11 * k2[i] + DP_D7_12 * k3[i];
-                    }
-                    // the next three function evaluations, module :682-691
-                    FOR_N y1[i] = y[i] + h * (DP_A14_1 * k1[i] + DP_A14_7 * k7[i] +
-                                              DP_A14_8 * k8[i] + DP_A14_9 * k9[i] +
-                                              DP_A14_10 * k10[i] + DP_A14_11 * k2[i] +
-                                              DP_A14_12 * k3[i] + DP_A14_13 * k4[i]);
-                    f(x + DP_C14 * h, y1, k10);
-                    FOR_N y1[i] = y[i] + h * (DP_A15_1 * k1[i] + DP_A15_6 * k6[i] +
-                                              DP_A15_7 * k7[i] + DP_A15_8 * k8[i] +
-                                              DP_A15_11 * k2[i] + DP_A15_12 * k3[i] +
-                                              DP_A15_13 * k4[i] + DP_A15_14 * k10[i]);
-                    f(x + DP_C15 * h, y1, k2);
-                    FOR_N y1[i] = y[i] + h * (DP_A16_1 * k1[i] + DP_A16_6 * k6[i] +
-                                              DP_A16_7 * k7[i] + DP_A16_8 * k8[i] +
-                                              DP_A16_9 * k9[i] + DP_A16_13 * k4[i] +
-                                              DP_A16_14 * k10[i] + DP_A16_15 * k2[i]);
-                    f(x + DP_C16 * h, y1, k3);
-                    nfcn += 3;
-                    FOR_N {
-                        c4[i] = h * (c4[i] + DP_D4_13 * k4[i] + DP_D4_14 * k10[i] +
-                                     DP_D4_15 * k2[i] + DP_D4_16 * k3[i]);
-                        c5[i] = h * (c5[i] + DP_D5_13 * k4[i] + DP_D5_14 * k10[i] +
-                                     DP_D5_15 * k2[i] + DP_D5_16 * k3[i]);
-                        c6[i] = h * (c6[i] + DP_D6_13 * k4[i] + DP_D6_14 * k10[i] +
-                                     DP_D6_15 * k2[i] + DP_D6_16 * k3[i]);
-                        c7[i] = h * (c7[i] + DP_D7_13 * k4[i] + DP_D7_14 * k10[i] +
-                                     DP_D7_15 * k2[i] + DP_D7_16 * k3[i]);
-                    }
-                    // solout (c_interface :60-68) with contd8 (module :861-869):
-                    // xold = x, hout = h, new x = xph
-                    while (row < nt) {
-                        const double tq = te[row];
-                        if (!(tq <= xph)) break;
-                        const double s = (tq - x) / h;
-                        const double s1 = 1.0 - s;
-                        double* o = out + (size_t)row * N;
-                        FOR_N {
-                            double conpar = c4[i] + s * (c5[i] + s1 * (c6[i] + s * c7[i]));
-                            o[i] = c0[i] + s * (c1[i] + s1 * (c2[i] + s * (c3[i] + s1 * conpar)));
-                        }
-                        row++;
-                    }
-                    if (row < nt) xout = te[row];
+        bool accepted = false, push = false;
+        int row_lo = 0;
+        double hnew = 0.0, xph = 0.0;
+        if (b >= 0) {
+            if (nstep > L.mxstep) {
+                idid = -2;  // module :539
+            } else if (0.1 * fabs(h) <= fabs(x) * DP_UROUND) {
+                idid = -3;  // module :546
+            } else {
+                const double xend = SPAN_XEND, posneg = SPAN_POSNEG;
+                if ((x + 1.01 * h - xend) * posneg > 0.0) {  // module :554-557
+                    h = xend - x;
+                    flags |= F_LAST;
                 }
+                nstep++;
+                // the twelve stages, module :561-587
+                FOR_N y1[i] = y[i] + h * DP_A2_1 * k1[i];
+                b200ode_user_rhs(x + DP_C2 * h, y1, k2, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A3_1 * k1[i] + DP_A3_2 * k2[i]);
+                b200ode_user_rhs(x + DP_C3 * h, y1, k3, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A4_1 * k1[i] + DP_A4_3 * k3[i]);
+                b200ode_user_rhs(x + DP_C4 * h, y1, k4, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A5_1 * k1[i] + DP_A5_3 * k3[i] + DP_A5_4 * k4[i]);
+                b200ode_user_rhs(x + DP_C5 * h, y1, k5, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A6_1 * k1[i] + DP_A6_4 * k4[i] + DP_A6_5 * k5[i]);
+                b200ode_user_rhs(x + DP_C6 * h, y1, k6, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A7_1 * k1[i] + DP_A7_4 * k4[i] + DP_A7_5 * k5[i] +
+                                          DP_A7_6 * k6[i]);
+                b200ode_user_rhs(x + DP_C7 * h, y1, k7, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A8_1 * k1[i] + DP_A8_4 * k4[i] + DP_A8_5 * k5[i] +
+                                          DP_A8_6 * k6[i] + DP_A8_7 * k7[i]);
+                b200ode_user_rhs(x + DP_C8 * h, y1, k8, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A9_1 * k1[i] + DP_A9_4 * k4[i] + DP_A9_5 * k5[i] +
+                                          DP_A9_6 * k6[i] + DP_A9_7 * k7[i] + DP_A9_8 * k8[i]);
+                b200ode_user_rhs(x + DP_C9 * h, y1, k9, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A10_1 * k1[i] + DP_A10_4 * k4[i] + DP_A10_5 * k5[i] +
+                                          DP_A10_6 * k6[i] + DP_A10_7 * k7[i] + DP_A10_8 * k8[i] +
+                                          DP_A10_9 * k9[i]);
+                b200ode_user_rhs(x + DP_C10 * h, y1, k10, pp);
+                FOR_N y1[i] = y[i] + h * (DP_A11_1 * k1[i] + DP_A11_4 * k4[i] + DP_A11_5 * k5[i] +
+                                          DP_A11_6 * k6[i] + DP_A11_7 * k7[i] + DP_A11_8 * k8[i] +
+                                          DP_A11_9 * k9[i] + DP_A11_10 * k10[i]);
+                b200ode_user_rhs(x + DP_C11 * h, y1, k2, pp);
+                xph = x + h;
+                FOR_N y1[i] = y[i] + h * (DP_A12_1 * k1[i] + DP_A12_4 * k4[i] + DP_A12_5 * k5[i] +
+                                          DP_A12_6 * k6[i] + DP_A12_7 * k7[i] + DP_A12_8 * k8[i] +
+                                          DP_A12_9 * k9[i] + DP_A12_10 * k10[i] +
+                                          DP_A12_11 * k2[i]);
+                b200ode_user_rhs(xph, y1, k3, pp);
+                FOR_N {
+                    k4[i] = DP_B1 * k1[i] + DP_B6 * k6[i] + DP_B7 * k7[i] + DP_B8 * k8[i] +
+                            DP_B9 * k9[i] + DP_B10 * k10[i] + DP_B11 * k2[i] + DP_B12 * k3[i];
+                    k5[i] = y[i] + h * k4[i];
+                }
+                // error estimation, module :591-616
+                double err = 0.0, err2 = 0.0;
+                FOR_N {
+                    double sk = atol + rtol * fmax_(fabs(y[i]), fabs(k5[i]));
+                    double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
+                    double qq = erri / sk;
+                    err2 = err2 + qq * qq;
+                    erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] +
+                           DP_ER9 * k9[i] + DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
+                    qq = erri / sk;
+                    err = err + qq * qq;
+                }
+                double deno = err + 0.01 * err2;
+                if (deno <= 0.0) deno = 1.0;
+                err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
+                // step size controller, module :618-623 (facold**beta == 1 for beta = 0,
+                // which also makes facold, module :626, dead)
+                const double fac11 = b200ode_pow_eighth(err);
+                double fac = fac11 / 1.0;
+                fac = fmax_(facc2, fmin_(facc1, fac / DP_SAFE));
+                hnew = h / fac;
+                if (err <= 1.0) {
+                    // ---- accepted, module :625-722
+                    accepted = true;
+                    naccpt++;
+                    b200ode_user_rhs(xph, k5, k4, pp);
+                    // (the stiffness detector, module :631-655, only prints: iprint /= 0)
+                    if (xout <= xph) {  // event, iout == 3, module :657
+                        // dense output is prepared for this step: module :658-705 costs
+                        // 3 RHS evaluations; solout writes every row with t_eval <= xph
+                        nevent++;
+                        row_lo = row;
+                        while (row < nt && xout <= xph) {
+                            row++;
+                            if (row < nt) xout = xout2;  // = te[row]; stays put at the end
+                            if (row + 1 < nt) xout2 = te[row + 1];
+                        }
+                        push = row > row_lo;
+                    }
+                    if (flags & F_LAST) {
+                        idid = 1;  // module :715-719
+                    } else {
+                        const double hmax = SPAN_HMAX;
+                        if (fabs(hnew) > hmax) hnew = posneg * hmax;
+                        if (flags & F_REJECT) hnew = posneg * fmin_(fabs(hnew), fabs(h));
+                        flags &= ~F_REJECT;
+                    }
+                } else {
+                    // ---- rejected, module :724-728
+                    hnew = h / fmin_(facc1, fac11 / DP_SAFE);
+                    if (naccpt >= 1) nrejct++;
+                    flags = F_REJECT;  // and last = .false.
+                }
+            }
+        }
+
+        // ---- queue the steps that passed output times
+        const unsigned pm = __ballot_sync(FULL, push);
+        if (pm) {
+            const int np = __popc(pm);
+            if (push) {
+                int slot = qhead + qcount + __popc(pm & ((1u << lane) - 1u));
+                if (slot >= QCAP) slot -= QCAP;
+                double* r = q + slot;
+                r[0 * QCAP] = x;
+                r[1 * QCAP] = h;
+                r[2 * QCAP] = __longlong_as_double((long long)b);
+                r[3 * QCAP] = __longlong_as_double(
+                    (long long)((unsigned long long)(unsigned)row_lo |
+                                ((unsigned long long)(unsigned)row << 32)));
+                FOR_N {
+                    r[QV(0, i) * QCAP] = y[i];
+                    r[QV(1, i) * QCAP] = k5[i];
+                    r[QV(2, i) * QCAP] = k1[i];
+                    r[QV(3, i) * QCAP] = k4[i];
+                    r[QV(4, i) * QCAP] = k6[i];
+                    r[QV(5, i) * QCAP] = k7[i];
+                    r[QV(6, i) * QCAP] = k8[i];
+                    r[QV(7, i) * QCAP] = k9[i];
+                    r[QV(8, i) * QCAP] = k10[i];
+                    r[QV(9, i) * QCAP] = k2[i];
+                    r[QV(10, i) * QCAP] = k3[i];
+                }
+            }
+            qcount += np;
+            __syncwarp();
+        }
+
+        if (b >= 0) {
+            if (accepted) {
                 FOR_N {
                     k1[i] = k4[i];
                     y[i] = k5[i];
                 }
                 x = xph;
-                if (last) {
-                    idid = 1;  // module :715-719
-                } else {
-                    if (fabs(hnew) > hmax) hnew = posneg * hmax;
-                    if (reject) hnew = posneg * fmin_(fabs(hnew), fabs(h));
-                    reject = false;
-                }
+            }
+            if (idid == 0) {
+                h = hnew;
             } else {
-                // ---- rejected, module :724-728
-                hnew = h / fmin_(facc1, fac11 / DP_SAFE);
-                reject = true;
-                if (naccpt >= 1) nrejct++;
-                last = false;
+                // dop853_wrapper epilogue, c_interface :125-128
+                L.success[b] = (idid < 0) ? 0 : 1;
+                if (L.counters) {
+                    int* c = L.counters + (long long)b * B200ODE_NCOUNTERS;
+                    c[0] = nstep;
+                    // nfcn (module :524,:587,:629,:691): 2 at start-up, 11 per attempted step,
+                    // 1 per accepted step, 3 per step that prepared dense output
+                    c[1] = 2 + 11 * nstep + naccpt + 3 * nevent;
+                    c[2] = naccpt;
+                    c[3] = nrejct;
+                    c[4] = nevent;
+                    c[5] = idid;
+                    c[6] = row;
+                    c[7] = 0;
+                }
+                b = -1;
             }
-            h = hnew;
-        }
-
-        if (idid != 0) {
-            // dop853_wrapper epilogue, c_interface :125-128
-            L.success[b] = (idid < 0) ? 0 : 1;
-            if (L.counters) {
-                int* c = L.counters + b * B200ODE_NCOUNTERS;
-                c[0] = nstep;
-                c[1] = nfcn;
-                c[2] = naccpt;
-                c[3] = nrejct;
-                c[4] = nevent;
-                c[5] = idid;
-                c[6] = row;
-                c[7] = 0;
-            }
-            b = -1;
         }
     }
 }
 
-extern "C" __global__ void __launch_bounds__(128) b200ode_dop853_kernel(const B200OdeLaunch L)
+extern "C" __global__ void __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+b200ode_dop853_kernel(const B200OdeLaunch L)
 {
     dop853_ensemble<true>(L);
 }
 
-extern "C" __global__ void __launch_bounds__(128) b200ode_dop853_kernel_ptr(const B200OdeLaunch L)
+extern "C" __global__ void __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+b200ode_dop853_kernel_ptr(const B200OdeLaunch L)
 {
     dop853_ensemble<false>(L);
+}
+
+// Build-time geometry of this image, read once by the host library after loading.
+extern "C" __global__ void b200ode_dop853_config(int* out)
+{
+    out[0] = QCAP;
+    out[1] = QF;
+    out[2] = B200_MINBLOCKS;
+    out[3] = N;
+    out[4] = B200_THREADS;
 }

@@ -14,7 +14,10 @@ REF = "/root/reference/src/dop853_constants.f90"
 def _read(path):
     out = {}
     for line in open(path):
-        m = re.match(r"#define (DP_\w+)\s+(\S+)", line)
+        m = re.match(r"#define (DP_\w+)\s+(\S+)", line) if "b200_dpc[" not in line else None
+        c = re.match(r"\s+(\S+),\s+// (DP_\w+)", line)
+        if c:
+            out[c.group(2)] = float(c.group(1))
         if m:
             out[m.group(1)] = float(m.group(2))
     return out
