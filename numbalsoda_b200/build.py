@@ -31,7 +31,7 @@ MINBLOCKS = {"dop853": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1}}
 THREADS = {"dop853": {n: 128 for n in range(1, 9)}}
 # DOP853 dense-output queue: records per warp (dop853_kernel.cu); 64 = single inlined
 # drain site; sized so that MINBLOCKS blocks fit the 227 KB of shared memory.
-QCAP = {1: 63, 2: 63, 3: 63, 4: 63, 5: 63, 6: 63, 7: 63, 8: 63}
+QCAP = {1: 55, 2: 55, 3: 55, 4: 63, 5: 63, 6: 63, 7: 63, 8: 63}
 
 
 def _smem_ok(n, mb, qcap):

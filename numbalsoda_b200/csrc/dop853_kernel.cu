@@ -247,8 +247,9 @@ template <bool STAGED>
 __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
 {
     extern __shared__ double b200_smem[];
-    const int lane = threadIdx.x & 31;
-    double* q = b200_smem + (size_t)(threadIdx.x >> 5) * (QF * QCAP);
+    // (lane and the warp's queue base are recomputed where needed: two registers less)
+#define LANE ((int)(threadIdx.x & 31u))
+#define WARP_Q (b200_smem + (size_t)(threadIdx.x >> 5) * (QF * QCAP))
     int qhead = 0, qcount = 0;  // warp-uniform
     // t_eval is shared by the whole ensemble, so the integration span is the same for
     // every trajectory: dop853_wrapper's t = teval(1), tout = teval(nt) (c_interface
@@ -271,7 +272,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     double y[N], y1[N], k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], k8[N], k9[N], k10[N];
     double pl[STAGED ? B200ODE_NPMAX : 1];
     double* pp = pl;
-    double x = 0.0, h = 0.0, xout = 0.0, xout2 = 0.0;
+    double x = 0.0, h = 0.0;
     int nstep = 0, naccpt = 0, nrejct = 0, nevent = 0, row = 0;
     // lane state bits (one register instead of three predicates kept across the loop)
     enum : unsigned { F_LAST = 1u, F_REJECT = 2u, F_EXHAUSTED = 4u };
@@ -339,23 +340,24 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     hh = fmin_(fmin_(100.0 * fabs(hh), h1), hmax);
                     h = copysign(fabs(hh), posneg);
                 }
-                xout = te[0];  // first solout call, c_interface :56-58
-                xout2 = nt > 1 ? te[1] : 0.0;  // te[row + 1], loaded one event ahead
+                // first solout call (c_interface :56-58): xout = teval(1), nt = 1.  From here
+                // on xout is always t_eval[min(row, nt-1)] (it keeps its last value once
+                // every row is written, c_interface :66-68), so it is read from t_eval when
+                // needed instead of being carried in registers.
                 row = 0;
             }
         }
 
         // ---- dense output for queued steps, converged across the warp
-        const unsigned active = __ballot_sync(FULL, b >= 0);
-        if (qcount >= QDRAIN_AT || (active == 0 && qcount > 0)) {
+        if (qcount >= QDRAIN_AT || (qcount > 0 && !__any_sync(FULL, b >= 0))) {
             const int m = qcount < 32 ? qcount : 32;
-            dop853_drain<STAGED>(L.data, L.data_stride, L.np, te, L.usol, nt, q, qhead, m);
+            dop853_drain<STAGED>(L.data, L.data_stride, L.np, te, L.usol, nt, WARP_Q, qhead, m);
             qhead += m;
             if (qhead >= QCAP) qhead -= QCAP;
             qcount -= m;
             __syncwarp();
         }
-        if (active == 0) {
+        if (!__any_sync(FULL, b >= 0)) {  // (voted again: cheaper than a register held across the drain)
             if (qcount == 0) break;
             continue;
         }
@@ -443,16 +445,12 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     naccpt++;
                     b200ode_user_rhs(xph, k5, k4, pp);
                     // (the stiffness detector, module :631-655, only prints: iprint /= 0)
-                    if (xout <= xph) {  // event, iout == 3, module :657
+                    if (te[row < nt ? row : nt - 1] <= xph) {  // event: xout <= xph, module :657
                         // dense output is prepared for this step: module :658-705 costs
                         // 3 RHS evaluations; solout writes every row with t_eval <= xph
                         nevent++;
                         row_lo = row;
-                        while (row < nt && xout <= xph) {
-                            row++;
-                            if (row < nt) xout = xout2;  // = te[row]; stays put at the end
-                            if (row + 1 < nt) xout2 = te[row + 1];
-                        }
+                        while (row < nt && te[row] <= xph) row++;
                         push = row > row_lo;
                     }
                     if (flags & F_LAST) {
@@ -477,9 +475,9 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
         if (pm) {
             const int np = __popc(pm);
             if (push) {
-                int slot = qhead + qcount + __popc(pm & ((1u << lane) - 1u));
+                int slot = qhead + qcount + __popc(pm & ((1u << LANE) - 1u));
                 if (slot >= QCAP) slot -= QCAP;
-                double* r = q + slot;
+                double* r = WARP_Q + slot;
                 r[0 * QCAP] = x;
                 r[1 * QCAP] = h;
                 r[2 * QCAP] = __longlong_as_double((long long)b);
