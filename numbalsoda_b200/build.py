@@ -27,8 +27,12 @@ NVCC_FLAGS = ["-O3", "-lineinfo", "-rdc=true", "-fatbin", "-std=c++17"]
 # __launch_bounds__(128, MINBLOCKS): register budget per system size (blocks of 128
 # threads that must fit one SM); chosen so that ptxas does not spill (checked by
 # tests/test_abi.py on the linked cubin).
-MINBLOCKS = {"dop853": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1}}
-THREADS = {"dop853": {n: 128 for n in range(1, 9)}}
+MINBLOCKS = {"dop853": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1},
+             "lsoda": {1: 3, 2: 3, 3: 3, 4: 2, 5: 4, 6: 3, 7: 2, 8: 2}}
+# lsoda keeps (13 n + n^2) doubles per thread in shared memory (lsoda_kernel.cu):
+# blocks of 64 threads from n = 5 so that several blocks still fit the 227 KB of an SM
+THREADS = {"dop853": {n: 128 for n in range(1, 9)},
+           "lsoda": {1: 128, 2: 128, 3: 128, 4: 128, 5: 64, 6: 64, 7: 64, 8: 64}}
 # DOP853 dense-output queue: records per warp (dop853_kernel.cu); 64 = single inlined
 # drain site; sized so that MINBLOCKS blocks fit the 227 KB of shared memory.
 QCAP = {1: 55, 2: 55, 3: 55, 4: 63, 5: 63, 6: 63, 7: 63, 8: 63}

@@ -282,22 +282,29 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
         CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
         CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
-        if (H->solver == B200ODE_DOP853) {
-            // ask the image for its queue geometry
+        {
+            // ask the image for its build-time geometry (queue / storage sizes, threads)
+            const bool dop = H->solver == B200ODE_DOP853;
             CUfunction cfg;
-            CU(cuModuleGetFunction(&cfg, P.mod, "b200ode_dop853_config"));
+            CU(cuModuleGetFunction(&cfg, P.mod, dop ? "b200ode_dop853_config" : "b200ode_lsoda_config"));
             int* d_cfg = reinterpret_cast<int*>(P.next);  // scratch: 32 bytes of the slots
             void* cp[] = {&d_cfg};
             CU(cuLaunchKernel(cfg, 1, 1, 1, 1, 1, 1, 0, nullptr, cp, nullptr));
             int cfgv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             CU(cuMemcpyDtoH_v2(cfgv, P.next, sizeof cfgv));
-            if (cfgv[0] < 32 || cfgv[1] != B200ODE_DOP853_QFIELDS(H->neq) || cfgv[3] != H->neq)
-                return fail(B200ODE_ECUDA, "dop853 image reports an inconsistent queue geometry");
-            P.qcap = cfgv[0];
+            if (cfgv[3] != H->neq)
+                return fail(B200ODE_ECUDA, "solver image was built for neq = %d", cfgv[3]);
             P.threads = cfgv[4];
             if (P.threads < 32 || P.threads > 1024 || P.threads % 32)
-                return fail(B200ODE_ECUDA, "dop853 image reports %d threads per block", P.threads);
-            P.dyn_smem = ((P.threads / 32) * cfgv[1] * cfgv[0] + 4) * (int)sizeof(double);
+                return fail(B200ODE_ECUDA, "solver image reports %d threads per block", P.threads);
+            if (dop) {
+                if (cfgv[0] < 32 || cfgv[1] != B200ODE_DOP853_QFIELDS(H->neq))
+                    return fail(B200ODE_ECUDA, "dop853 image reports an inconsistent queue geometry");
+                P.qcap = cfgv[0];
+                P.dyn_smem = ((P.threads / 32) * cfgv[1] * cfgv[0] + 4) * (int)sizeof(double);
+            } else {
+                P.dyn_smem = cfgv[0] * (int)sizeof(double);
+            }
         }
         if (P.dyn_smem > 48 * 1024) {
             CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));

@@ -1,0 +1,55 @@
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+// Compiles the LSODA device core (numbalsoda_b200/csrc/lsoda_core.cuh) as host C++ for
+// one system size (-DB200_NEQ=n) so that its restated control flow can be compared
+// with the CPU oracle bit for bit in a container without a GPU
+// (tests/test_lsoda_core_host.py).  Build: g++ -O2 -ffp-contract=off -mfma.
+#include <cstddef>
+#include <cstring>
+
+typedef void (*rhs_fn)(double, double*, double*, void*);
+static thread_local rhs_fn g_rhs;
+static inline long long b200ode_user_rhs(double t, double* u, double* du, double* p)
+{
+    g_rhs(t, u, du, p);
+    return 0;
+}
+
+#define LS_STRIDE 1
+#include "../numbalsoda_b200/csrc/lsoda_core.cuh"
+
+static const B200LsodaTables g_tables = B200_LSODA_TABLES_INIT;
+
+extern "C" const B200LsodaTables* lsoda_core_tables(void) { return &g_tables; }
+
+extern "C" void lsoda_core_host(rhs_fn f, int neq, const double* u0, void* data, int nt,
+                                const double* teval, double* usol, double rtol, double atol,
+                                int mxstep, int* success, int exit_on_warning, int* counters)
+{
+    if (neq != N) {
+        *success = -99;
+        return;
+    }
+    g_rhs = f;
+    double yh[13 * N], wm[N * N];
+    memset(yh, 0, sizeof yh);
+    memset(wm, 0, sizeof wm);
+    LsLane s;
+    LsRun R;
+    double* pp = static_cast<double*>(data);
+    bool done = ls_begin(s, R, yh, u0, pp, nt, teval, usol, rtol, atol);
+    const unsigned long long mxstep_u = (unsigned long long)(long long)mxstep;
+    while (!done)
+        done = ls_advance(s, R, yh, wm, &g_tables, pp, nt, teval, usol, rtol, atol, mxstep_u,
+                          exit_on_warning);
+    *success = R.istate > 0 ? 1 : 0;
+    if (counters) {
+        counters[0] = s.nst;
+        counters[1] = s.nfe;
+        counters[2] = s.nje;
+        counters[3] = R.nswitch;
+        counters[4] = s.nqu;
+        counters[5] = R.istate;
+        counters[6] = R.row;
+        counters[7] = s.meth;
+    }
+}

@@ -40,7 +40,7 @@ def test_link_errors_are_reported():
     assert rc == -2 and not out.value
 
 
-@pytest.mark.parametrize("solver", ["dop853"])
+@pytest.mark.parametrize("solver", ["dop853", "lsoda"])
 @pytest.mark.parametrize("strict", [False, True])
 def test_link_builtin_and_numba_rhs(solver, strict):
     import numbalsoda_b200 as nb
@@ -53,16 +53,17 @@ def test_link_builtin_and_numba_rhs(solver, strict):
         assert nb.get_handle(rhs, sid, 3, strict=strict) is h  # cached
 
 
-def test_linked_kernel_keeps_state_in_registers(tmp_path):
+@pytest.mark.parametrize("solver", ["dop853", "lsoda"])
+def test_linked_kernel_keeps_state_in_registers(tmp_path, solver):
     """cuobjdump on the linked cubin: no local-memory spills, no stack, the user RHS
     inlined (no CALL to b200ode_user_rhs survives)."""
     import numbalsoda_b200 as nb
     from numbalsoda_b200 import _lib
-    h = nb.get_handle(pr.lorenz_rhs, _lib.DOP853, 3)
+    h = nb.get_handle(pr.lorenz_rhs, _lib.DOP853 if solver == "dop853" else _lib.LSODA, 3)
     f = tmp_path / "k.cubin"
     f.write_bytes(h.cubin())
     res = subprocess.run(["cuobjdump", "-res-usage", str(f)], capture_output=True, text=True).stdout
-    m = re.search(r"Function b200ode_dop853_kernel:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", res)
+    m = re.search(r"Function b200ode_%s_kernel:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)" % solver, res)
     assert m, res
     regs, stack, shared, local = map(int, m.groups())
     assert stack == 0 and local == 0 and regs <= 255

@@ -1,0 +1,252 @@
+"""Parity of the CUDA LSODA path (through the C ABI / numbalsoda-compatible driver)
+with the CPU oracle -- itself pinned bit-for-bit to the compiled reference
+(tests/test_oracle_lsoda.py) -- and with the golden vectors generated from the
+reference's own C++ (tests/golden/lsoda_reference.npz).  strict=True links the
+kernels with FMA contraction disabled: states are then compared bit-for-bit and the
+step / RHS / Jacobian / method-switch counters must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as orc
+import _problems as pr
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "lsoda_reference.npz"))
+CASES = ["lv_test", "lv_readme", "robertson", "lorenz_short", "lorenz"]
+
+
+def _nb():
+    import numbalsoda_b200 as nb
+    return nb
+
+
+def _cnt(st):
+    return [st.nst, st.nfe, st.nje, st.nswitch, st.nqu, st.istate, st.rows, st.meth]
+
+
+def same(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("kind", ["builtin", "numba"])
+def test_single_trajectory_strict_bitwise(name, kind):
+    nb = _nb()
+    p = pr.problem(name)
+    rhs = nb.builtin(p["builtin"]) if kind == "builtin" else p["rhs"]
+    us, ok, cnt = nb.lsoda(rhs, p["u0"], p["t_eval"], p["data"], p["rtol"], p["atol"],
+                           strict=True, counters=True)
+    ref, okr, st = orc.lsoda(orc.builtin_rhs(p["builtin"]), p["u0"], p["t_eval"], p["data"],
+                             p["rtol"], p["atol"])
+    assert ok == okr
+    assert list(cnt) == _cnt(st)
+    assert same(us, ref)
+    # the reference's own C++, run when the fixtures were made
+    assert same(us, GOLD[name + "/usol"])
+    assert list(cnt) == list(GOLD[name + "/counters"])
+
+
+def test_reference_known_answers():
+    # /root/reference/tests/test_numbalsoda.py:11-20 and README.md / comparison2scipy.ipynb:175,
+    # through the drop-in driver with a cfunc address, exactly as a numbalsoda user calls it
+    import numba
+    nb = _nb()
+    p = pr.problem("lv_test")
+    cf = numba.cfunc(nb.lsoda_sig)(p["rhs"])
+    usol, success = nb.lsoda(cf.address, p["u0"], p["t_eval"], p["data"], rtol=1e-8, atol=1e-8,
+                             strict=True)
+    assert success and usol.shape == (11, 2)
+    assert list(usol[-1]) == [0.38583246250193476, 4.602012234037773]  # bit-for-bit
+    usol, success = nb.lsoda(cf.address, p["u0"], p["t_eval"], p["data"], rtol=1e-8, atol=1e-8)
+    assert success and np.all(np.isclose(usol[-1], [0.38583246250193476, 4.602012234037773]))
+    p = pr.problem("lv_readme")
+    usol, success = nb.lsoda(cf.address, p["u0"], p["t_eval"], p["data"], strict=True)
+    assert success and list(usol[-1]) == [0.15204821320141523, 0.10552706409364211]
+
+
+def test_exit_on_warning_like_the_reference():
+    # /root/reference/tests/test_exit_on_warning.py (u0 = int64 1 reinterpreted as a double)
+    nb = _nb()
+    u0 = np.array([1]).view(np.float64)
+    te = np.linspace(100, 101, 11)
+    d = np.array([1e15])
+    _, ok = nb.lsoda(pr.growth_rhs, u0, te, d, rtol=1e-9, atol=1e-9, exit_on_warning=True)
+    assert not ok
+    _, ok = nb.lsoda(pr.growth_rhs, u0, te, d, rtol=1e-9, atol=1e-9, exit_on_warning=False)
+    assert ok
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_robertson_sweep_against_oracle(strict):
+    """Config C3's parameter sweep (full benchmark_robber.py shape) at B = 2000."""
+    nb = _nb()
+    B = 2000
+    P = pr.robertson_sweep(B)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 1e5, 100)
+    us, ok, cnt = nb.lsoda(nb.builtin("robertson"), u0, te, P, 1e-8, 1e-8, strict=strict,
+                           counters=True)
+    ref, okr, cr = orc.solve_batch("lsoda", orc.builtin_rhs("robertson"), u0, te, P, 1e-8, 1e-8)
+    assert ok.all() and okr.all() and us.shape == (B, 100, 3)
+    if strict:
+        assert np.array_equal(cnt, cr)
+        assert np.array_equal(us, ref)
+        assert (cnt[:, 3] >= 1).all() and (cnt[:, 7] == 2).all()  # every one switched to BDF
+    else:
+        # fused multiply-adds perturb the last bits, and a chaotic-in-the-rounding step
+        # sequence follows: north_star's bound is 10 * rtol, taken
+        # in the solver's own error weights rtol * |y| + atol
+        err = np.abs(us - ref) / (1e-8 * np.abs(ref) + 1e-8)
+        print("fast-mode max weighted error: %.3g (bound 10)" % err.max())
+        assert err.max() <= 10.0
+        assert np.abs(cnt[:, 0].astype(float) - cr[:, 0]).mean() < 40
+
+
+def test_numba_robertson_sweep_counts_match_reference_counts():
+    """north_star: integer step / Jacobian-evaluation / method-switch counts match on
+    Lotka-Volterra and Robertson -- with the RHS compiled by numba.cuda."""
+    nb = _nb()
+    B = 256
+    P = pr.robertson_sweep(B, seed=3)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 1e5, 100)
+    us, ok, cnt = nb.lsoda(pr.robertson_rhs, u0, te, P, 1e-8, 1e-8, strict=True, counters=True)
+    fptr = pr.cfunc_address(pr.robertson_rhs)
+    ref, okr, cr = orc.solve_batch("lsoda", fptr, u0, te, P, 1e-8, 1e-8)
+    assert ok.all() and np.array_equal(cnt, cr) and np.array_equal(us, ref)
+    Pl = np.random.default_rng(2).uniform(0.5, 3.0, (B, 1))
+    te = np.linspace(0, 50, 200)
+    us, ok, cnt = nb.lsoda(pr.lv_rhs, np.array([5.0, 0.8]), te, Pl, 1e-6, 1e-9, strict=True,
+                           counters=True)
+    ref, okr, cr = orc.solve_batch("lsoda", pr.cfunc_address(pr.lv_rhs), np.array([5.0, 0.8]), te,
+                                   Pl, 1e-6, 1e-9)
+    assert ok.all() and np.array_equal(cnt, cr) and np.array_equal(us, ref)
+
+
+def test_batched_u0_and_shared_data():
+    nb = _nb()
+    rng = np.random.default_rng(5)
+    B = 257
+    u0 = np.array([5.0, 0.8]) * rng.uniform(0.5, 1.5, (B, 2))
+    te = np.linspace(0, 10, 31)
+    d = np.array([1.3])
+    us, ok, cnt = nb.lsoda(nb.builtin("lotka_volterra"), u0, te, d, 1e-7, 1e-9, strict=True,
+                           counters=True)
+    ref, okr, cr = orc.solve_batch("lsoda", orc.builtin_rhs("lotka_volterra"), u0, te, d, 1e-7, 1e-9)
+    assert ok.all() and np.array_equal(us, ref) and np.array_equal(cnt, cr)
+
+
+def test_failures_and_edge_cases():
+    nb = _nb()
+    f = nb.builtin("lotka_volterra")
+    fo = orc.builtin_rhs("lotka_volterra")
+    u0, d = np.array([5.0, 0.8]), np.array([1.0])
+    cases = [
+        dict(te=np.linspace(0, 10, 11), rtol=1e-8, atol=1e-8, mxstep=5),       # istate -1
+        dict(te=np.linspace(0, 10, 11), rtol=1e-8, atol=1e-8, mxstep=0),
+        dict(te=np.linspace(0, 10, 11), rtol=1e-8, atol=1e-8, mxstep=-1),
+        dict(te=np.array([0.0]), rtol=1e-8, atol=1e-8),                        # nt = 1
+        dict(te=np.array([0.0, 0.0, 1.0]), rtol=1e-8, atol=1e-8),              # tout too close
+        dict(te=np.array([0.0, 1.0, 1.0, 2.0, 2.0]), rtol=1e-8, atol=1e-8),    # duplicates
+        dict(te=np.array([0.0, 1.0, 0.5, 2.0]), rtol=1e-8, atol=1e-8),         # not monotone
+        dict(te=np.array([1.0, 0.0]), rtol=1e-8, atol=1e-8),                   # decreasing
+        dict(te=np.linspace(0, 10, 11), rtol=-1.0, atol=1e-8),                 # illegal tolerance
+        dict(te=np.linspace(0, 10, 11), rtol=0.0, atol=0.0),                   # ewt <= 0 quirk
+        dict(te=np.linspace(0, 10, 11), rtol=0.0, atol=1e-10),
+        dict(te=np.linspace(0, 10, 11), rtol=1e-17, atol=1e-20),               # too much accuracy
+        dict(te=np.array([0.0, 1e-9, 2e-9, 5.0, 5.0 + 1e-9]), rtol=1e-6, atol=1e-9),
+    ]
+    for c in cases:
+        kw = dict(rtol=c["rtol"], atol=c["atol"], mxstep=c.get("mxstep", 10000))
+        us, ok, cnt = nb.lsoda(f, u0, c["te"], d, strict=True, counters=True, **kw)
+        ref, okr, st = orc.lsoda(fo, u0, c["te"], d, **kw)
+        assert ok == okr and list(cnt) == _cnt(st), (c, list(cnt), _cnt(st))
+        assert same(us[:st.rows], ref[:st.rows]), c
+    # a batch in which only some trajectories fail (per-interval step budget)
+    U = np.array([[5.0, 0.8], [0.5, 0.08], [5.0, 0.8]])
+    P = np.array([[1.0], [1.0], [1.0]])
+    te = np.linspace(0, 10, 3)
+    us, ok, cnt = nb.lsoda(f, U, te, P, 1e-8, 1e-8, mxstep=120, strict=True, counters=True)
+    ref, okr, cr = orc.solve_batch("lsoda", fo, U, te, P, 1e-8, 1e-8, mxstep=120)
+    assert list(ok) == list(okr) and np.array_equal(cnt, cr)
+    for b in range(3):
+        assert same(us[b, :cr[b, 6]], ref[b, :cr[b, 6]])
+
+
+def test_stiff_problems_with_pivoting():
+    nb = _nb()
+    import numba
+    from numba import types
+    sig = types.void(types.double, types.CPointer(types.double), types.CPointer(types.double),
+                     types.CPointer(types.double))
+
+    def vdp(t, u, du, p):
+        du[0] = u[1]
+        du[1] = p[0] * ((1.0 - u[0] * u[0]) * u[1]) - u[0]
+
+    def lin3(t, u, du, p):
+        du[0] = -p[0] * u[0] + p[1] * u[1]
+        du[1] = p[0] * u[0] - p[1] * u[1] - p[2] * u[1] + 3.0 * u[2]
+        du[2] = p[2] * u[1] - 3.0 * u[2]
+
+    runs = [(vdp, [2.0, 0.0], [1000.0], np.linspace(0, 3000, 61), 1e-6, 1e-8),
+            (lin3, [1.0, 0.0, 0.0], [1e4, 2e6, 5e3], np.linspace(0, 10, 21), 1e-7, 1e-10),
+            (lin3, [1.0, 2.0, 3.0], [1e-3, 7e5, 1e7], np.linspace(0, 100, 21), 1e-5, 1e-9),
+            (pr.robertson_rhs, [1.0, 0, 0], [0.04, 3e7, 1e4], np.linspace(0, 1e11, 12), 1e-2, 1e-4),
+            (pr.robertson_rhs, [1.0, 0, 0], [0.04, 3e7, 1e4], np.linspace(0, 1e11, 12), 1e-10, 1e-14)]
+    for f, u0, d, te, rtol, atol in runs:
+        cf = numba.cfunc(sig)(f)
+        u0, d = np.array(u0), np.array(d)
+        us, ok, cnt = nb.lsoda(f, u0, te, d, rtol, atol, strict=True, counters=True)
+        ref, okr, st = orc.lsoda(cf.address, u0, te, d, rtol, atol)
+        assert ok == okr and list(cnt) == _cnt(st), (list(cnt), _cnt(st))
+        assert same(us[:st.rows], ref[:st.rows])
+
+
+def test_full_size_properties():
+    """BASELINE config C3 at reduced B: every trajectory succeeds, row 0 is u0 exactly,
+    mass is conserved (Robertson: u0+u1+u2 = 1) within the tolerance, and a permuted
+    ensemble gives the permuted result (lane / launch-order independence)."""
+    nb = _nb()
+    B = 20000
+    P = pr.robertson_sweep(B)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 1e5, 100)
+    us, ok = nb.lsoda(nb.builtin("robertson"), u0, te, P, 1e-8, 1e-8)
+    assert ok.all() and np.isfinite(us).all()
+    assert np.array_equal(us[:, 0, :], np.broadcast_to(u0, (B, 3)))
+    assert np.abs(us.sum(axis=2) - 1.0).max() < 1e-5
+    perm = np.random.default_rng(0).permutation(B)
+    us2, ok2 = nb.lsoda(nb.builtin("robertson"), u0, te, P[perm], 1e-8, 1e-8)
+    assert np.array_equal(us2, us[perm])
+
+
+def test_device_resident_entry_point():
+    """b200ode_lsoda_batched_device on torch-owned device memory and stream."""
+    import ctypes as ct
+    import torch
+    nb = _nb()
+    from numbalsoda_b200 import _lib
+    B, nt = 512, 100
+    P = torch.tensor(pr.robertson_sweep(B), device="cuda")
+    u0 = torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64, device="cuda")
+    te = torch.linspace(0, 1e5, nt, dtype=torch.float64, device="cuda")
+    usol = torch.empty((B, nt, 3), dtype=torch.float64, device="cuda")
+    ok = torch.zeros(B, dtype=torch.int32, device="cuda")
+    h = nb.get_handle(nb.builtin("robertson"), _lib.LSODA, 3, strict=True)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        rc = _lib.lib.b200ode_lsoda_batched_device(
+            h.ptr, B, 3, u0.data_ptr(), 0, P.data_ptr(), 24, 3, nt, te.data_ptr(),
+            usol.data_ptr(), 1e-8, 1e-8, 10000, ok.data_ptr(), None, 0,
+            ct.c_void_p(s.cuda_stream))
+    _lib.check(rc)
+    s.synchronize()
+    ref, okr, _ = orc.solve_batch("lsoda", orc.builtin_rhs("robertson"), np.array([1.0, 0, 0]),
+                                  te.cpu().numpy(), P.cpu().numpy(), 1e-8, 1e-8)
+    assert bool((ok == 1).all()) and np.array_equal(usol.cpu().numpy(), ref)
+    info = h.kernel_info()
+    assert info["local_bytes"] == 0 and info["launches"] >= 1
