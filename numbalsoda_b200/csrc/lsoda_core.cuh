@@ -20,8 +20,10 @@
 //  * driver.  Instead of re-entering the solver once per output time (wrapper.cpp:32)
 //    the lane steps freely and, after each accepted step, interpolates every t_eval
 //    point the step has passed -- the same arithmetic.
-//  * stoda's many exits funnel through one rescale site and one order-selection
-//    site, so a warp whose lanes take different exits re-converges there.
+//  * control.  The reference's loop nest (steps / retries / corrector iterations) is
+//    flattened into a state machine whose pass is one corrector iteration
+//    (ls_advance), so that lanes of a warp at different depths of the nest still
+//    execute the same code together.
 //
 // This header also compiles as host C++ (tests/lsoda_core_host.cpp) so that the
 // restated control flow can be checked against the CPU oracle without a GPU; the
@@ -65,11 +67,25 @@
 #define ELCO(q, k) T->elco[s.meth - 1][q][k]
 #define TESCO(q, k) T->tesco[s.meth - 1][q][k]
 
+// where a lane is in its step (ls_advance)
+#define LS_P_STEP 0     // about to start a step
+#define LS_P_ATTEMPT 1  // about to predict (first attempt of a step, or a retry)
+#define LS_P_ITER 2     // inside the corrector iteration
+// work a pass leaves for the lane's next pass
+#define LS_F_RESCALE 1u  // apply scaleh with the ratio s.rh
+#define LS_F_RMAX10 2u   // ... then rmax = 10 (the rescale ends an accepted step)
+#define LS_F_FINISH 4u   // an accepted step is complete: endstoda, output rows
+
 struct LsLane {
-    double y[N];  // the caller's vector: last corrector iterate (LSODA.cpp:1809,:1828)
+    double y[N];    // the caller's vector: last corrector iterate (LSODA.cpp:1809,:1828)
+    double ewt[N];  // inverse error weights of the step (LSODA.cpp:787-798)
+    double acor[N];  // accumulated correction (LSODA.cpp:1789,:1827)
     double h, hu, hold, tn, rc, el0, crate, rmax, pdest, pdlast, pdnorm;
+    double told, pnorm, del, delp, rate, rh;  // stoda / correction locals that outlive a pass
     int nq, meth, mused, ialth, ipup, nslp, icount, irflag, jstart, jcur, kflag;
     int nst, nfe, nje, nqu;
+    int m, phase;
+    unsigned flags;
     unsigned ipvt;  // 4 bits per row
 };
 
@@ -283,96 +299,6 @@ LS_FN int ls_prja(LsLane& s, double* wmp, const double (&savf)[N], double (&acor
 
 // corfailure, LSODA.cpp:1904-1922.  The reference increments the pointer `ncf`
 // (:1906), so its mxncf limit never fires; with hmin = 0 corflag 2 needs h == 0.
-LS_FN int ls_corfailure(LsLane& s, double* yhp, double told, double& rh)
-{
-    s.rmax = 2.0;
-    s.tn = told;
-    ls_pascal<false>(s, yhp);
-    if (fabs(s.h) <= 0.0 * 1.00001) return 2;
-    rh = 0.25;
-    s.ipup = (s.meth == 2) ? 2 : 0;
-    return 1;
-}
-
-// correction, LSODA.cpp:1743-1902.  Returns corflag; m = corrector iterations done.
-LS_FN int ls_correction(LsLane& s, double* yhp, double* wmp, const B200LsodaTables* T,
-                        double (&savf)[N], double (&acor)[N], const double (&ewt)[N],
-                        double* pp, double pnorm, double& del, double told, double& rh, int& m)
-{
-    const int miter = (s.meth == 2) ? 2 : 0;
-    double rate = 0.0, delp = 0.0;
-    m = 0;
-    del = 0.0;
-    LS_FOR_N s.y[i] = YH(1, i);
-    for (;;) {
-        b200ode_user_rhs(s.tn, s.y, savf, pp);
-        s.nfe++;
-        if (m == 0) {
-            if (s.ipup > 0) {
-                const int ierpj = ls_prja(s, wmp, savf, acor, ewt, pp);
-                s.ipup = 0;
-                s.rc = 1.0;
-                s.nslp = s.nst;
-                s.crate = 0.7;
-                if (ierpj != 0) return ls_corfailure(s, yhp, told, rh);
-            }
-            LS_FOR_N acor[i] = 0.0;
-        }
-        const double el1 = ELCO(s.nq, 1);
-        if (miter == 0) {
-            // functional iteration, LSODA.cpp:1792-1809
-            LS_FOR_N {
-                savf[i] = s.h * savf[i] - YH(2, i);
-                s.y[i] = savf[i] - acor[i];
-            }
-            del = ls_vmnorm(s.y, ewt);
-            LS_FOR_N {
-                s.y[i] = YH(1, i) + el1 * savf[i];
-                acor[i] = savf[i];
-            }
-        } else {
-            // chord iteration, LSODA.cpp:1816-1829
-            LS_FOR_N s.y[i] = s.h * savf[i] - (YH(2, i) + acor[i]);
-            ls_dgesl(s.ipvt, wmp, s.y);
-            del = ls_vmnorm(s.y, ewt);
-            LS_FOR_N {
-                acor[i] += s.y[i];
-                s.y[i] = YH(1, i) + el1 * acor[i];
-            }
-        }
-        // convergence test, LSODA.cpp:1842-1862
-        if (del <= 100.0 * pnorm * LS_ETA) break;
-        if (m != 0 || s.meth != 1) {
-            if (m != 0) {
-                double rm = 1024.0;
-                if (del <= (1024.0 * delp)) rm = del / delp;
-                rate = ls_max(rate, rm);
-                s.crate = ls_max(0.2 * s.crate, rm);
-            }
-            const double dcon = del * ls_min(1.0, 1.5 * s.crate) / (TESCO(s.nq, 2) * T->conit[s.nq]);
-            if (dcon <= 1.0) {
-                s.pdest = ls_max(s.pdest, rate / fabs(s.h * el1));
-                if (s.pdest != 0.0) s.pdlast = s.pdest;
-                break;
-            }
-        }
-        m++;
-        if (m == LS_MAXCOR || (m >= 2 && del > 2.0 * delp)) {
-            // LSODA.cpp:1871-1891
-            if (miter == 0 || s.jcur == 1) return ls_corfailure(s, yhp, told, rh);
-            s.ipup = miter;
-            m = 0;
-            rate = 0.0;
-            del = 0.0;
-            LS_FOR_N s.y[i] = YH(1, i);
-        } else {
-            delp = del;
-        }
-    }
-    return 0;
-}
-
-// methodswitch, LSODA.cpp:1946-2069
 LS_FN void ls_methodswitch(LsLane& s, const double* yhp, const B200LsodaTables* T,
                            const double (&ewt)[N], double dsm, double pnorm, double& pdh, double& rh)
 {
@@ -498,179 +424,6 @@ LS_FN int ls_orderswitch(LsLane& s, double* yhp, const B200LsodaTables* T, const
 
 // stoda, LSODA.cpp:995-1366: one accepted step, or a failure reported in s.kflag
 // (-1 repeated error-test failures, -2 corrector could not converge).
-LS_FN void ls_stoda(LsLane& s, double* yhp, double* wmp, const B200LsodaTables* T,
-                    const double (&ewt)[N], double* pp)
-{
-    double savf[N], acor[N];
-    double del = 0.0, dsm = 0.0, rh = 0.0, pdh = 0.0, pnorm = 0.0;
-    int m = 0;
-    bool rescale = false;   // a step-size change is pending (scaleh)
-    bool finished = false;  // ... and it ends an accepted step (rmax = 10, endstoda)
-    bool fix_rmax = false;
-    s.kflag = 0;
-    const double told = s.tn;
-    s.jcur = 0;
-    if (s.jstart == 0) {
-        // first call, LSODA.cpp:1058-1084 (lmax, l follow from meth and nq)
-        s.nq = 1;
-        s.ialth = 2;
-        s.rmax = 10000.0;
-        s.rc = 0.0;
-        s.el0 = 1.0;
-        s.crate = 0.7;
-        s.hold = s.h;
-        s.nslp = 0;
-        s.ipup = 0;  // miter = 0 for meth = 1
-        s.icount = 20;
-        s.irflag = 0;
-        s.pdest = 0.0;
-        s.pdlast = 0.0;
-        ls_resetcoeff(s, T);
-    }
-    if (s.jstart == -1) {
-        // after a method switch, LSODA.cpp:1096-1124
-        s.ipup = (s.meth == 2) ? 2 : 0;
-        if (s.ialth == 1) s.ialth = 2;
-        if (s.meth != s.mused) {
-            s.ialth = s.nq + 1;
-            ls_resetcoeff(s, T);
-        }
-        if (s.h != s.hold) {
-            rh = s.h / s.hold;
-            s.h = s.hold;
-            rescale = true;
-        }
-    }
-    for (;;) {
-        if (rescale) {
-            ls_scaleh(s, yhp, T, rh, pdh);
-            rescale = false;
-            if (finished) {
-                if (fix_rmax) s.rmax = 10.0;
-                break;
-            }
-        }
-        // prediction, LSODA.cpp:1132-1147
-        const int miter = (s.meth == 2) ? 2 : 0;
-        if (fabs(s.rc - 1.0) > LS_CCMAX) s.ipup = miter;
-        if (s.nst >= s.nslp + LS_MSBP) s.ipup = miter;
-        s.tn += s.h;
-        ls_pascal<true>(s, yhp);
-        pnorm = ls_vmnorm_yh(yhp, 1, ewt);
-        const int corflag = ls_correction(s, yhp, wmp, T, savf, acor, ewt, pp, pnorm, del, told, rh, m);
-        if (corflag == 1) {
-            rh = ls_max(rh, ls_hmin_ratio(s.h));
-            rescale = true;
-            continue;
-        }
-        if (corflag == 2) {
-            s.kflag = -2;
-            s.hold = s.h;
-            s.jstart = 1;
-            return;
-        }
-        // local error test, LSODA.cpp:1170-1177
-        s.jcur = 0;
-        if (m == 0) dsm = del / TESCO(s.nq, 2);
-        if (m > 0) dsm = ls_vmnorm(acor, ewt) / TESCO(s.nq, 2);
-        double rhup = 0.0;
-        bool select_order = false;
-        const bool accepted = dsm <= 1.0;
-        if (accepted) {
-            // LSODA.cpp:1191-1277
-            const int l = s.nq + 1;
-            const int lmax = (s.meth == 1 ? LS_MXORDN : LS_MXORDS) + 1;
-            s.kflag = 0;
-            s.nst++;
-            s.hu = s.h;
-            s.nqu = s.nq;
-            s.mused = s.meth;
-            for (int j = 1; j <= l; j++) {
-                const double r = ELCO(s.nq, j);
-                LS_FOR_N YH(j, i) = YH(j, i) + r * acor[i];
-            }
-            s.icount--;
-            if (s.icount < 0) {
-                ls_methodswitch(s, yhp, T, ewt, dsm, pnorm, pdh, rh);
-                if (s.meth != s.mused) {
-                    rh = ls_max(rh, ls_hmin_ratio(s.h));
-                    rescale = finished = fix_rmax = true;
-                    continue;
-                }
-            }
-            s.ialth--;
-            if (s.ialth == 0) {
-                if (l != lmax) {
-                    LS_FOR_N savf[i] = acor[i] - YH(lmax, i);
-                    const double dup = ls_vmnorm(savf, ewt) / TESCO(s.nq, 3);
-                    const double exup = 1.0 / (double)(l + 1);
-                    rhup = 1.0 / (1.4 * b200ode_pow(dup, exup) + 0.0000014);
-                }
-                select_order = true;
-            } else {
-                if (!(s.ialth > 1 || l == lmax)) LS_FOR_N YH(lmax, i) = acor[i];
-                break;
-            }
-        } else {
-            // error test failed, LSODA.cpp:1286-1363
-            s.kflag--;
-            s.tn = told;
-            ls_pascal<false>(s, yhp);
-            s.rmax = 2.0;
-            if (fabs(s.h) <= 0.0 * 1.00001) {
-                s.kflag = -1;
-                s.hold = s.h;
-                s.jstart = 1;
-                return;
-            }
-            if (s.kflag > -3) {
-                select_order = true;
-            } else {
-                if (s.kflag == -10) {
-                    s.kflag = -1;
-                    s.hold = s.h;
-                    s.jstart = 1;
-                    return;
-                }
-                // three or more failures: back to order 1 with a fresh derivative
-                rh = 0.1;
-                rh = ls_max(ls_hmin_ratio(s.h), rh);
-                s.h *= rh;
-                LS_FOR_N s.y[i] = YH(1, i);
-                b200ode_user_rhs(s.tn, s.y, savf, pp);
-                s.nfe++;
-                LS_FOR_N YH(2, i) = s.h * savf[i];
-                s.ipup = (s.meth == 2) ? 2 : 0;
-                s.ialth = 5;
-                if (s.nq != 1) {
-                    s.nq = 1;
-                    ls_resetcoeff(s, T);
-                }
-                continue;
-            }
-        }
-        if (select_order) {
-            const int orderflag = ls_orderswitch(s, yhp, T, acor, ewt, rhup, dsm, pdh, rh);
-            if (accepted) {
-                if (orderflag == 0) break;
-                if (orderflag == 2) ls_resetcoeff(s, T);
-                rh = ls_max(rh, ls_hmin_ratio(s.h));
-                rescale = finished = fix_rmax = true;
-            } else {
-                if (orderflag == 0) rh = ls_min(rh, 0.2);
-                if (orderflag == 2) ls_resetcoeff(s, T);
-                rh = ls_max(rh, ls_hmin_ratio(s.h));
-                rescale = true;
-            }
-        }
-    }
-    // endstoda, LSODA.cpp:2075-2082.  acor is not read again before the next step
-    // clears it (:1789), so its scaling by 1/tesco[nqu][2] is dropped.
-    s.hold = s.h;
-    s.jstart = 1;
-}
-
-// intdy with k = 0, LSODA.cpp:1435-1453 (c = 1: the reference's products with it are exact)
 LS_FN void ls_intdy(const LsLane& s, const double* yhp, double t, double* out)
 {
     const double sfrac = (t - s.tn) / s.h;
@@ -711,6 +464,10 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* 
     s.jcur = 0;
     s.kflag = 0;
     s.ipvt = 0;
+    s.m = 0;
+    s.phase = LS_P_STEP;
+    s.flags = 0;
+    s.told = s.pnorm = s.del = s.delp = s.rate = s.rh = 0.0;
     s.hu = 0.0;
     s.tn = 0.0;
     s.h = 0.0;
@@ -781,81 +538,379 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* 
 
 // One pass of the step loop of LSODA::lsoda (block e, LSODA.cpp:774-992) followed by
 // the output rows the step has reached.  Returns true when the trajectory is finished.
+// One pass of the solver's state machine for one trajectory; returns true when the
+// trajectory is finished (R.istate says how).
+//
+// The reference nests three loops -- lsoda's step loop (LSODA.cpp:774), stoda's retry
+// loop (:1127) and the corrector iteration (:1763) -- and a warp that runs them as
+// written spends most of its time with a few lanes in an inner loop while the others
+// wait (ncu, profiles/r1_lsoda_v0: 5.1 of 32 lanes active).  Here the nest is
+// flattened: every pass performs exactly ONE corrector iteration (one RHS evaluation),
+// preceded, for the lanes that need it, by the end of the previous step (rescale,
+// output rows), the start of a new step (weights, stop tests) and the prediction, and
+// followed, for the lanes whose corrector converged, by the error test and the step /
+// order / method selection.  A retry after a failed error or convergence test is just
+// the lane's next pass, taken together with the other lanes' next iterations.  The
+// arithmetic and its order per trajectory are unchanged.
+//
+// The function is written without early exits: a `return` inside a divergent branch
+// moves the branch's re-convergence point to the end of the function, and the warp
+// then runs everything after it once per group of lanes (ncu, profiles/r1_lsoda_v1:
+// the blocks below were executed 2-3 times per pass, 7 lanes at a time).  `fin` carries
+// the exits instead, and LS_SYNC() -- __syncwarp over the lanes that entered, a no-op
+// in the host build -- pins the lanes together between blocks.
 LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200LsodaTables* T,
                       double* pp, int nt, const double* teval, double* usol, double rtol,
-                      double atol, unsigned long long mxstep_u, int exit_on_warning)
+                      double atol, unsigned long long mxstep_u, int exit_on_warning,
+                      unsigned lanes)
 {
-    double ewt[N];
-    if (s.nst != 0 && (unsigned long long)(long long)(s.nst - R.nslast) >= mxstep_u) {  // :778
-        R.istate = -1;
-        return true;
+#if defined(__CUDA_ARCH__)
+#define LS_SYNC() __syncwarp(lanes)
+#else
+#define LS_SYNC() (void)lanes
+#endif
+    double pdh = 0.0;
+    bool fin = false;
+    // ---- (0) pending step-size change (scaleh), requested by the previous pass
+    if (s.flags & LS_F_RESCALE) {
+        ls_scaleh(s, yhp, T, s.rh, pdh);
+        if (s.flags & LS_F_RMAX10) s.rmax = 10.0;  // LSODA.cpp:1211,:1258
+        s.flags &= ~(LS_F_RESCALE | LS_F_RMAX10);
     }
-    // ewset (:787-798).  Before the first step yh[1] is u0, whose weights were checked
-    // by ls_begin, and the test for non-positive weights is skipped (:776).
-    bool bad_ewt = false;
-    LS_FOR_N {
-        ewt[i] = rtol * fabs(YH(1, i)) + atol;
-        if (ewt[i] <= 0.0) bad_ewt = true;
-        ewt[i] = 1.0 / ewt[i];
-    }
-    if (s.nst != 0 && bad_ewt) {
-        R.istate = -6;
-        return true;
-    }
-    const double tolsf = LS_ETA * ls_vmnorm_yh(yhp, 1, ewt);
-    if (tolsf > 0.01) {  // :801-818
-        R.istate = (s.nst == 0) ? -3 : -2;
-        return true;
-    }
-    if ((s.tn + s.h) == s.tn) {  // :820-845
-        R.nhnil++;
-        if (R.nhnil <= LS_MXHNIL && exit_on_warning) {
-            R.istate = -2;
-            return true;
+    LS_SYNC();
+    // ---- (1) end of an accepted step: endstoda (LSODA.cpp:2075-2082; acor is not read
+    //      again before :1789 clears it, so its scaling is dropped), the method-switch
+    //      bookkeeping of lsoda (:861-877) and every output row the step has reached
+    if (s.flags & LS_F_FINISH) {
+        s.flags &= ~LS_F_FINISH;
+        s.hold = s.h;
+        s.jstart = 1;
+        if (s.meth != s.mused) {
+            s.jstart = -1;
+            R.nswitch++;
         }
-    }
-    ls_stoda(s, yhp, wmp, T, ewt, pp);
-    if (s.kflag != 0) {  // :961-991
-        R.istate = (s.kflag == -1) ? -4 : -5;
-        return true;
-    }
-    if (s.meth != s.mused) {  // :861-877
-        s.jstart = -1;
-        R.nswitch++;
-    }
-    // Every output time this step has reached: the first is what the reference
-    // interpolates at :887, the others are its block-d returns (:675-689) on the
-    // following calls, which re-check t_eval's order (wrapper.cpp:33) and intdy's
-    // interval (:1426-1434).
-    bool first_in_step = true;
-    while (R.row < nt) {
-        if (teval[R.row] < teval[R.row - 1]) {
-            R.istate = 0;
-            return true;
-        }
-        const double tout = teval[R.row];
-        if ((s.tn - tout) * s.h < 0.0) break;
-        const double tp = s.tn - s.hu - 100.0 * LS_ETA * (s.tn + s.hu);
-        if ((tout - tp) * (tout - s.tn) > 0.0) {
-            // intdy refuses (:1426-1434): after a step the reference ignores that and
-            // returns the last corrector iterate; on a later call it is illegal input
-            if (!first_in_step) {
-                R.istate = -3;
-                return true;
+        // The first row is what the reference interpolates at :887, the others are its
+        // block-d returns (:675-689) on the following calls, which re-check t_eval's order
+        // (wrapper.cpp:33) and intdy's interval (:1426-1434).
+        bool first_in_step = true, more = R.row < nt;
+        while (more) {
+            const double tout = teval[R.row];
+            if (tout < teval[R.row - 1]) {
+                R.istate = 0;
+                fin = true;
+                more = false;
+            } else if ((s.tn - tout) * s.h < 0.0) {
+                more = false;
+            } else {
+                const double tp = s.tn - s.hu - 100.0 * LS_ETA * (s.tn + s.hu);
+                const bool refused = (tout - tp) * (tout - s.tn) > 0.0;
+                if (refused && !first_in_step) {
+                    // intdy refuses: on a later call that is illegal input
+                    R.istate = -3;
+                    fin = true;
+                    more = false;
+                } else {
+                    if (refused) {
+                        // ... right after a step the reference ignores intdy's refusal and
+                        // returns the last corrector iterate
+                        LS_FOR_N usol[(size_t)R.row * N + i] = s.y[i];
+                    } else {
+                        ls_intdy(s, yhp, tout, usol + (size_t)R.row * N);
+                    }
+                    first_in_step = false;
+                    R.nslast = s.nst;
+                    R.row++;
+                    more = R.row < nt;
+                }
             }
-            LS_FOR_N usol[(size_t)R.row * N + i] = s.y[i];
-        } else {
-            ls_intdy(s, yhp, tout, usol + (size_t)R.row * N);
         }
-        first_in_step = false;
-        R.nslast = s.nst;
-        R.row++;
+        if (!fin) {
+            if (R.row >= nt) {
+                R.istate = 2;
+                fin = true;
+            } else {
+                s.phase = LS_P_STEP;
+            }
+        }
     }
-    if (R.row >= nt) {
-        R.istate = 2;
-        return true;
+    LS_SYNC();
+    // ---- (2) start of a step: lsoda's stop tests (:774-845) and stoda's prologue (:1040-1124)
+    if (!fin && s.phase == LS_P_STEP) {
+        // ewset (:787-798).  Before the first step yh[1] is u0, whose weights ls_begin
+        // checked, and the test for non-positive weights is skipped (:776).
+        bool bad_ewt = false;
+        LS_FOR_N {
+            s.ewt[i] = rtol * fabs(YH(1, i)) + atol;
+            if (s.ewt[i] <= 0.0) bad_ewt = true;
+            s.ewt[i] = 1.0 / s.ewt[i];
+        }
+        const double tolsf = LS_ETA * ls_vmnorm_yh(yhp, 1, s.ewt);
+        if (s.nst != 0 && (unsigned long long)(long long)(s.nst - R.nslast) >= mxstep_u) {  // :778
+            R.istate = -1;
+            fin = true;
+        } else if (s.nst != 0 && bad_ewt) {  // :793
+            R.istate = -6;
+            fin = true;
+        } else if (tolsf > 0.01) {  // :801-818
+            R.istate = (s.nst == 0) ? -3 : -2;
+            fin = true;
+        } else {
+            if ((s.tn + s.h) == s.tn) {  // :820-845
+                R.nhnil++;
+                if (R.nhnil <= LS_MXHNIL && exit_on_warning) {
+                    R.istate = -2;
+                    fin = true;
+                }
+            }
+            if (!fin) {
+                s.kflag = 0;
+                s.told = s.tn;
+                s.jcur = 0;
+                s.phase = LS_P_ATTEMPT;
+                if (s.jstart == 0) {
+                    // first call, LSODA.cpp:1058-1084 (l and lmax follow from nq and meth)
+                    s.nq = 1;
+                    s.ialth = 2;
+                    s.rmax = 10000.0;
+                    s.rc = 0.0;
+                    s.el0 = 1.0;
+                    s.crate = 0.7;
+                    s.hold = s.h;
+                    s.nslp = 0;
+                    s.ipup = 0;  // miter = 0 for meth = 1
+                    s.icount = 20;
+                    s.irflag = 0;
+                    s.pdest = 0.0;
+                    s.pdlast = 0.0;
+                    ls_resetcoeff(s, T);
+                }
+                if (s.jstart == -1) {
+                    // after a method switch, LSODA.cpp:1096-1124
+                    s.ipup = (s.meth == 2) ? 2 : 0;
+                    if (s.ialth == 1) s.ialth = 2;
+                    if (s.meth != s.mused) {
+                        s.ialth = s.nq + 1;
+                        ls_resetcoeff(s, T);
+                    }
+                    if (s.h != s.hold) {
+                        // (cannot happen in this driver -- nothing changes h between steps --
+                        // but kept: the rescale is done at the top of the lane's next pass,
+                        // and this pass ends here)
+                        s.rh = s.h / s.hold;
+                        s.h = s.hold;
+                        s.flags |= LS_F_RESCALE;
+                    }
+                }
+            }
+        }
     }
-    return false;
+    LS_SYNC();
+    const int miter = (s.meth == 2) ? 2 : 0;
+    const bool go = !fin && !(s.flags & LS_F_RESCALE);
+    // ---- (3) start of an attempt: prediction, LSODA.cpp:1132-1147, and the corrector's
+    //      initialisation, :1748-1762
+    if (go && s.phase == LS_P_ATTEMPT) {
+        if (fabs(s.rc - 1.0) > LS_CCMAX) s.ipup = miter;
+        if (s.nst >= s.nslp + LS_MSBP) s.ipup = miter;
+        s.tn += s.h;
+        ls_pascal<true>(s, yhp);
+        s.pnorm = ls_vmnorm_yh(yhp, 1, s.ewt);
+        s.m = 0;
+        s.rate = 0.0;
+        s.del = 0.0;
+        s.delp = 0.0;
+        LS_FOR_N s.y[i] = YH(1, i);
+        s.phase = LS_P_ITER;
+    }
+    LS_SYNC();
+    // ---- (4) one corrector iteration, LSODA.cpp:1763-1900
+    double savf[N];
+    bool corfail = false, converged = false;
+    if (go) {
+        b200ode_user_rhs(s.tn, s.y, savf, pp);
+        s.nfe++;
+        if (s.m == 0 && s.ipup > 0) {
+            const int ierpj = ls_prja(s, wmp, savf, s.acor, s.ewt, pp);
+            s.ipup = 0;
+            s.rc = 1.0;
+            s.nslp = s.nst;
+            s.crate = 0.7;
+            if (ierpj != 0) corfail = true;
+        }
+    }
+    LS_SYNC();
+    if (go && !corfail) {
+        if (s.m == 0) LS_FOR_N s.acor[i] = 0.0;
+        const double el1 = ELCO(s.nq, 1);
+        if (miter == 0) {
+            // functional iteration, :1792-1809
+            LS_FOR_N {
+                savf[i] = s.h * savf[i] - YH(2, i);
+                s.y[i] = savf[i] - s.acor[i];
+            }
+            s.del = ls_vmnorm(s.y, s.ewt);
+            LS_FOR_N {
+                s.y[i] = YH(1, i) + el1 * savf[i];
+                s.acor[i] = savf[i];
+            }
+        } else {
+            // chord iteration, :1816-1829
+            LS_FOR_N s.y[i] = s.h * savf[i] - (YH(2, i) + s.acor[i]);
+            ls_dgesl(s.ipvt, wmp, s.y);
+            s.del = ls_vmnorm(s.y, s.ewt);
+            LS_FOR_N {
+                s.acor[i] += s.y[i];
+                s.y[i] = YH(1, i) + el1 * s.acor[i];
+            }
+        }
+        // convergence test, :1842-1862
+        if (s.del <= 100.0 * s.pnorm * LS_ETA) {
+            converged = true;
+        } else if (s.m != 0 || s.meth != 1) {
+            if (s.m != 0) {
+                double rm = 1024.0;
+                if (s.del <= (1024.0 * s.delp)) rm = s.del / s.delp;
+                s.rate = ls_max(s.rate, rm);
+                s.crate = ls_max(0.2 * s.crate, rm);
+            }
+            const double dcon = s.del * ls_min(1.0, 1.5 * s.crate) / (TESCO(s.nq, 2) * T->conit[s.nq]);
+            if (dcon <= 1.0) {
+                s.pdest = ls_max(s.pdest, s.rate / fabs(s.h * el1));
+                if (s.pdest != 0.0) s.pdlast = s.pdest;
+                converged = true;
+            }
+        }
+        if (!converged) {
+            s.m++;
+            if (s.m == LS_MAXCOR || (s.m >= 2 && s.del > 2.0 * s.delp)) {
+                // :1871-1891
+                if (miter == 0 || s.jcur == 1) {
+                    corfail = true;
+                } else {
+                    s.ipup = miter;
+                    s.m = 0;
+                    s.rate = 0.0;
+                    s.del = 0.0;
+                    LS_FOR_N s.y[i] = YH(1, i);
+                }
+            } else {
+                s.delp = s.del;
+            }
+        }
+    }
+    LS_SYNC();
+    // ---- (5) the attempt is over: local error test, LSODA.cpp:1170-1177
+    double dsm = 0.0, rhup = 0.0;
+    bool accepted = false, select_order = false;
+    if (converged) {
+        s.jcur = 0;
+        if (s.m == 0) dsm = s.del / TESCO(s.nq, 2);
+        if (s.m > 0) dsm = ls_vmnorm(s.acor, s.ewt) / TESCO(s.nq, 2);
+        accepted = dsm <= 1.0;
+    }
+    if (accepted) {
+        // LSODA.cpp:1191-1277
+        const int l = s.nq + 1;
+        const int lmax = (s.meth == 1 ? LS_MXORDN : LS_MXORDS) + 1;
+        s.kflag = 0;
+        s.nst++;
+        s.hu = s.h;
+        s.nqu = s.nq;
+        s.mused = s.meth;
+        for (int j = 1; j <= l; j++) {
+            const double r = ELCO(s.nq, j);
+            LS_FOR_N YH(j, i) = YH(j, i) + r * s.acor[i];
+        }
+        s.flags |= LS_F_FINISH;
+        s.icount--;
+        bool switched = false;
+        if (s.icount < 0) {
+            ls_methodswitch(s, yhp, T, s.ewt, dsm, s.pnorm, pdh, s.rh);
+            if (s.meth != s.mused) {
+                s.rh = ls_max(s.rh, ls_hmin_ratio(s.h));
+                s.flags |= LS_F_RESCALE | LS_F_RMAX10;
+                switched = true;
+            }
+        }
+        if (!switched) {
+            s.ialth--;
+            if (s.ialth == 0) {
+                if (l != lmax) {
+                    LS_FOR_N savf[i] = s.acor[i] - YH(lmax, i);
+                    const double dup = ls_vmnorm(savf, s.ewt) / TESCO(s.nq, 3);
+                    const double exup = 1.0 / (double)(l + 1);
+                    rhup = 1.0 / (1.4 * b200ode_pow(dup, exup) + 0.0000014);
+                }
+                select_order = true;
+            } else if (!(s.ialth > 1 || l == lmax)) {
+                LS_FOR_N YH(lmax, i) = s.acor[i];
+            }
+        }
+    } else if (converged || corfail) {
+        // the attempt failed: corfailure (:1904-1922) or error-test failure (:1286-1363);
+        // both retract the prediction
+        s.rmax = 2.0;
+        s.tn = s.told;
+        ls_pascal<false>(s, yhp);
+        s.phase = LS_P_ATTEMPT;
+        const bool h_is_zero = fabs(s.h) <= 0.0 * 1.00001;  // hmin = 0
+        if (corfail) {
+            // (the reference's mxncf limit never fires: it increments the pointer, :1906)
+            if (h_is_zero) {
+                s.kflag = -2;
+                R.istate = -5;  // :976
+                fin = true;
+            } else {
+                s.rh = 0.25;
+                s.ipup = miter;
+                s.rh = ls_max(s.rh, ls_hmin_ratio(s.h));
+                s.flags |= LS_F_RESCALE;
+            }
+        } else {
+            s.kflag--;
+            if (h_is_zero || s.kflag == -10) {
+                s.kflag = -1;
+                R.istate = -4;  // :969
+                fin = true;
+            } else if (s.kflag > -3) {
+                select_order = true;
+            } else {
+                // three or more failures: back to order 1 with a fresh derivative, :1333-1361
+                s.rh = 0.1;
+                s.rh = ls_max(ls_hmin_ratio(s.h), s.rh);
+                s.h *= s.rh;
+                LS_FOR_N s.y[i] = YH(1, i);
+                b200ode_user_rhs(s.tn, s.y, savf, pp);
+                s.nfe++;
+                LS_FOR_N YH(2, i) = s.h * savf[i];
+                s.ipup = miter;
+                s.ialth = 5;
+                if (s.nq != 1) {
+                    s.nq = 1;
+                    ls_resetcoeff(s, T);
+                }
+            }
+        }
+    }
+    LS_SYNC();
+    if (select_order) {
+        const int orderflag = ls_orderswitch(s, yhp, T, s.acor, s.ewt, rhup, dsm, pdh, s.rh);
+        if (accepted) {
+            if (orderflag != 0) {
+                if (orderflag == 2) ls_resetcoeff(s, T);
+                s.rh = ls_max(s.rh, ls_hmin_ratio(s.h));
+                s.flags |= LS_F_RESCALE | LS_F_RMAX10;
+            }
+        } else {
+            if (orderflag == 0) s.rh = ls_min(s.rh, 0.2);
+            if (orderflag == 2) ls_resetcoeff(s, T);
+            s.rh = ls_max(s.rh, ls_hmin_ratio(s.h));
+            s.flags |= LS_F_RESCALE;
+        }
+    }
+    LS_SYNC();
+    return fin;
+#undef LS_SYNC
 }
 
 #endif

@@ -78,10 +78,12 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
                                 L.usol + (size_t)b * (size_t)nt * N, rtol, atol);
             }
         }
-        if (!__any_sync(FULL, b >= 0)) break;
+        // lanes with a running trajectory take one pass of the state machine together
+        const unsigned lanes = __ballot_sync(FULL, b >= 0 && !done);
+        if (lanes == 0 && !__any_sync(FULL, b >= 0)) break;
         if (b >= 0 && !done)
             done = ls_advance(s, R, yhp, wmp, T, pp, nt, te, L.usol + (size_t)b * (size_t)nt * N,
-                              rtol, atol, mxstep_u, L.exit_on_warning);
+                              rtol, atol, mxstep_u, L.exit_on_warning, lanes);
         if (b >= 0 && done) {
             // wrapper.cpp:41-45: istate <= 0 -> success = 0
             L.success[b] = (R.istate > 0) ? 1 : 0;

@@ -76,11 +76,11 @@ def _pyfunc_from_address(addr):
         return _by_address[addr]
     from numba.core.ccallback import CFunc
     for obj in gc.get_objects():
-        if isinstance(obj, CFunc):
-            try:
+        try:  # (isinstance itself raises on dead weakref proxies)
+            if isinstance(obj, CFunc):
                 _by_address[obj.address] = obj._pyfunc
-            except Exception:
-                pass
+        except Exception:
+            pass
     if addr in _by_address:
         return _by_address[addr]
     raise ValueError(

@@ -40,7 +40,7 @@ extern "C" void lsoda_core_host(rhs_fn f, int neq, const double* u0, void* data,
     const unsigned long long mxstep_u = (unsigned long long)(long long)mxstep;
     while (!done)
         done = ls_advance(s, R, yh, wm, &g_tables, pp, nt, teval, usol, rtol, atol, mxstep_u,
-                          exit_on_warning);
+                          exit_on_warning, 0u);
     *success = R.istate > 0 ? 1 : 0;
     if (counters) {
         counters[0] = s.nst;
