@@ -41,12 +41,25 @@ WORKLOADS = {
     "robertson_lsoda": dict(solver="lsoda", rhs="robertson", n=3, p=3, u0=[1.0, 0.0, 0.0],
                             t_eval=(0.0, 1.0e5, 100), rtol=1e-8, atol=1e-8, mxstep=10000,
                             batch=1 << 20, config="BASELINE.json configs[2] (SURVEY 8d C3)"),
+    "brusselator_lsoda": dict(solver="lsoda", rhs="brusselator1d", n=64, p=3, u0="brusselator",
+                              t_eval=(0.0, 10.0, 100), rtol=1e-6, atol=1e-8, mxstep=10000,
+                              batch=100000, config="BASELINE.json configs[3] (SURVEY 8d C4): "
+                              "1-D Brusselator on 32 cells, warp per trajectory"),
 }
 
 
 def sweep(name, B, seed):
     import _problems as pr
-    return pr.lorenz_sweep(B, seed) if name == "lorenz" else pr.robertson_sweep(B, seed)
+    if name == "lorenz":
+        return pr.lorenz_sweep(B, seed)
+    if name == "brusselator1d":
+        return pr.brusselator_sweep(B, seed)
+    return pr.robertson_sweep(B, seed)
+
+
+def initial_state(wl):
+    import _problems as pr
+    return pr.brusselator_u0() if wl["u0"] == "brusselator" else np.array(wl["u0"], dtype=np.float64)
 
 
 # ---------------------------------------------------------------- algorithmic FLOPs
@@ -79,7 +92,7 @@ def lsoda_flops(cnt, n, f_rhs, nt):
     return float(fl.sum())
 
 
-F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6}
+F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6, "brusselator1d": 608}
 
 
 # ---------------------------------------------------------------- clocks
@@ -166,7 +179,7 @@ def cpu_arm(wl, budget_s, seed=0):
     import _oracle as orc
     cores = os.cpu_count() or 1
     te = np.linspace(*wl["t_eval"][:2], wl["t_eval"][2])
-    u0 = np.array(wl["u0"])
+    u0 = initial_state(wl)
     f = orc.builtin_rhs(wl["rhs"])
     use_ref = wl["solver"] == "lsoda" and orc.ref_probe is not None
 
@@ -280,7 +293,7 @@ def main():
     Ph = sweep(wl["rhs"], B, seed=rank)  # every rank integrates its own shard of the sweep
     teh = np.linspace(*wl["t_eval"][:2], nt)
     P = torch.tensor(Ph, device=dev)
-    u0 = torch.tensor(wl["u0"], dtype=torch.float64, device=dev)
+    u0 = torch.tensor(initial_state(wl), dtype=torch.float64, device=dev)
     te = torch.tensor(teh, device=dev)
     usol = torch.empty((B, nt, n), dtype=torch.float64, device=dev)
     ok = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -341,7 +354,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         Pp = torch.from_numpy(Ph).pin_memory()
-        u0p = torch.tensor(wl["u0"], dtype=torch.float64).pin_memory()
+        u0p = torch.tensor(initial_state(wl), dtype=torch.float64).pin_memory()
         tep = torch.from_numpy(teh).pin_memory()
         usolp = torch.empty((B, nt, n), dtype=torch.float64).pin_memory()
         okp = torch.empty(B, dtype=torch.int32).pin_memory()
@@ -388,7 +401,7 @@ def main():
     out_bytes = B * (nt * n * 8 + (n + wl["p"]) * 8 + 4)
     roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
-            "kernel": "b200ode_%s_kernel" % wl["solver"],
+            "kernel": "b200ode_%s_kernel" % (wl["solver"] + ("w" if wl["n"] > 8 else "")),
             "flops_per_launch": flops, "flops_per_trajectory": flops / B,
             "flop_count": "algorithmic, SURVEY.md 8(d) formulas x per-trajectory counters",
             "peak_source": peak_src,

@@ -89,6 +89,12 @@ def build(force=False, verbose=False):
                 if verbose and log.strip():
                     print(log)
             images.append(("%s_n%d" % (name, n), out))
+    # LSODA, one warp per trajectory: a single image, system size at run time
+    srcp = os.path.join(CSRC, "lsoda_warp_kernel.cu")
+    out = os.path.join(OBJ, "lsodaw.fatbin")
+    if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
+        _run([NVCC] + ARCH + NVCC_FLAGS + ["-o", out, srcp])
+    images.append(("lsodaw", out))
     srcp = os.path.join(CSRC, "rhs_builtin.cu")
     for r in BUILTIN_RHS:
         out = os.path.join(OBJ, "rhs_%s.fatbin" % r)

@@ -144,9 +144,16 @@ struct b200ode_rhs_s {
     int last_grid = 0;
 };
 
-static const char* kernel_name(int solver)
+// LSODA systems larger than B200ODE_THREAD_NMAX run one trajectory per warp
+// (lsoda_warp_kernel.cu: a single image, system size passed at run time).
+static bool warp_kernel(int solver, int neq)
 {
-    return solver == B200ODE_DOP853 ? "b200ode_dop853_kernel" : "b200ode_lsoda_kernel";
+    return solver == B200ODE_LSODA && neq > B200ODE_THREAD_NMAX;
+}
+static const char* kernel_name(int solver, int neq)
+{
+    if (solver == B200ODE_DOP853) return "b200ode_dop853_kernel";
+    return warp_kernel(solver, neq) ? "b200ode_lsodaw_kernel" : "b200ode_lsoda_kernel";
 }
 
 extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t size, int kind,
@@ -159,7 +166,13 @@ extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t s
     if (neq < 1) return fail(B200ODE_EINVAL, "neq = %d", neq);
     if (!image) return fail(B200ODE_EINVAL, "image is NULL");
     char name[64];
-    snprintf(name, sizeof name, "%s_n%d", solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq);
+    if (warp_kernel(solver, neq)) {
+        if (neq > B200ODE_WARP_NMAX)
+            return fail(B200ODE_ENOSYS, "lsoda: neq = %d exceeds %d", neq, B200ODE_WARP_NMAX);
+        snprintf(name, sizeof name, "lsodaw");
+    } else {
+        snprintf(name, sizeof name, "%s_n%d", solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq);
+    }
     const B200EmbeddedImage* solver_img = find_image(name);
     if (!solver_img)
         return fail(B200ODE_ENOSYS, "no %s kernel was built for neq = %d (image %s missing)",
@@ -275,14 +288,21 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
     if (!P.mod) {
         CU(cuDeviceGet(&dev, device));
         CU(cuModuleLoadData(&P.mod, H->cubin.data()));
-        CU(cuModuleGetFunction(&P.fn, P.mod, kernel_name(H->solver)));
-        CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
-                               (std::string(kernel_name(H->solver)) + "_ptr").c_str()));
+        const bool warp = warp_kernel(H->solver, H->neq);
+        CU(cuModuleGetFunction(&P.fn, P.mod, kernel_name(H->solver, H->neq)));
+        if (warp)
+            P.fn_ptr = P.fn;  // the warp kernel always hands the data record over by address
+        else
+            CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
+                                   (std::string(kernel_name(H->solver, H->neq)) + "_ptr").c_str()));
         CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
         CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
         CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
         CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
-        {
+        if (warp) {
+            P.threads = 32;
+            P.dyn_smem = B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double);
+        } else {
             // ask the image for its build-time geometry (queue / storage sizes, threads)
             const bool dop = H->solver == B200ODE_DOP853;
             CUfunction cfg;
@@ -308,7 +328,8 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         }
         if (P.dyn_smem > 48 * 1024) {
             CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));
-            CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));
+            if (P.fn_ptr != P.fn)
+                CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));
         }
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
         CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
@@ -346,11 +367,13 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
     CU(cuMemsetD8Async(next, 0, sizeof(unsigned long long), stream));
     args.next = reinterpret_cast<unsigned long long*>(next);
     const int kThreads = P->threads;
-    long long want = (args.B + kThreads - 1) / kThreads;
+    const bool warp = warp_kernel(H->solver, H->neq);
+    args.neq = H->neq;
+    long long want = warp ? args.B : (args.B + kThreads - 1) / kThreads;
     long long resident = (long long)P->sms * P->blocks_per_sm;
     int grid = (int)std::min(want, resident);
     void* params[] = {&args};
-    CU(cuLaunchKernel(args.np >= 0 ? P->fn : P->fn_ptr, grid, 1, 1, kThreads, 1, 1, (unsigned)P->dyn_smem, stream, params, nullptr));
+    CU(cuLaunchKernel((args.np >= 0 && !warp) ? P->fn : P->fn_ptr, grid, 1, 1, kThreads, 1, 1, (unsigned)P->dyn_smem, stream, params, nullptr));
     H->last_grid = grid;
     H->launches++;
     return 0;
@@ -459,7 +482,8 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     size_t target = std::min<size_t>((size_t)2 << 30, free_b / 4);
     long long chunk = (long long)std::max<size_t>(1, target / std::max<size_t>(row_bytes, 1));
     // keep every SM busy within a chunk where the ensemble allows it
-    chunk = std::max<long long>(chunk, std::min<long long>(B, (long long)P->sms * P->blocks_per_sm * P->threads));
+    chunk = std::max<long long>(chunk, std::min<long long>(B, (long long)P->sms * P->blocks_per_sm *
+                                                               (warp_kernel(solver, neq) ? 1 : P->threads)));
     chunk = std::min(chunk, B);
     // record size: |data_stride| bytes, or np doubles when data_stride == 0
     const size_t rec = data_stride != 0 ? (size_t)(data_stride > 0 ? data_stride : -data_stride)

@@ -12,6 +12,15 @@
 #define B200ODE_DOP853_QFIELDS(n) (4 + 11 * (n))
 #define B200ODE_THREADS 128 /* threads per block of every solver kernel */
 
+/* LSODA: systems of up to B200ODE_THREAD_NMAX equations run one trajectory per thread
+ * (lsoda_kernel.cu, one image per size), larger ones -- up to B200ODE_WARP_NMAX -- one
+ * trajectory per warp (lsoda_warp_kernel.cu, a single image, size at run time) with this
+ * many doubles of dynamic shared memory per warp (lsoda_vec_warp.cuh). */
+#define B200ODE_THREAD_NMAX 8
+#define B200ODE_WARP_NMAX 128
+#define B200ODE_LSODAW_DOUBLES(n) \
+    (17 * (n) + (n) * ((n) + 1) + ((n) < 32 ? (n) : 32) * ((n) + 1) + ((n) + 2) / 2)
+
 typedef struct B200OdeLaunch {
     long long B;              /* trajectories in this launch */
     const double* u0;         /* [B,n] (u0_stride = n) or [n] shared (u0_stride = 0) */
@@ -25,6 +34,8 @@ typedef struct B200OdeLaunch {
     double rtol, atol;
     int mxstep;
     int exit_on_warning;      /* lsoda only */
+    int neq;                  /* system size (run-time for the warp-per-trajectory kernel) */
+    int pad_;
     int* success;             /* [B] 1 / 0, as the reference's *success */
     int* counters;            /* [B,8] or null */
     unsigned long long* next; /* work queue head (zeroed before the launch) */

@@ -1,55 +1,52 @@
-// LSODA for one trajectory held by one thread (systems of N <= 8 equations).
+// LSODA: the solver's control flow for ONE trajectory, independent of how the
+// trajectory's vectors are stored and who works on them.
 //
 // Replaces, per trajectory, the reference's lsoda_wrapper (src/wrapper.cpp:10-57) ->
 // LSODA::lsoda_update (src/LSODA.cpp:2247-2277) -> LSODA::lsoda (:287-993) ->
-// stoda (:995-1366) -> correction / prja / dgefa / dgesl / methodswitch /
-// orderswitch / scaleh / intdy.  Every floating-point expression keeps the
-// reference's operand order, so that with FMA contraction disabled at link time the
-// states and the step / RHS / Jacobian / method-switch counters are those of the CPU
-// path bit for bit.  What is different is where things live and how control flows:
+// stoda (:995-1366) -> correction (:1743-1902) / methodswitch (:1946-2069) /
+// orderswitch (:2097-2209) / scaleh (:1594-1631).  Every floating-point expression
+// keeps the reference's operand order, so that with FMA contraction disabled at link
+// time the states and the step / RHS / Jacobian / method-switch counters are those of
+// the CPU path bit for bit.  What is different:
 //
-//  * storage.  The Nordsieck history yh (13 x N) and the iteration matrix wm (N x N)
-//    are indexed by the *run-time* order and pivot, which registers cannot do; they
-//    live in shared memory, one column per thread ([slot][thread]: consecutive lanes
-//    hit consecutive banks, no conflicts), so nothing is ever spilled to local
-//    memory.  y, savf, acor, ewt and ~25 scalars stay in registers.  The pivot
-//    vector is packed 4 bits per row into one register.
+//  * vectors.  Everything of length n (Nordsieck history yh, y, savf, acor, ewt, the
+//    iteration matrix and its LU factors) belongs to a *vector backend* V:
+//      lsoda_vec_thread.cuh  one thread per trajectory, n <= 8: y / ewt / acor in
+//                            registers, yh and the matrix in shared memory as
+//                            [slot][thread] columns (run-time order and pivot
+//                            indices without local memory);
+//      lsoda_vec_warp.cuh    one warp per trajectory, n <= 128: all vectors in shared
+//                            memory, lanes own components, norms and pivot searches
+//                            by shuffles, Jacobian columns evaluated in parallel.
+//    This file holds the scalars (LsLane) and the decisions.
 //  * coefficients.  cfode's elco / tesco tables depend only on the method: they are
 //    compile-time tables (lsoda_tables.cuh, bit-equal to cfode's arithmetic) instead
 //    of being recomputed at every method switch; el[] is read from them in place.
 //  * driver.  Instead of re-entering the solver once per output time (wrapper.cpp:32)
-//    the lane steps freely and, after each accepted step, interpolates every t_eval
+//    a trajectory steps freely and, after each accepted step, interpolates every t_eval
 //    point the step has passed -- the same arithmetic.
 //  * control.  The reference's loop nest (steps / retries / corrector iterations) is
 //    flattened into a state machine whose pass is one corrector iteration
 //    (ls_advance), so that lanes of a warp at different depths of the nest still
 //    execute the same code together.
 //
-// This header also compiles as host C++ (tests/lsoda_core_host.cpp) so that the
+// The headers also compile as host C++ (tests/lsoda_core_host.cpp) so that the
 // restated control flow can be checked against the CPU oracle without a GPU; the
-// product only ever runs it inside lsoda_kernel.cu.
+// product only ever runs them inside lsoda_kernel.cu / lsoda_warp_kernel.cu.
 #ifndef B200ODE_LSODA_CORE_CUH
 #define B200ODE_LSODA_CORE_CUH
 
 #include "b200ode_pow.cuh"
 #include "lsoda_tables.cuh"
 
-#ifndef N
-#define N B200_NEQ
-#endif
-
 #if defined(__CUDACC__)
 #define LS_FN __device__ __forceinline__
+#define LS_MFN __device__ __forceinline__  // member functions
 #else
 #include <cmath>
 #define LS_FN static inline
+#define LS_MFN inline
 #endif
-
-#ifndef LS_STRIDE
-#error "define LS_STRIDE: distance, in doubles, between two slots of one trajectory"
-#endif
-
-#define LS_FOR_N _Pragma("unroll") for (int i = 0; i < N; i++)
 
 #define LS_ETA 2.2204460492503131e-16      // LSODA.cpp:33
 #define LS_SQRTETA 1.4901161193847656e-08  // sqrt(ETA) = 2^-26, LSODA.cpp:483
@@ -60,33 +57,36 @@
 #define LS_MXHNIL 10  // LSODA.cpp:294
 #define LS_CCMAX 0.3  // LSODA.cpp:563
 
-// yh[j][i], j = 1..13 (LSODA.h:114); wm[r][c] = d f_r / d y_c (LSODA.cpp:1680)
-#define YH(j, i) yhp[(((j) - 1) * N + (i)) * LS_STRIDE]
-#define WM(r, c) wmp[((r) * N + (c)) * LS_STRIDE]
 // tables of the method in use (cfode is re-run for `meth` at :1086 before any use)
 #define ELCO(q, k) T->elco[s.meth - 1][q][k]
 #define TESCO(q, k) T->tesco[s.meth - 1][q][k]
 
-// where a lane is in its step (ls_advance)
+// where a trajectory is in its step (ls_advance)
 #define LS_P_STEP 0     // about to start a step
 #define LS_P_ATTEMPT 1  // about to predict (first attempt of a step, or a retry)
 #define LS_P_ITER 2     // inside the corrector iteration
-// work a pass leaves for the lane's next pass
+// work a pass leaves for the trajectory's next pass
 #define LS_F_RESCALE 1u  // apply scaleh with the ratio s.rh
 #define LS_F_RMAX10 2u   // ... then rmax = 10 (the rescale ends an accepted step)
 #define LS_F_FINISH 4u   // an accepted step is complete: endstoda, output rows
 
+// The scalars of class LSODA (LSODA.h:105-143) plus the locals of stoda / correction
+// that outlive a pass of the state machine.
 struct LsLane {
-    double y[N];    // the caller's vector: last corrector iterate (LSODA.cpp:1809,:1828)
-    double ewt[N];  // inverse error weights of the step (LSODA.cpp:787-798)
-    double acor[N];  // accumulated correction (LSODA.cpp:1789,:1827)
     double h, hu, hold, tn, rc, el0, crate, rmax, pdest, pdlast, pdnorm;
-    double told, pnorm, del, delp, rate, rh;  // stoda / correction locals that outlive a pass
+    double told, pnorm, del, delp, rate, rh;
     int nq, meth, mused, ialth, ipup, nslp, icount, irflag, jstart, jcur, kflag;
     int nst, nfe, nje, nqu;
     int m, phase;
     unsigned flags;
-    unsigned ipvt;  // 4 bits per row
+};
+
+struct LsRun {
+    int row;      // next usol row to write
+    int nslast;   // nst at the last output (mxstep is per output interval, LSODA.cpp:671,:778)
+    int nhnil;    // t + h == t warnings
+    int nswitch;  // Adams <-> BDF switches
+    int istate;   // 1 running; 2 finished; <= 0 failed (as LSODA.cpp:782-976; 0 = t_eval not monotone)
 };
 
 // std::max / std::min as the reference uses them (they differ from fmax/fmin on NaN)
@@ -95,72 +95,6 @@ LS_FN double ls_min(double a, double b) { return (b < a) ? b : a; }
 
 // hmin / |h| with hmin = 0 (LSODA.cpp:401, :1155, :1243 ...): +0, or NaN when h is 0 or NaN
 LS_FN double ls_hmin_ratio(double h) { return 0.0 / fabs(h); }
-
-// vmnorm, LSODA.cpp:1705-1712
-LS_FN double ls_vmnorm(const double (&v)[N], const double (&w)[N])
-{
-    double vm = 0.0;
-    LS_FOR_N vm = ls_max(vm, fabs(v[i]) * w[i]);
-    return vm;
-}
-LS_FN double ls_vmnorm_yh(const double* yhp, int j, const double (&w)[N])
-{
-    double vm = 0.0;
-    LS_FOR_N vm = ls_max(vm, fabs(YH(j, i)) * w[i]);
-    return vm;
-}
-
-// resetcoeff, LSODA.cpp:2211-2225 (el[] is read from the table where it is used)
-LS_FN void ls_resetcoeff(LsLane& s, const B200LsodaTables* T)
-{
-    const double el1 = ELCO(s.nq, 1);
-    s.rc = s.rc * el1 / s.el0;
-    s.el0 = el1;
-}
-
-// scaleh, LSODA.cpp:1594-1631 (hmxi = 0)
-LS_FN void ls_scaleh(LsLane& s, double* yhp, const B200LsodaTables* T, double& rh, double& pdh)
-{
-    rh = ls_min(rh, s.rmax);
-    rh = rh / ls_max(1.0, fabs(s.h) * 0.0 * rh);
-    if (s.meth == 1) {
-        s.irflag = 0;
-        pdh = ls_max(fabs(s.h) * s.pdlast, 0.000001);
-        if ((rh * pdh * 1.00001) >= T->sm1[s.nq]) {
-            rh = T->sm1[s.nq] / pdh;
-            s.irflag = 1;
-        }
-    }
-    double r = 1.0;
-    const int l = s.nq + 1;
-    for (int j = 2; j <= l; j++) {
-        r *= rh;
-        LS_FOR_N YH(j, i) = YH(j, i) * r;
-    }
-    s.h *= rh;
-    s.rc *= rh;
-    s.ialth = l;
-}
-
-// Pascal-triangle sweeps: prediction (LSODA.cpp:1141-1144) and retraction
-// (:1290-1295, :1909-1912).  For fixed j the inner loop runs i1 = j..nq upwards, so
-// yh[i1+1] is still the value of the previous pass when it is added: it is carried in
-// a register and every element costs one shared-memory load and one store.
-template <bool FORWARD>
-LS_FN void ls_pascal(const LsLane& s, double* yhp)
-{
-    for (int j = s.nq; j >= 1; j--) {
-        double a[N];
-        LS_FOR_N a[i] = YH(j, i);
-        for (int i1 = j; i1 <= s.nq; i1++) {
-            LS_FOR_N {
-                const double b = YH(i1 + 1, i);
-                YH(i1, i) = FORWARD ? a[i] + b : a[i] - b;
-                a[i] = b;
-            }
-        }
-    }
-}
 
 // idamax1's integer truncation (LSODA.cpp:59-77) as x86-64 evaluates (size_t)|x|:
 // cvttsd2si below 2^63, (x - 2^63) with the top bit set up to 2^64, 0 above and for NaN.
@@ -175,132 +109,38 @@ LS_FN unsigned long long ls_trunc_u64(double x)
 #endif
 }
 
-// dgefa, LSODA.cpp:173-231: row-oriented elimination; the pivot is searched along
-// row k and columns are swapped.  Returns nonzero when a zero pivot was met.
-LS_FN int ls_dgefa(LsLane& s, double* wmp)
+// resetcoeff, LSODA.cpp:2211-2225 (el[] is read from the table where it is used)
+LS_FN void ls_resetcoeff(LsLane& s, const B200LsodaTables* T)
 {
-    int info = 0;
-    unsigned ipvt = 0;
-#pragma unroll
-    for (int k = 0; k < N - 1; k++) {
-        int j = k;
-        unsigned long long vmax = 0;
-#pragma unroll
-        for (int c = k; c < N; c++) {
-            const unsigned long long v = ls_trunc_u64(WM(k, c));
-            if (v > vmax) {
-                vmax = v;
-                j = c;
-            }
-        }
-        ipvt |= (unsigned)j << (4 * k);
-        const double akj = WM(k, j);
-        if (akj == 0.0) {
-            info = k + 1;
-            continue;
-        }
-        if (j != k) {
-            WM(k, j) = WM(k, k);
-            WM(k, k) = akj;
-        }
-        double t = -1.0 / akj;
-        double rowk[N];
-#pragma unroll
-        for (int c = k + 1; c < N; c++) {
-            rowk[c] = t * WM(k, c);
-            WM(k, c) = rowk[c];
-        }
-#pragma unroll
-        for (int r = k + 1; r < N; r++) {
-            t = WM(r, j);
-            if (j != k) {
-                WM(r, j) = WM(r, k);
-                WM(r, k) = t;
-            }
-#pragma unroll
-            for (int c = k + 1; c < N; c++) WM(r, c) = t * rowk[c] + WM(r, c);
-        }
-    }
-    ipvt |= (unsigned)(N - 1) << (4 * (N - 1));
-    if (WM(N - 1, N - 1) == 0.0) info = N;
-    s.ipvt = ipvt;
-    return info;
+    const double el1 = ELCO(s.nq, 1);
+    s.rc = s.rc * el1 / s.el0;
+    s.el0 = el1;
 }
 
-// dgesl with job = 0, LSODA.cpp:119-144
-LS_FN void ls_dgesl(unsigned ipvt, const double* wmp, double (&b)[N])
+// scaleh, LSODA.cpp:1594-1631 (hmxi = 0)
+template <class V>
+LS_FN void ls_scaleh(LsLane& s, V& v, const B200LsodaTables* T, double& rh, double& pdh)
 {
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c < k; c++) t += WM(k, c) * b[c];
-        b[k] = (b[k] - t) / WM(k, k);
-    }
-#pragma unroll
-    for (int k = N - 2; k >= 0; k--) {
-        double t = 0.0;
-#pragma unroll
-        for (int c = k + 1; c < N; c++) t += WM(k, c) * b[c];
-        b[k] = b[k] + t;
-        const int j = (int)((ipvt >> (4 * k)) & 15u);
-#pragma unroll
-        for (int c = k + 1; c < N; c++) {
-            if (c == j) {
-                const double tt = b[c];
-                b[c] = b[k];
-                b[k] = tt;
-            }
+    rh = ls_min(rh, s.rmax);
+    rh = rh / ls_max(1.0, fabs(s.h) * 0.0 * rh);
+    if (s.meth == 1) {
+        s.irflag = 0;
+        pdh = ls_max(fabs(s.h) * s.pdlast, 0.000001);
+        if ((rh * pdh * 1.00001) >= T->sm1[s.nq]) {
+            rh = T->sm1[s.nq] / pdh;
+            s.irflag = 1;
         }
     }
+    const int l = s.nq + 1;
+    v.scale_yh(l, rh);  // r = 1; for j = 2..l: r *= rh; yh[j] *= r
+    s.h *= rh;
+    s.rc *= rh;
+    s.ialth = l;
 }
 
-// prja, LSODA.cpp:1633-1696 (miter == 2: dense finite-difference Jacobian), fnorm
-// (:1714-1736) and the LU factorisation.  Sets s.jcur; returns ierpj.
-LS_FN int ls_prja(LsLane& s, double* wmp, const double (&savf)[N], double (&acor)[N],
-                  const double (&ewt)[N], double* pp)
-{
-    s.nje++;
-    s.jcur = 1;
-    const double hl0 = s.h * s.el0;
-    double fac = ls_vmnorm(savf, ewt);
-    double r0 = 1000.0 * fabs(s.h) * LS_ETA * ((double)N) * fac;
-    if (r0 == 0.0) r0 = 1.0;
-    // one column per pass; a single (not unrolled) loop keeps one inlined copy of the RHS
-#pragma unroll 1
-    for (int j = 0; j < N; j++) {
-        double yj = 0.0, ewtj = 0.0;
-        LS_FOR_N {
-            if (i == j) {
-                yj = s.y[i];
-                ewtj = ewt[i];
-            }
-        }
-        const double r = ls_max(LS_SQRTETA * fabs(yj), r0 / ewtj);
-        double yp[N];
-        LS_FOR_N yp[i] = (i == j) ? s.y[i] + r : s.y[i];
-        fac = -hl0 / r;
-        b200ode_user_rhs(s.tn, yp, acor, pp);
-        LS_FOR_N WM(i, j) = (acor[i] - savf[i]) * fac;
-    }
-    s.nfe += N;
-    double an = 0.0;
-#pragma unroll
-    for (int r = 0; r < N; r++) {
-        double sum = 0.0;
-#pragma unroll
-        for (int c = 0; c < N; c++) sum += fabs(WM(r, c)) / ewt[c];
-        an = ls_max(an, sum * ewt[r]);
-    }
-    s.pdnorm = an / fabs(hl0);
-    LS_FOR_N WM(i, i) = WM(i, i) + 1.0;
-    return ls_dgefa(s, wmp) != 0 ? 1 : 0;
-}
-
-// corfailure, LSODA.cpp:1904-1922.  The reference increments the pointer `ncf`
-// (:1906), so its mxncf limit never fires; with hmin = 0 corflag 2 needs h == 0.
-LS_FN void ls_methodswitch(LsLane& s, const double* yhp, const B200LsodaTables* T,
-                           const double (&ewt)[N], double dsm, double pnorm, double& pdh, double& rh)
+// methodswitch, LSODA.cpp:1946-2069
+LS_FN void ls_methodswitch(LsLane& s, const B200LsodaTables* T, double dsm, double pnorm,
+                           double& pdh, double& rh)
 {
     const int l = s.nq + 1;
     if (s.meth == 1) {
@@ -352,13 +192,12 @@ LS_FN void ls_methodswitch(LsLane& s, const double* yhp, const B200LsodaTables* 
     s.meth = 1;
     s.pdlast = 0.0;
     s.nq = nqm1;
-    (void)yhp;
-    (void)ewt;
 }
 
 // orderswitch, LSODA.cpp:2097-2209.  Returns orderflag.
-LS_FN int ls_orderswitch(LsLane& s, double* yhp, const B200LsodaTables* T, const double (&acor)[N],
-                         const double (&ewt)[N], double rhup, double dsm, double& pdh, double& rh)
+template <class V>
+LS_FN int ls_orderswitch(LsLane& s, V& v, const B200LsodaTables* T, double rhup, double dsm,
+                         double& pdh, double& rh)
 {
     const int l = s.nq + 1;
     const int lmax = (s.meth == 1 ? LS_MXORDN : LS_MXORDS) + 1;
@@ -367,7 +206,7 @@ LS_FN int ls_orderswitch(LsLane& s, double* yhp, const B200LsodaTables* T, const
     double rhsm = 1.0 / (1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
     double rhdn = 0.0;
     if (s.nq != 1) {
-        const double ddn = ls_vmnorm_yh(yhp, l, ewt) / TESCO(s.nq, 1);
+        const double ddn = v.norm_yh(l) / TESCO(s.nq, 1);
         const double exdn = 1.0 / (double)s.nq;
         rhdn = 1.0 / (1.3 * b200ode_pow(ddn, exdn) + 0.0000013);
     }
@@ -397,7 +236,7 @@ LS_FN int ls_orderswitch(LsLane& s, double* yhp, const B200LsodaTables* T, const
             if (rh >= 1.1) {
                 const double r = ELCO(s.nq, l) / (double)l;
                 s.nq = l;
-                LS_FOR_N YH(s.nq + 1, i) = acor[i] * r;
+                v.yh_from_acor_scaled(s.nq + 1, r);
                 return 2;
             }
             s.ialth = 3;
@@ -422,35 +261,18 @@ LS_FN int ls_orderswitch(LsLane& s, double* yhp, const B200LsodaTables* T, const
     return 2;
 }
 
-// stoda, LSODA.cpp:995-1366: one accepted step, or a failure reported in s.kflag
-// (-1 repeated error-test failures, -2 corrector could not converge).
-LS_FN void ls_intdy(const LsLane& s, const double* yhp, double t, double* out)
-{
-    const double sfrac = (t - s.tn) / s.h;
-    double v[N];
-    LS_FOR_N v[i] = 1.0 * YH(s.nq + 1, i);
-    for (int j = s.nq - 1; j >= 0; j--) LS_FOR_N v[i] = 1.0 * YH(j + 1, i) + sfrac * v[i];
-    LS_FOR_N out[i] = v[i];
-}
-
 // ---------------------------------------------------------------------------
 // The driver: what lsoda_wrapper's loop over t_eval and LSODA::lsoda's blocks a-e
-// do for one trajectory, reorganised as  begin / advance-one-step.
-
-struct LsRun {
-    int row;      // next usol row to write
-    int nslast;   // nst at the last output (mxstep is per output interval, LSODA.cpp:671,:778)
-    int nhnil;    // t + h == t warnings
-    int nswitch;  // Adams <-> BDF switches
-    int istate;   // 1 running; 2 finished; <= 0 failed (as LSODA.cpp:782-976; 0 = t_eval not monotone)
-};
+// do for one trajectory, reorganised as  begin / advance-by-one-pass.
 
 // First call: wrapper.cpp:25-36 and blocks b, c of LSODA::lsoda (LSODA.cpp:341-663).
 // Returns true when the trajectory is already finished (R.istate says how).
-LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* pp, int nt,
+template <class V>
+LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int nt,
                     const double* teval, double* usol, double rtol, double atol)
 {
-    LS_FOR_N usol[i] = u0[i];
+    const int n = v.size();
+    v.begin(u0, usol);  // usol row 0 = u0 (wrapper.cpp:25-28), y = u0
     R.row = 1;
     R.nslast = 0;
     R.nhnil = 0;
@@ -463,7 +285,6 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* 
     s.jstart = 0;
     s.jcur = 0;
     s.kflag = 0;
-    s.ipvt = 0;
     s.m = 0;
     s.phase = LS_P_STEP;
     s.flags = 0;
@@ -483,19 +304,9 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* 
         R.istate = -3;
         return true;
     }
-    LS_FOR_N s.y[i] = u0[i];
-    double f0[N];
-    b200ode_user_rhs(t0, s.y, f0, pp);
+    v.rhs_yh2(t0, pp);  // yh[2] = f(t0, y), yh[1] = y (:572-578)
     s.nfe = 1;
-    LS_FOR_N YH(1, i) = s.y[i];
-    double ewt[N];
-    bool bad_ewt = false;
-    LS_FOR_N {
-        ewt[i] = rtol * fabs(s.y[i]) + atol;  // ewset with itol = 2
-        if (ewt[i] <= 0.0) bad_ewt = true;
-        ewt[i] = 1.0 / ewt[i];
-    }
-    if (bad_ewt) {
+    if (v.set_ewt(rtol, atol)) {
         // LSODA.cpp:585-590 leaves through terminate2 with istate still 1, which
         // wrapper.cpp:41 does not treat as a failure: every later call re-initialises,
         // fails the same way and hands u0 back.
@@ -504,7 +315,7 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* 
                 R.istate = 0;
                 return true;
             }
-            LS_FOR_N usol[(size_t)r * N + i] = u0[i];
+            v.fill_row(usol + (size_t)r * n, u0);
             R.row = r + 1;
         }
         R.istate = 2;
@@ -517,27 +328,20 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* 
         return true;
     }
     double tol = rtol;
-    if (tol <= 0.0) {
-        LS_FOR_N {
-            const double ayi = fabs(s.y[i]);
-            if (ayi != 0.0) tol = ls_max(tol, atol / ayi);
-        }
-    }
+    if (tol <= 0.0) tol = v.tol_floor(atol, tol);  // :626-634
     tol = ls_max(tol, 100.0 * LS_ETA);
     tol = ls_min(tol, 0.001);
-    double sum = ls_vmnorm(f0, ewt);
+    double sum = v.norm_yh(2);
     sum = 1.0 / (tol * w0 * w0) + tol * sum * sum;
     double h0 = 1.0 / sqrt(sum);
     h0 = ls_min(h0, tdist);
     h0 = h0 * ((tout - t0 >= 0.0) ? 1.0 : -1.0);
     s.h = h0;
-    LS_FOR_N YH(2, i) = f0[i] * h0;
+    v.scale_yh2(h0);
     R.istate = 1;
     return false;
 }
 
-// One pass of the step loop of LSODA::lsoda (block e, LSODA.cpp:774-992) followed by
-// the output rows the step has reached.  Returns true when the trajectory is finished.
 // One pass of the solver's state machine for one trajectory; returns true when the
 // trajectory is finished (R.istate says how).
 //
@@ -557,23 +361,21 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, double* yhp, const double* u0, double* 
 // moves the branch's re-convergence point to the end of the function, and the warp
 // then runs everything after it once per group of lanes (ncu, profiles/r1_lsoda_v1:
 // the blocks below were executed 2-3 times per pass, 7 lanes at a time).  `fin` carries
-// the exits instead, and LS_SYNC() -- __syncwarp over the lanes that entered, a no-op
-// in the host build -- pins the lanes together between blocks.
-LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200LsodaTables* T,
-                      double* pp, int nt, const double* teval, double* usol, double rtol,
-                      double atol, unsigned long long mxstep_u, int exit_on_warning,
-                      unsigned lanes)
+// the exits instead, and v.sync(lanes) -- __syncwarp over the lanes that entered; a
+// no-op in the host build and for the warp backend, whose 32 lanes run one trajectory
+// in lock step -- pins the lanes together between blocks.
+template <class V>
+LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, double* pp, int nt,
+                      const double* teval, double* usol, double rtol, double atol,
+                      unsigned long long mxstep_u, int exit_on_warning, unsigned lanes)
 {
-#if defined(__CUDA_ARCH__)
-#define LS_SYNC() __syncwarp(lanes)
-#else
-#define LS_SYNC() (void)lanes
-#endif
+#define LS_SYNC() v.sync(lanes)
+    const int n = v.size();
     double pdh = 0.0;
     bool fin = false;
     // ---- (0) pending step-size change (scaleh), requested by the previous pass
     if (s.flags & LS_F_RESCALE) {
-        ls_scaleh(s, yhp, T, s.rh, pdh);
+        ls_scaleh(s, v, T, s.rh, pdh);
         if (s.flags & LS_F_RMAX10) s.rmax = 10.0;  // LSODA.cpp:1211,:1258
         s.flags &= ~(LS_F_RESCALE | LS_F_RMAX10);
     }
@@ -613,9 +415,10 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
                     if (refused) {
                         // ... right after a step the reference ignores intdy's refusal and
                         // returns the last corrector iterate
-                        LS_FOR_N usol[(size_t)R.row * N + i] = s.y[i];
+                        v.store_y(usol + (size_t)R.row * n);
                     } else {
-                        ls_intdy(s, yhp, tout, usol + (size_t)R.row * N);
+                        // intdy with k = 0, LSODA.cpp:1435-1453
+                        v.intdy(s.nq, (tout - s.tn) / s.h, usol + (size_t)R.row * n);
                     }
                     first_in_step = false;
                     R.nslast = s.nst;
@@ -638,13 +441,8 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
     if (!fin && s.phase == LS_P_STEP) {
         // ewset (:787-798).  Before the first step yh[1] is u0, whose weights ls_begin
         // checked, and the test for non-positive weights is skipped (:776).
-        bool bad_ewt = false;
-        LS_FOR_N {
-            s.ewt[i] = rtol * fabs(YH(1, i)) + atol;
-            if (s.ewt[i] <= 0.0) bad_ewt = true;
-            s.ewt[i] = 1.0 / s.ewt[i];
-        }
-        const double tolsf = LS_ETA * ls_vmnorm_yh(yhp, 1, s.ewt);
+        const bool bad_ewt = v.set_ewt(rtol, atol);
+        const double tolsf = LS_ETA * v.norm_yh(1);
         if (s.nst != 0 && (unsigned long long)(long long)(s.nst - R.nslast) >= mxstep_u) {  // :778
             R.istate = -1;
             fin = true;
@@ -713,24 +511,27 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
         if (fabs(s.rc - 1.0) > LS_CCMAX) s.ipup = miter;
         if (s.nst >= s.nslp + LS_MSBP) s.ipup = miter;
         s.tn += s.h;
-        ls_pascal<true>(s, yhp);
-        s.pnorm = ls_vmnorm_yh(yhp, 1, s.ewt);
+        v.template pascal<true>(s.nq);
+        s.pnorm = v.norm_yh(1);
         s.m = 0;
         s.rate = 0.0;
         s.del = 0.0;
         s.delp = 0.0;
-        LS_FOR_N s.y[i] = YH(1, i);
+        v.y_from_yh1();
         s.phase = LS_P_ITER;
     }
     LS_SYNC();
     // ---- (4) one corrector iteration, LSODA.cpp:1763-1900
-    double savf[N];
     bool corfail = false, converged = false;
     if (go) {
-        b200ode_user_rhs(s.tn, s.y, savf, pp);
+        v.rhs_savf(s.tn, pp);
         s.nfe++;
         if (s.m == 0 && s.ipup > 0) {
-            const int ierpj = ls_prja(s, wmp, savf, s.acor, s.ewt, pp);
+            // prja (LSODA.cpp:1633-1696): finite-difference Jacobian, P = I - h el0 J, LU
+            s.nje++;
+            s.jcur = 1;
+            const int ierpj = v.prja(s.tn, s.h, s.h * s.el0, pp, s.pdnorm);
+            s.nfe += n;
             s.ipup = 0;
             s.rc = 1.0;
             s.nslp = s.nst;
@@ -740,29 +541,12 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
     }
     LS_SYNC();
     if (go && !corfail) {
-        if (s.m == 0) LS_FOR_N s.acor[i] = 0.0;
+        if (s.m == 0) v.acor_zero();
         const double el1 = ELCO(s.nq, 1);
-        if (miter == 0) {
-            // functional iteration, :1792-1809
-            LS_FOR_N {
-                savf[i] = s.h * savf[i] - YH(2, i);
-                s.y[i] = savf[i] - s.acor[i];
-            }
-            s.del = ls_vmnorm(s.y, s.ewt);
-            LS_FOR_N {
-                s.y[i] = YH(1, i) + el1 * savf[i];
-                s.acor[i] = savf[i];
-            }
-        } else {
-            // chord iteration, :1816-1829
-            LS_FOR_N s.y[i] = s.h * savf[i] - (YH(2, i) + s.acor[i]);
-            ls_dgesl(s.ipvt, wmp, s.y);
-            s.del = ls_vmnorm(s.y, s.ewt);
-            LS_FOR_N {
-                s.acor[i] += s.y[i];
-                s.y[i] = YH(1, i) + el1 * s.acor[i];
-            }
-        }
+        if (miter == 0)
+            s.del = v.functional(s.h, el1);  // functional iteration, :1792-1809
+        else
+            s.del = v.chord(s.h, el1);  // chord iteration, :1816-1829
         // convergence test, :1842-1862
         if (s.del <= 100.0 * s.pnorm * LS_ETA) {
             converged = true;
@@ -791,7 +575,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
                     s.m = 0;
                     s.rate = 0.0;
                     s.del = 0.0;
-                    LS_FOR_N s.y[i] = YH(1, i);
+                    v.y_from_yh1();
                 }
             } else {
                 s.delp = s.del;
@@ -805,7 +589,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
     if (converged) {
         s.jcur = 0;
         if (s.m == 0) dsm = s.del / TESCO(s.nq, 2);
-        if (s.m > 0) dsm = ls_vmnorm(s.acor, s.ewt) / TESCO(s.nq, 2);
+        if (s.m > 0) dsm = v.norm_acor() / TESCO(s.nq, 2);
         accepted = dsm <= 1.0;
     }
     if (accepted) {
@@ -817,15 +601,12 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
         s.hu = s.h;
         s.nqu = s.nq;
         s.mused = s.meth;
-        for (int j = 1; j <= l; j++) {
-            const double r = ELCO(s.nq, j);
-            LS_FOR_N YH(j, i) = YH(j, i) + r * s.acor[i];
-        }
+        v.accept(l, &ELCO(s.nq, 0));  // yh[j] += el[j] * acor, j = 1..l
         s.flags |= LS_F_FINISH;
         s.icount--;
         bool switched = false;
         if (s.icount < 0) {
-            ls_methodswitch(s, yhp, T, s.ewt, dsm, s.pnorm, pdh, s.rh);
+            ls_methodswitch(s, T, dsm, s.pnorm, pdh, s.rh);
             if (s.meth != s.mused) {
                 s.rh = ls_max(s.rh, ls_hmin_ratio(s.h));
                 s.flags |= LS_F_RESCALE | LS_F_RMAX10;
@@ -836,14 +617,14 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
             s.ialth--;
             if (s.ialth == 0) {
                 if (l != lmax) {
-                    LS_FOR_N savf[i] = s.acor[i] - YH(lmax, i);
-                    const double dup = ls_vmnorm(savf, s.ewt) / TESCO(s.nq, 3);
+                    // savf = acor - yh[lmax], :1222-1228
+                    const double dup = v.norm_acor_minus_yh(lmax) / TESCO(s.nq, 3);
                     const double exup = 1.0 / (double)(l + 1);
                     rhup = 1.0 / (1.4 * b200ode_pow(dup, exup) + 0.0000014);
                 }
                 select_order = true;
             } else if (!(s.ialth > 1 || l == lmax)) {
-                LS_FOR_N YH(lmax, i) = s.acor[i];
+                v.yh_from_acor(lmax);
             }
         }
     } else if (converged || corfail) {
@@ -851,7 +632,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
         // both retract the prediction
         s.rmax = 2.0;
         s.tn = s.told;
-        ls_pascal<false>(s, yhp);
+        v.template pascal<false>(s.nq);
         s.phase = LS_P_ATTEMPT;
         const bool h_is_zero = fabs(s.h) <= 0.0 * 1.00001;  // hmin = 0
         if (corfail) {
@@ -879,10 +660,8 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
                 s.rh = 0.1;
                 s.rh = ls_max(ls_hmin_ratio(s.h), s.rh);
                 s.h *= s.rh;
-                LS_FOR_N s.y[i] = YH(1, i);
-                b200ode_user_rhs(s.tn, s.y, savf, pp);
+                v.refresh_yh2(s.tn, s.h, pp);  // y = yh[1]; yh[2] = h f(tn, y)
                 s.nfe++;
-                LS_FOR_N YH(2, i) = s.h * savf[i];
                 s.ipup = miter;
                 s.ialth = 5;
                 if (s.nq != 1) {
@@ -894,7 +673,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, double* yhp, double* wmp, const B200L
     }
     LS_SYNC();
     if (select_order) {
-        const int orderflag = ls_orderswitch(s, yhp, T, s.acor, s.ewt, rhup, dsm, pdh, s.rh);
+        const int orderflag = ls_orderswitch(s, v, T, rhup, dsm, pdh, s.rh);
         if (accepted) {
             if (orderflag != 0) {
                 if (orderflag == 2) ls_resetcoeff(s, T);

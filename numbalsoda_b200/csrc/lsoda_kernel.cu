@@ -1,7 +1,8 @@
 // Batched LSODA for sm_100a: one trajectory per thread, systems of N <= 8 equations.
 //
 // Replaces, for ensembles, the reference's lsoda_wrapper (src/wrapper.cpp:10-57) and
-// class LSODA (src/LSODA.cpp); the solver arithmetic is lsoda_core.cuh.  This file is
+// class LSODA (src/LSODA.cpp); the solver is lsoda_core.cuh (control flow) +
+// lsoda_vec_thread.cuh (vector work of one thread's trajectory).  This file is
 // the ensemble organisation:
 //
 //  * a persistent grid (blocks = SMs x resident blocks) pulls trajectories from a
@@ -26,7 +27,7 @@
 #define B200_THREADS 128
 #endif
 #define LS_STRIDE B200_THREADS
-#include "lsoda_core.cuh"
+#include "lsoda_vec_thread.cuh"
 
 #define FULL 0xffffffffu
 #define LS_TABLE_DOUBLES ((int)(sizeof(B200LsodaTables) / sizeof(double)))
@@ -43,11 +44,11 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
     }
     __syncthreads();
     const B200LsodaTables* T = reinterpret_cast<const B200LsodaTables*>(b200_smem);
-    double* yhp = b200_smem + LS_TABLE_DOUBLES + threadIdx.x;
-    double* wmp = yhp + 13 * N * B200_THREADS;
-
     LsLane s;
     LsRun R;
+    LsThreadVec v;
+    v.yhp = b200_smem + LS_TABLE_DOUBLES + threadIdx.x;
+    v.wmp = v.yhp + 13 * N * B200_THREADS;
     double pl[STAGED ? B200ODE_NPMAX : 1];
     double* pp = pl;
     long long b = -1;  // trajectory of this lane, -1 = idle
@@ -74,7 +75,7 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
                 } else {
                     pp = const_cast<double*>(pg);
                 }
-                done = ls_begin(s, R, yhp, L.u0 + b * L.u0_stride, pp, nt, te,
+                done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te,
                                 L.usol + (size_t)b * (size_t)nt * N, rtol, atol);
             }
         }
@@ -82,7 +83,7 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
         const unsigned lanes = __ballot_sync(FULL, b >= 0 && !done);
         if (lanes == 0 && !__any_sync(FULL, b >= 0)) break;
         if (b >= 0 && !done)
-            done = ls_advance(s, R, yhp, wmp, T, pp, nt, te, L.usol + (size_t)b * (size_t)nt * N,
+            done = ls_advance(s, R, v, T, pp, nt, te, L.usol + (size_t)b * (size_t)nt * N,
                               rtol, atol, mxstep_u, L.exit_on_warning, lanes);
         if (b >= 0 && done) {
             // wrapper.cpp:41-45: istate <= 0 -> success = 0

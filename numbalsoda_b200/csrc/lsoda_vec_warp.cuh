@@ -1,0 +1,404 @@
+// LSODA vector backend: one warp owns one trajectory of 9 <= n <= 128 equations.
+//
+// The vector work of the reference's routines -- vmnorm / fnorm (LSODA.cpp:1705-1736),
+// ewset (:1368-1390), the Pascal sweeps of stoda (:1141-1144, :1290-1295), scaleh's
+// rescale (:1621-1627), prja (:1633-1696), dgefa / dgesl (:110-231), the corrector
+// updates (:1792-1829), the Nordsieck update (:1197-1202) and intdy (:1435-1453) -- for
+// the warp-per-trajectory kernel (lsoda_warp_kernel.cu).  Control flow: lsoda_core.cuh;
+// all 32 lanes execute it redundantly on the same scalars, so there is no divergence.
+//
+// Storage (shared memory, per warp): yh[13][n], y, savf, acor, ewt, the iteration
+// matrix stored transposed with a padded leading dimension (wmT[c*ld + r] = a[r][c],
+// ld = n + 1: a lane per row is conflict free, a lane per column 2-way), one private
+// copy of y per lane for the finite-difference Jacobian, the pivot vector.
+//
+// Parallel decomposition, chosen so that every floating-point result is the one the
+// reference's sequential loops produce (bit-for-bit in strict mode):
+//   * elementwise vector updates, Pascal sweeps, interpolation: lane i owns components
+//     i, i + 32, ...;
+//   * max-norms and the pivot search: per-lane partial results combined by shuffles
+//     (max and first-arg-max are order independent);
+//   * Jacobian (prja): the n perturbed RHS evaluations are independent -- 32 columns at
+//     a time, one per lane, each lane calling the user's RHS on its private copy of y and
+//     writing straight into the matrix column; fnorm's row sums run over j in order, a
+//     lane per row;
+//   * LU (dgefa): the row-k scaling and the rank-1 update touch independent elements:
+//     a lane per row of the trailing block;
+//   * forward substitution (dgesl): column sweep -- once b[c] is final every later row
+//     adds a[k][c] * b[c] to its private running sum, which accumulates the terms in the
+//     same order c = 0, 1, ... as the reference's dot product;
+//   * back substitution: the reference's dot products run over ascending c with pivot
+//     swaps in between, which fixes a sequential summation order: kept sequential here
+//     (the one O(n^2) serial chain left; a shuffle-tree variant for the fast mode is a
+//     follow-up);
+//   * the RHS of a corrector iteration is one call of the user's scalar function: lane 0.
+#ifndef B200ODE_LSODA_VEC_WARP_CUH
+#define B200ODE_LSODA_VEC_WARP_CUH
+
+#include "lsoda_core.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define WV_LANE ((int)(threadIdx.x & 31u))
+#define WV_NL 32
+#define WV_SYNC() __syncwarp()
+LS_FN double wv_bcast(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+LS_FN double wv_max(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = ls_max(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+LS_FN bool wv_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+// first position of the largest value: larger v wins, ties go to the smaller index
+LS_FN void wv_argmax(unsigned long long& v, int& j)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+        if (ov > v || (ov == v && oj < j)) {
+            v = ov;
+            j = oj;
+        }
+    }
+}
+#else
+// host build (tests/lsoda_core_host.cpp): one "lane" walks every component in order
+#define WV_LANE 0
+#define WV_NL 1
+#define WV_SYNC() (void)0
+LS_FN double wv_bcast(double x, int) { return x; }
+LS_FN double wv_max(double x) { return x; }
+LS_FN bool wv_any(bool p) { return p; }
+LS_FN void wv_argmax(unsigned long long&, int&) {}
+#endif
+
+#define WV_NMAX 128
+#define WV_NPL (WV_NMAX / WV_NL)  // rows a lane can own
+#define WV_FOR_OWN(i) for (int i = WV_LANE; i < n; i += WV_NL)
+#define WYH(j, i) yh[((j) - 1) * n + (i)]
+#define WMT(r, c) wmT[(c) * ld + (r)]  // a[r][c]
+
+#include "b200ode_launch.h"  // B200ODE_LSODAW_DOUBLES(n): shared memory of one trajectory
+
+struct LsWarpVec {
+    int n, ld;
+    double *yh, *y, *savf, *acor, *ewt, *wmT, *ucopy;
+    int* ipvt;
+
+    LS_MFN void attach(double* base, int neq)
+    {
+        n = neq;
+        ld = neq + 1;
+        yh = base;
+        y = yh + 13 * n;
+        savf = y + n;
+        acor = savf + n;
+        ewt = acor + n;
+        wmT = ewt + n;
+        ucopy = wmT + n * ld;
+        ipvt = reinterpret_cast<int*>(ucopy + (n < 32 ? n : 32) * ld);
+    }
+    LS_MFN int size() const { return n; }
+    LS_MFN void sync(unsigned) {}
+
+    LS_MFN double norm_ptr(const double* v) const
+    {
+        double vm = 0.0;
+        WV_FOR_OWN(i) vm = ls_max(vm, fabs(v[i]) * ewt[i]);
+        return wv_max(vm);
+    }
+    LS_MFN double norm_yh(int j) const { return norm_ptr(yh + (j - 1) * n); }
+    LS_MFN double norm_acor() const { return norm_ptr(acor); }
+    LS_MFN double norm_acor_minus_yh(int j)
+    {
+        WV_FOR_OWN(i) savf[i] = acor[i] - WYH(j, i);
+        return norm_ptr(savf);
+    }
+
+    LS_MFN bool set_ewt(double rtol, double atol)
+    {
+        bool bad = false;
+        WV_FOR_OWN(i) {
+            double w = rtol * fabs(WYH(1, i)) + atol;
+            if (w <= 0.0) bad = true;
+            ewt[i] = 1.0 / w;
+        }
+        bad = wv_any(bad);
+        WV_SYNC();
+        return bad;
+    }
+
+    template <bool FORWARD>
+    LS_MFN void pascal(int nq)
+    {
+        WV_FOR_OWN(i) {
+            for (int j = nq; j >= 1; j--) {
+                double a = WYH(j, i);
+                for (int i1 = j; i1 <= nq; i1++) {
+                    const double b = WYH(i1 + 1, i);
+                    WYH(i1, i) = FORWARD ? a + b : a - b;
+                    a = b;
+                }
+            }
+        }
+        WV_SYNC();
+    }
+
+    LS_MFN void scale_yh(int l, double rh)
+    {
+        double r = 1.0;
+        for (int j = 2; j <= l; j++) {
+            r *= rh;
+            WV_FOR_OWN(i) WYH(j, i) = WYH(j, i) * r;
+        }
+        WV_SYNC();
+    }
+
+    LS_MFN void y_from_yh1()
+    {
+        WV_FOR_OWN(i) y[i] = WYH(1, i);
+        WV_SYNC();
+    }
+    LS_MFN void rhs_to(double t, double* out, double* pp)
+    {
+        WV_SYNC();
+        if (WV_LANE == 0) b200ode_user_rhs(t, y, out, pp);
+        WV_SYNC();
+    }
+    LS_MFN void rhs_savf(double t, double* pp) { rhs_to(t, savf, pp); }
+    LS_MFN void acor_zero()
+    {
+        WV_FOR_OWN(i) acor[i] = 0.0;
+        WV_SYNC();
+    }
+
+    LS_MFN double functional(double h, double el1)
+    {
+        WV_FOR_OWN(i) {
+            savf[i] = h * savf[i] - WYH(2, i);
+            y[i] = savf[i] - acor[i];
+        }
+        const double del = norm_ptr(y);
+        WV_FOR_OWN(i) {
+            y[i] = WYH(1, i) + el1 * savf[i];
+            acor[i] = savf[i];
+        }
+        WV_SYNC();
+        return del;
+    }
+
+    LS_MFN double chord(double h, double el1)
+    {
+        WV_FOR_OWN(i) y[i] = h * savf[i] - (WYH(2, i) + acor[i]);
+        WV_SYNC();
+        dgesl(y);
+        const double del = norm_ptr(y);
+        WV_FOR_OWN(i) {
+            acor[i] += y[i];
+            y[i] = WYH(1, i) + el1 * acor[i];
+        }
+        WV_SYNC();
+        return del;
+    }
+
+    LS_MFN void accept(int l, const double* el)
+    {
+        for (int j = 1; j <= l; j++) {
+            const double r = el[j];
+            WV_FOR_OWN(i) WYH(j, i) = WYH(j, i) + r * acor[i];
+        }
+        WV_SYNC();
+    }
+    LS_MFN void yh_from_acor(int j)
+    {
+        WV_FOR_OWN(i) WYH(j, i) = acor[i];
+        WV_SYNC();
+    }
+    LS_MFN void yh_from_acor_scaled(int j, double r)
+    {
+        WV_FOR_OWN(i) WYH(j, i) = acor[i] * r;
+        WV_SYNC();
+    }
+    LS_MFN void refresh_yh2(double t, double h, double* pp)
+    {
+        y_from_yh1();
+        rhs_savf(t, pp);
+        WV_FOR_OWN(i) WYH(2, i) = h * savf[i];
+        WV_SYNC();
+    }
+
+    LS_MFN void intdy(int nq, double sfrac, double* out) const
+    {
+        WV_FOR_OWN(i) {
+            double v = 1.0 * WYH(nq + 1, i);
+            for (int j = nq - 1; j >= 0; j--) v = 1.0 * WYH(j + 1, i) + sfrac * v;
+            out[i] = v;
+        }
+    }
+    LS_MFN void store_y(double* out) const { WV_FOR_OWN(i) out[i] = y[i]; }
+
+    // ---- first call (ls_begin)
+    LS_MFN void begin(const double* u0, double* usol)
+    {
+        WV_FOR_OWN(i) {
+            y[i] = u0[i];
+            usol[i] = y[i];
+        }
+        WV_SYNC();
+    }
+    LS_MFN void fill_row(double* out, const double* u0) const { WV_FOR_OWN(i) out[i] = u0[i]; }
+    LS_MFN void rhs_yh2(double t0, double* pp)
+    {
+        rhs_to(t0, yh + n, pp);
+        WV_FOR_OWN(i) WYH(1, i) = y[i];
+        WV_SYNC();
+    }
+    LS_MFN double tol_floor(double atol, double tol) const
+    {
+        WV_FOR_OWN(i) {
+            const double ayi = fabs(y[i]);
+            if (ayi != 0.0) tol = ls_max(tol, atol / ayi);
+        }
+        return wv_max(tol);
+    }
+    LS_MFN void scale_yh2(double h0)
+    {
+        WV_FOR_OWN(i) WYH(2, i) = WYH(2, i) * h0;
+        WV_SYNC();
+    }
+
+    // ---- linear algebra
+    // dgefa, LSODA.cpp:173-231.  Returns nonzero when a zero pivot was met.
+    LS_MFN int dgefa()
+    {
+        int info = 0;
+        for (int k = 0; k < n - 1; k++) {
+            // idamax1 along row k (integer-truncated magnitudes, first maximum)
+            unsigned long long best = 0;
+            int bj = n;
+            for (int c = k + WV_LANE; c < n; c += WV_NL) {
+                const unsigned long long v = ls_trunc_u64(WMT(k, c));
+                if (v > best) {
+                    best = v;
+                    bj = c;
+                }
+            }
+            wv_argmax(best, bj);
+            const int j = (best == 0) ? k : bj;
+            const double akj = WMT(k, j);
+            WV_SYNC();
+            if (WV_LANE == 0) ipvt[k] = j;
+            if (akj == 0.0) {
+                info = k + 1;
+                continue;
+            }
+            if (j != k && WV_LANE == 0) {
+                WMT(k, j) = WMT(k, k);
+                WMT(k, k) = akj;
+            }
+            WV_SYNC();
+            const double t = -1.0 / akj;
+            for (int c = k + 1 + WV_LANE; c < n; c += WV_NL) WMT(k, c) = t * WMT(k, c);
+            WV_SYNC();
+            for (int r = k + 1 + WV_LANE; r < n; r += WV_NL) {
+                const double tr = WMT(r, j);
+                if (j != k) {
+                    WMT(r, j) = WMT(r, k);
+                    WMT(r, k) = tr;
+                }
+                for (int c = k + 1; c < n; c++) WMT(r, c) = tr * WMT(k, c) + WMT(r, c);
+            }
+            WV_SYNC();
+        }
+        if (WV_LANE == 0) ipvt[n - 1] = n - 1;
+        if (WMT(n - 1, n - 1) == 0.0) info = n;
+        WV_SYNC();
+        return info;
+    }
+
+    // dgesl with job = 0, LSODA.cpp:119-144
+    LS_MFN void dgesl(double* b) const
+    {
+        // forward: t_k = sum_{c<k} a[k][c] b[c] accumulated column by column
+        double t[WV_NPL];
+#pragma unroll
+        for (int q = 0; q < WV_NPL; q++) t[q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < WV_NPL; q++) {
+            if (q * WV_NL < n) {
+                for (int cc = 0; cc < WV_NL; cc++) {
+                    const int c = q * WV_NL + cc;
+                    if (c >= n) break;
+                    double bc = 0.0;
+                    if (WV_LANE == cc) {
+                        bc = (b[c] - t[q]) / WMT(c, c);
+                        b[c] = bc;
+                    }
+                    bc = wv_bcast(bc, cc);
+#pragma unroll
+                    for (int q2 = q; q2 < WV_NPL; q2++) {
+                        const int k = WV_LANE + WV_NL * q2;
+                        if (k > c && k < n) t[q2] += WMT(k, c) * bc;
+                    }
+                }
+            }
+        }
+        WV_SYNC();
+        // backward: dot products over ascending c, pivot swaps in between
+        for (int k = n - 2; k >= 0; k--) {
+            double tk = 0.0;
+            for (int c = k + 1; c < n; c++) tk += WMT(k, c) * b[c];
+            WV_SYNC();
+            if (WV_LANE == 0) {
+                const double bk = b[k] + tk;
+                const int j = ipvt[k];
+                if (j != k) {
+                    const double tt = b[j];
+                    b[j] = bk;
+                    b[k] = tt;
+                } else {
+                    b[k] = bk;
+                }
+            }
+            WV_SYNC();
+        }
+    }
+
+    // prja, LSODA.cpp:1633-1696, with fnorm (:1714-1736) and the LU factorisation.
+    // Uses y, savf = f(tn, y), ewt.  Returns ierpj.
+    LS_MFN int prja(double tn, double h, double hl0, double* pp, double& pdnorm)
+    {
+        const double fac0 = norm_ptr(savf);
+        double r0 = 1000.0 * fabs(h) * LS_ETA * ((double)n) * fac0;
+        if (r0 == 0.0) r0 = 1.0;
+        for (int j0 = 0; j0 < n; j0 += WV_NL) {
+            const int j = j0 + WV_LANE;
+            if (j < n) {
+                double* u = ucopy + WV_LANE * ld;
+                for (int i = 0; i < n; i++) u[i] = y[i];
+                const double yj = y[j];
+                const double r = ls_max(LS_SQRTETA * fabs(yj), r0 / ewt[j]);
+                u[j] = yj + r;
+                const double fac = -hl0 / r;
+                double* col = wmT + j * ld;
+                b200ode_user_rhs(tn, u, col, pp);
+                for (int i = 0; i < n; i++) col[i] = (col[i] - savf[i]) * fac;
+            }
+            WV_SYNC();
+        }
+        double an = 0.0;
+        WV_FOR_OWN(i) {
+            double sum = 0.0;
+            for (int j = 0; j < n; j++) sum += fabs(WMT(i, j)) / ewt[j];
+            an = ls_max(an, sum * ewt[i]);
+        }
+        an = wv_max(an);
+        pdnorm = an / fabs(hl0);
+        WV_FOR_OWN(i) WMT(i, i) = WMT(i, i) + 1.0;
+        WV_SYNC();
+        return dgefa() != 0 ? 1 : 0;
+    }
+};
+
+#endif

@@ -1,0 +1,66 @@
+// Batched LSODA for sm_100a: one WARP per trajectory, systems of 9 <= n <= 128
+// equations (BASELINE config 4: stiff method-of-lines problems, n = 64).
+//
+// Replaces, for ensembles, the reference's lsoda_wrapper (src/wrapper.cpp:10-57) and
+// class LSODA (src/LSODA.cpp) where the system is too large for one thread: the dense
+// Jacobian (n RHS evaluations, LSODA.cpp:1663-1691), its LU factorisation (dgefa,
+// :173-231) and the triangular solves (dgesl, :110-170) dominate, and they are what the
+// 32 lanes share (lsoda_vec_warp.cuh).  The solver's control flow is the same code as
+// the thread-per-trajectory kernel's (lsoda_core.cuh), executed redundantly by every
+// lane on identical scalars: no divergence, no inter-lane communication for decisions.
+//
+//  * one block = one warp; a persistent grid pulls trajectories from a global counter;
+//  * all solver storage of the trajectory in dynamic shared memory
+//    (B200ODE_LSODAW_DOUBLES(n) doubles: 58.9 KB at n = 64 -> 3 warps per SM); nothing
+//    of it ever touches HBM;
+//  * method-coefficient tables in constant memory (every lane reads the same entry);
+//  * `data` is passed to the RHS by address (the record stays in global memory / L1);
+//  * n is a run-time argument: one image serves every size.
+#include "b200ode_device_nosize.cuh"
+#include "lsoda_vec_warp.cuh"
+
+__constant__ B200LsodaTables b200_lsoda_tables = B200_LSODA_TABLES_INIT;
+
+extern "C" __global__ void __launch_bounds__(32)
+b200ode_lsodaw_kernel(const B200OdeLaunch L)
+{
+    extern __shared__ double b200_smem[];
+    const B200LsodaTables* T = &b200_lsoda_tables;
+    const int n = L.neq;
+    LsWarpVec v;
+    v.attach(b200_smem, n);
+    const int nt = L.nt;
+    const double* __restrict__ te = L.t_eval;
+    // wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130)
+    const unsigned long long mxstep_u = (unsigned long long)(long long)L.mxstep;
+    for (;;) {
+        long long b = 0;
+        if (WV_LANE == 0) b = b200ode_fetch(L.next);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= L.B) break;
+        double* pp = reinterpret_cast<double*>(const_cast<char*>(L.data + b * L.data_stride));
+        double* usol = L.usol + (size_t)b * (size_t)nt * (size_t)n;
+        LsLane s;
+        LsRun R;
+        bool done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te, usol, L.rtol, L.atol);
+        while (!done)
+            done = ls_advance(s, R, v, T, pp, nt, te, usol, L.rtol, L.atol, mxstep_u,
+                              L.exit_on_warning, 0xffffffffu);
+        if (WV_LANE == 0) {
+            // wrapper.cpp:41-45: istate <= 0 -> success = 0
+            L.success[b] = (R.istate > 0) ? 1 : 0;
+            if (L.counters) {
+                int* c = L.counters + b * B200ODE_NCOUNTERS_DEV;
+                c[0] = s.nst;
+                c[1] = s.nfe;
+                c[2] = s.nje;
+                c[3] = R.nswitch;
+                c[4] = s.nqu;
+                c[5] = R.istate;
+                c[6] = R.row;
+                c[7] = s.meth;
+            }
+        }
+        __syncwarp();
+    }
+}

@@ -35,6 +35,24 @@ def robertson_rhs(t, u, du, p):
     du[2] = k2 * u[1] ** 2
 
 
+def brusselator_rhs(t, u, du, p):
+    # this repository's n = 64 method-of-lines problem (oracle/rhs_builtin.c, same operation order)
+    A = p[0]
+    B = p[1]
+    D = p[2]
+    m = 32
+    for i in range(m):
+        uu = u[i]
+        v = u[m + i]
+        ul = A if i == 0 else u[i - 1]
+        ur = A if i == m - 1 else u[i + 1]
+        vl = B if i == 0 else u[m + i - 1]
+        vr = B if i == m - 1 else u[m + i + 1]
+        uuv = uu * uu * v
+        du[i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur)
+        du[m + i] = B * uu - uuv + D * (vl - 2.0 * v + vr)
+
+
 def growth_rhs(t, u, du, p):
     # tests/test_exit_on_warning.py:13-14
     du[0] = p[0] * u[0] * np.sin(t)
@@ -88,3 +106,20 @@ def robertson_sweep(B, seed=0):
     """[0.04, 3e7, 1e4] * 10^U(-0.5, 0.5)."""
     rng = np.random.default_rng(seed)
     return np.array([0.04, 3e7, 1e4]) * 10.0 ** rng.uniform(-0.5, 0.5, (B, 3))
+
+
+def brusselator_sweep(B, seed=0):
+    """Config C4 (no reference shape exists; defined in DESIGN.md): 1-D Brusselator on 32
+    cells, n = 64, data = [A, B, D] with A~U(0.8,1.2), B~U(2.5,3.5), D = 10^U(1.5,3.5) (stiff:
+    LSODA switches to BDF, 15-25 Jacobians of 64 RHS evaluations each)."""
+    rng = np.random.default_rng(seed)
+    p = np.empty((B, 3))
+    p[:, 0] = rng.uniform(0.8, 1.2, B)
+    p[:, 1] = rng.uniform(2.5, 3.5, B)
+    p[:, 2] = 10.0 ** rng.uniform(1.5, 3.5, B)
+    return p
+
+
+def brusselator_u0(A=1.0, Bp=3.0, m=32):
+    x = (np.arange(m) + 1) / (m + 1.0)
+    return np.concatenate([A + 0.5 * np.sin(np.pi * x), Bp / A + 0.5 * np.sin(2 * np.pi * x)])

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
 // Compiles the LSODA device core (numbalsoda_b200/csrc/lsoda_core.cuh) as host C++ for
-// one system size (-DB200_NEQ=n) so that its restated control flow can be compared
+// one system size (-DB200_NEQ=n, thread backend) or any size (-DB200_WARP_BACKEND) so that its restated control flow can be compared
 // with the CPU oracle bit for bit in a container without a GPU
 // (tests/test_lsoda_core_host.py).  Build: g++ -O2 -ffp-contract=off -mfma.
 #include <cstddef>
@@ -14,8 +14,14 @@ static inline long long b200ode_user_rhs(double t, double* u, double* du, double
     return 0;
 }
 
+#ifdef B200_WARP_BACKEND
+// warp-per-trajectory backend, one emulated lane, any neq <= 128
+#include <vector>
+#include "../numbalsoda_b200/csrc/lsoda_vec_warp.cuh"
+#else
 #define LS_STRIDE 1
-#include "../numbalsoda_b200/csrc/lsoda_core.cuh"
+#include "../numbalsoda_b200/csrc/lsoda_vec_thread.cuh"
+#endif
 
 static const B200LsodaTables g_tables = B200_LSODA_TABLES_INIT;
 
@@ -25,21 +31,34 @@ extern "C" void lsoda_core_host(rhs_fn f, int neq, const double* u0, void* data,
                                 const double* teval, double* usol, double rtol, double atol,
                                 int mxstep, int* success, int exit_on_warning, int* counters)
 {
+    g_rhs = f;
+    LsLane s;
+    LsRun R;
+#ifdef B200_WARP_BACKEND
+    if (neq < 1 || neq > WV_NMAX) {
+        *success = -99;
+        return;
+    }
+    std::vector<double> store(B200ODE_LSODAW_DOUBLES(neq), 0.0);
+    LsWarpVec v;
+    v.attach(store.data(), neq);
+#else
     if (neq != N) {
         *success = -99;
         return;
     }
-    g_rhs = f;
     double yh[13 * N], wm[N * N];
     memset(yh, 0, sizeof yh);
     memset(wm, 0, sizeof wm);
-    LsLane s;
-    LsRun R;
+    LsThreadVec v;
+    v.yhp = yh;
+    v.wmp = wm;
+#endif
     double* pp = static_cast<double*>(data);
-    bool done = ls_begin(s, R, yh, u0, pp, nt, teval, usol, rtol, atol);
+    bool done = ls_begin(s, R, v, u0, pp, nt, teval, usol, rtol, atol);
     const unsigned long long mxstep_u = (unsigned long long)(long long)mxstep;
     while (!done)
-        done = ls_advance(s, R, yh, wm, &g_tables, pp, nt, teval, usol, rtol, atol, mxstep_u,
+        done = ls_advance(s, R, v, &g_tables, pp, nt, teval, usol, rtol, atol, mxstep_u,
                           exit_on_warning, 0u);
     *success = R.istate > 0 ? 1 : 0;
     if (counters) {

@@ -254,3 +254,78 @@ def test_device_resident_entry_point():
     assert bool((ok == 1).all()) and np.array_equal(usol.cpu().numpy(), ref)
     info = h.kernel_info()
     assert info["local_bytes"] == 0 and info["launches"] >= 1
+
+
+# ---------------------------------------------------------------- warp-per-trajectory kernel
+def test_warp_kernel_brusselator_n64_strict_bitwise():
+    """BASELINE config 4: n = 64 stiff method-of-lines sweep, one warp per trajectory
+    (shared-memory Jacobian / LU): states and counters bit-for-bit vs the oracle."""
+    nb = _nb()
+    B = 96
+    P = pr.brusselator_sweep(B)
+    u0 = np.stack([pr.brusselator_u0(P[b, 0], P[b, 1]) for b in range(B)])
+    te = np.linspace(0.0, 10.0, 100)
+    us, ok, cnt = nb.lsoda(nb.builtin("brusselator1d"), u0, te, P, 1e-6, 1e-8, strict=True,
+                           counters=True)
+    ref, okr, cr = orc.solve_batch("lsoda", orc.builtin_rhs("brusselator1d"), u0, te, P, 1e-6, 1e-8)
+    assert ok.all() and okr.all() and us.shape == (B, 100, 64)
+    assert np.array_equal(cnt, cr)
+    assert np.array_equal(us, ref)
+    assert (cnt[:, 2] >= 5).all() and (cnt[:, 7] == 2).all()  # stiff: Jacobians, ends in BDF
+    # fast mode (FMA): close to the strict result
+    us2, ok2 = nb.lsoda(nb.builtin("brusselator1d"), u0, te, P, 1e-6, 1e-8)
+    assert ok2.all()
+    err = np.abs(us2 - ref) / (1e-6 * np.abs(ref) + 1e-8)
+    print("fast-mode max weighted error (n=64): %.3g" % err.max())
+    assert err.max() <= 100.0
+
+
+def test_warp_kernel_numba_rhs_and_other_sizes():
+    """numba-compiled RHS with a loop (u / du are shared-memory pointers in this kernel),
+    and sizes that are not multiples of the warp: a stiff linear chain of n = 9, 20, 33."""
+    import numba
+    nb = _nb()
+    P = pr.brusselator_sweep(8, seed=7)
+    u0 = pr.brusselator_u0()
+    te = np.linspace(0.0, 10.0, 30)
+    us, ok, cnt = nb.lsoda(pr.brusselator_rhs, u0, te, P, 1e-6, 1e-8, strict=True, counters=True)
+    ref, okr, cr = orc.solve_batch("lsoda", pr.cfunc_address(pr.brusselator_rhs), u0, te, P, 1e-6, 1e-8)
+    assert ok.all() and np.array_equal(cnt, cr) and np.array_equal(us, ref)
+
+    def chain(t, u, du, p):
+        n = int(p[1])
+        k = p[0]
+        du[0] = -k * u[0] + 0.5 * u[1] * u[1]
+        for i in range(1, n - 1):
+            du[i] = k * (u[i - 1] - u[i]) / (1.0 + i) + 0.1 * u[i + 1] - 0.1 * u[i] * u[i]
+        du[n - 1] = k * (u[n - 2] - u[n - 1]) / n
+
+    cf = numba.cfunc(nb.lsoda_sig)(chain)
+    for n in (9, 20, 33):
+        u0n = 1.0 + 0.1 * np.arange(n)
+        Pn = np.array([[50.0 * (1 + b), float(n)] for b in range(5)])
+        ten = np.linspace(0.0, 5.0, 11)
+        us, ok, cnt = nb.lsoda(chain, u0n, ten, Pn, 1e-7, 1e-9, strict=True, counters=True)
+        ref, okr, cr = orc.solve_batch("lsoda", cf.address, u0n, ten, Pn, 1e-7, 1e-9)
+        assert list(ok) == list(okr) and np.array_equal(cnt, cr), n
+        for b in range(5):
+            assert same(us[b, :cr[b, 6]], ref[b, :cr[b, 6]]), (n, b)
+
+
+def test_warp_kernel_failures_and_edge_cases():
+    nb = _nb()
+    f, fo = nb.builtin("brusselator1d"), orc.builtin_rhs("brusselator1d")
+    u0, d = pr.brusselator_u0(), np.array([1.0, 3.0, 300.0])
+    cases = [dict(te=np.linspace(0, 10, 11), rtol=1e-6, atol=1e-8, mxstep=5),
+             dict(te=np.array([0.0]), rtol=1e-6, atol=1e-8),
+             dict(te=np.array([0.0, 0.0, 1.0]), rtol=1e-6, atol=1e-8),
+             dict(te=np.array([0.0, 1.0, 0.5]), rtol=1e-6, atol=1e-8),
+             dict(te=np.linspace(0, 10, 11), rtol=-1.0, atol=1e-8),
+             dict(te=np.linspace(0, 10, 11), rtol=0.0, atol=0.0),
+             dict(te=np.linspace(0, 1, 5), rtol=1e-17, atol=1e-20)]
+    for c in cases:
+        kw = dict(rtol=c["rtol"], atol=c["atol"], mxstep=c.get("mxstep", 10000))
+        us, ok, cnt = nb.lsoda(f, u0, c["te"], d, strict=True, counters=True, **kw)
+        ref, okr, st = orc.lsoda(fo, u0, c["te"], d, **kw)
+        assert ok == okr and list(cnt) == _cnt(st), (c, list(cnt), _cnt(st))
+        assert same(us[:st.rows], ref[:st.rows]), c

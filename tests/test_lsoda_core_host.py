@@ -17,20 +17,36 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "lsoda_core_host.cpp")
 HDRS = [os.path.join(ROOT, "numbalsoda_b200", "csrc", f)
-        for f in ("lsoda_core.cuh", "lsoda_tables.cuh", "b200ode_pow.cuh")]
+        for f in ("lsoda_core.cuh", "lsoda_vec_thread.cuh", "lsoda_vec_warp.cuh", "lsoda_tables.cuh",
+                  "b200ode_pow.cuh") if os.path.exists(os.path.join(ROOT, "numbalsoda_b200", "csrc", f))]
 _libs = {}
 
 
 def core(n):
+    """n = system size for the thread backend, "warp" for the warp backend (any size)."""
     if n not in _libs:
         os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
-        so = os.path.join(HERE, "_build", "liblsoda_core_n%d.so" % n)
+        so = os.path.join(HERE, "_build", "liblsoda_core_%s.so" % ("n%d" % n if n != "warp" else n))
         deps = [SRC] + HDRS
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            flag = "-DB200_NEQ=%d" % n if n != "warp" else "-DB200_WARP_BACKEND"
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared",
-                                   "-Wno-unknown-pragmas", "-DB200_NEQ=%d" % n, "-o", so, SRC])
+                                   "-Wno-unknown-pragmas", flag, "-o", so, SRC])
         _libs[n] = ct.CDLL(so)
     return _libs[n]
+
+
+BACKEND = {"thread": lambda n: core(n), "warp": lambda n: core("warp")}
+_backend = "thread"
+
+
+@pytest.fixture(params=["thread", "warp"], autouse=True)
+def backend(request):
+    """Every test runs on both vector backends of the LSODA core."""
+    global _backend
+    _backend = request.param
+    yield request.param
+    _backend = "thread"
 
 
 def run_core(fptr, u0, te, data, rtol, atol, mxstep=10000, exit_on_warning=False):
@@ -41,7 +57,7 @@ def run_core(fptr, u0, te, data, rtol, atol, mxstep=10000, exit_on_warning=False
     ok = ct.c_int(999)
     cnt = (ct.c_int * 8)()
     p = lambda a: a.ctypes.data_as(ct.c_void_p)  # noqa: E731
-    core(len(u0)).lsoda_core_host(ct.c_void_p(fptr), len(u0), p(u0), p(data), len(te), p(te),
+    BACKEND[_backend](len(u0)).lsoda_core_host(ct.c_void_p(fptr), len(u0), p(u0), p(data), len(te), p(te),
                                   p(us), ct.c_double(rtol), ct.c_double(atol), int(mxstep),
                                   ct.byref(ok), int(exit_on_warning), cnt)
     return us, ok.value == 1, list(cnt)
@@ -80,7 +96,7 @@ def test_tables_equal_cfode_of_the_oracle():
         _fields_ = [("elco", ct.c_double * 14 * 13 * 2), ("tesco", ct.c_double * 4 * 13 * 2),
                     ("cm1", ct.c_double * 13), ("cm2", ct.c_double * 6), ("sm1", ct.c_double * 13),
                     ("conit", ct.c_double * 13), ("pad", ct.c_double * 3)]
-    lib = core(2)
+    lib = BACKEND[_backend](2)
     lib.lsoda_core_tables.restype = ct.POINTER(T)
     t = lib.lsoda_core_tables().contents
     assert np.array_equal(np.array(t.elco[0]), np.array(e1))
@@ -182,3 +198,21 @@ def test_stiff_problems_with_pivoting_and_failures():
         ref, okr, st = orc.lsoda(f, u0, te, d, rtol, atol)
         assert ok == okr and cnt == ocnt(st), (cnt, ocnt(st))
         assert same(us[:st.rows], ref[:st.rows])
+
+
+def test_brusselator_n64_bitwise():
+    """BASELINE config 4's problem (n = 64 method of lines, stiff): warp backend only."""
+    if _backend != "warp":
+        pytest.skip("n = 64 is the warp backend's range")
+    f = orc.builtin_rhs("brusselator1d")
+    rng = np.random.default_rng(4)
+    te = np.linspace(0.0, 10.0, 21)
+    for k in range(6):
+        A, B, D = 1.0 + 0.2 * rng.uniform(-1, 1), 3.0 + 0.5 * rng.uniform(-1, 1), 10.0 ** rng.uniform(1.5, 3.5)
+        x = (np.arange(32) + 1) / 33.0
+        u0 = np.concatenate([A + 0.5 * np.sin(np.pi * x), B / A + 0.5 * np.sin(2 * np.pi * x)])
+        us, ok, cnt = run_core(f, u0, te, [A, B, D], 1e-6, 1e-8)
+        ref, okr, st = orc.lsoda(f, u0, te, [A, B, D], 1e-6, 1e-8)
+        assert ok == okr and cnt == ocnt(st), (k, cnt, ocnt(st))
+        assert same(us[:st.rows], ref[:st.rows]), k
+        assert cnt[2] > 0 and cnt[7] == 2  # Jacobians were needed: it is stiff
