@@ -92,6 +92,13 @@ def lsoda_flops(cnt, n, f_rhs, nt):
     return float(fl.sum())
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per trajectory of the solver kernel, from the
+# `ncu --set full` captures summarised under profiles/ (bytes, capture, trajectories in it)
+NCU_TRAFFIC = {
+    "lorenz_dop853": (848.322304e6 + 13.346549e9, "profiles/r1_dop853_v1_queue_8warps.txt", 524288),
+    "robertson_lsoda": (17.270784e6 + 280.736e6, "profiles/r1_lsoda_v2_flat_synced.txt", 131072),
+}
+
 F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6, "brusselator1d": 608}
 
 
@@ -240,6 +247,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "ours" and a.gpus != world and world == 1 and a.gpus > 1:
+        # python bench.py --gpus N without torchrun: re-launch one rank per GPU
+        import socket
+        sk = socket.socket()
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+        sk.close()
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   "--nproc-per-node", str(a.gpus), "--master-addr", "127.0.0.1",
+                                   "--master-port", str(port)] + sys.argv)
     cfg = {"workload": "%s: %s n=%d sweep, %s, t_eval=linspace(%g,%g,%d), rtol=atol=%g, "
                        "%d trajectories per GPU" % (a.workload, wl["rhs"], wl["n"], wl["solver"],
                                                     *wl["t_eval"], wl["rtol"], wl["batch"]),
@@ -276,16 +293,15 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     import numbalsoda_b200 as nb
     from numbalsoda_b200 import _lib
+    from numbalsoda_b200._dist import Ranks
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    ranks = Ranks(backend="nccl" if world > 1 else None)  # plumbing only: no data-path collective
 
     B, n, nt = wl["batch"], wl["n"], wl["t_eval"][2]
     solver = _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
@@ -316,8 +332,7 @@ def main():
         peak_tf, peak_src, peak_raw = fp64_peak()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        ranks.barrier()
         torch.cuda.synchronize()
 
     for _ in range(max(a.warmup, 0)):
@@ -341,13 +356,8 @@ def main():
     launches = h.kernel_info()["launches"] - launches0
     ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     dev_s = sum(ms) / 1e3
-    if world > 1:
-        t = torch.tensor([dev_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s_max = float(t.item())
-    else:
-        dev_s_max = dev_s
-    n_ok = int((ok == 1).sum().item())
+    dev_s_max = ranks.max(dev_s)  # every multi-GPU time is the slowest rank's
+    n_ok = int(ranks.sum(int((ok == 1).sum().item())))
     value = world * B * a.steps / dev_s_max
 
     # ---- end to end through the numbalsoda-compatible host API, pinned host buffers
@@ -377,10 +387,7 @@ def main():
             e2e_step()
         barrier()
         te2e = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([te2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            te2e = float(t.item())
+        te2e = ranks.max(te2e)
         e2e = {"value": world * B * ke / te2e, "unit": "traj/s",
                "h2d_bytes_per_step": int(Ph.nbytes + teh.nbytes + 24),
                "d2h_bytes_per_step": int(B * nt * n * 8 + B * 4),
@@ -389,8 +396,7 @@ def main():
         del usolp
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        ranks.close()
         return
 
     cnt_h = cnt.cpu().numpy()
@@ -399,8 +405,11 @@ def main():
     achieved_tf = flops / per_launch_s / 1e12
     peaks = measured_peaks()
     out_bytes = B * (nt * n * 8 + (n + wl["p"]) * 8 + 4)
+    tr = NCU_TRAFFIC.get(a.workload)
     roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+            "frac": achieved_tf / peak_tf if peak_tf else None,
+            "traffic": (tr[0] / tr[2] * B) if tr else None,
+            "traffic_source": ("ncu dram bytes per trajectory x B, %s" % tr[1]) if tr else None,
             "kernel": "b200ode_%s_kernel" % (wl["solver"] + ("w" if wl["n"] > 8 else "")),
             "flops_per_launch": flops, "flops_per_trajectory": flops / B,
             "flop_count": "algorithmic, SURVEY.md 8(d) formulas x per-trajectory counters",
@@ -415,7 +424,7 @@ def main():
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s_max / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg, "mode": "strict" if a.strict else "fast (FMA)",
-            "success_fraction": n_ok / B, "wall_s_timed_region": t_wall,
+            "success_fraction": n_ok / (B * world), "wall_s_timed_region": t_wall,
             "mean_steps_per_trajectory": float(cnt_h[:, 0].mean()),
             "roofline": roof, "clocks": clocks, "gpu_launches": launches,
             "kernel_info": h.kernel_info()}
@@ -426,8 +435,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": kind,
                                 "sample": sample, "seconds": secs}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 if __name__ == "__main__":

@@ -369,6 +369,7 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
     const int kThreads = P->threads;
     const bool warp = warp_kernel(H->solver, H->neq);
     args.neq = H->neq;
+    args.strict = (H->flags & B200ODE_STRICT_FP) ? 1 : 0;
     long long want = warp ? args.B : (args.B + kThreads - 1) / kThreads;
     long long resident = (long long)P->sms * P->blocks_per_sm;
     int grid = (int)std::min(want, resident);

@@ -18,8 +18,9 @@
  * many doubles of dynamic shared memory per warp (lsoda_vec_warp.cuh). */
 #define B200ODE_THREAD_NMAX 8
 #define B200ODE_WARP_NMAX 128
+#define B200ODE_LSODAW_JCOLS 8 /* Jacobian columns evaluated concurrently */
 #define B200ODE_LSODAW_DOUBLES(n) \
-    (17 * (n) + (n) * ((n) + 1) + ((n) < 32 ? (n) : 32) * ((n) + 1) + ((n) + 2) / 2)
+    (18 * (n) + (n) * ((n) + 1) + B200ODE_LSODAW_JCOLS * ((n) + 1) + (n) + 1)
 
 typedef struct B200OdeLaunch {
     long long B;              /* trajectories in this launch */
@@ -35,7 +36,8 @@ typedef struct B200OdeLaunch {
     int mxstep;
     int exit_on_warning;      /* lsoda only */
     int neq;                  /* system size (run-time for the warp-per-trajectory kernel) */
-    int pad_;
+    int strict;               /* handle linked with B200ODE_STRICT_FP: keep the reference's
+                                 summation order everywhere (warp kernel's triangular solves) */
     int* success;             /* [B] 1 / 0, as the reference's *success */
     int* counters;            /* [B,8] or null */
     unsigned long long* next; /* work queue head (zeroed before the launch) */

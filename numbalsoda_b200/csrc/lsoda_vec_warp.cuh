@@ -18,7 +18,7 @@
 //     i, i + 32, ...;
 //   * max-norms and the pivot search: per-lane partial results combined by shuffles
 //     (max and first-arg-max are order independent);
-//   * Jacobian (prja): the n perturbed RHS evaluations are independent -- 32 columns at
+//   * Jacobian (prja): the n perturbed RHS evaluations are independent -- 8 columns at
 //     a time, one per lane, each lane calling the user's RHS on its private copy of y and
 //     writing straight into the matrix column; fnorm's row sums run over j in order, a
 //     lane per row;
@@ -28,9 +28,13 @@
 //     adds a[k][c] * b[c] to its private running sum, which accumulates the terms in the
 //     same order c = 0, 1, ... as the reference's dot product;
 //   * back substitution: the reference's dot products run over ascending c with pivot
-//     swaps in between, which fixes a sequential summation order: kept sequential here
-//     (the one O(n^2) serial chain left; a shuffle-tree variant for the fast mode is a
-//     follow-up);
+//     swaps in between, which fixes a sequential summation order: n^2/2 dependent adds.
+//     Strict mode keeps it (bit parity); the fast mode (`fast`, the default of the
+//     library) factors with full column interchanges -- the swaps are also applied to the
+//     multipliers above the diagonal -- which turns the back substitution into a swap-free
+//     column sweep (n dependent steps, lanes own rows) followed by one permutation, and
+//     multiplies by precomputed reciprocals of the diagonal in the forward sweep.  Same
+//     mathematics, different summation order: last-bit differences only;
 //   * the RHS of a corrector iteration is one call of the user's scalar function: lane 0.
 #ifndef B200ODE_LSODA_VEC_WARP_CUH
 #define B200ODE_LSODA_VEC_WARP_CUH
@@ -74,6 +78,10 @@ LS_FN void wv_argmax(unsigned long long&, int&) {}
 #endif
 
 #define WV_NMAX 128
+// Jacobian columns evaluated concurrently (each needs a private copy of y in shared
+// memory): 8 keeps a trajectory at 47 KB for n = 64, i.e. 4 warps per SM instead of 3,
+// and the n/8 rounds of RHS evaluations stay a small part of prja next to the LU
+#define WV_JCOLS (WV_NL < B200ODE_LSODAW_JCOLS ? WV_NL : B200ODE_LSODAW_JCOLS)
 #define WV_NPL (WV_NMAX / WV_NL)  // rows a lane can own
 #define WV_FOR_OWN(i) for (int i = WV_LANE; i < n; i += WV_NL)
 #define WYH(j, i) yh[((j) - 1) * n + (i)]
@@ -83,21 +91,25 @@ LS_FN void wv_argmax(unsigned long long&, int&) {}
 
 struct LsWarpVec {
     int n, ld;
-    double *yh, *y, *savf, *acor, *ewt, *wmT, *ucopy;
-    int* ipvt;
+    bool fast;  // parallel triangular solves (see above); false = the reference's summation order
+    double *yh, *y, *savf, *acor, *ewt, *rdiag, *wmT, *ucopy;
+    int *ipvt, *perm;
 
-    LS_MFN void attach(double* base, int neq)
+    LS_MFN void attach(double* base, int neq, bool fast_mode)
     {
         n = neq;
         ld = neq + 1;
+        fast = fast_mode;
         yh = base;
         y = yh + 13 * n;
         savf = y + n;
         acor = savf + n;
         ewt = acor + n;
-        wmT = ewt + n;
+        rdiag = ewt + n;
+        wmT = rdiag + n;
         ucopy = wmT + n * ld;
-        ipvt = reinterpret_cast<int*>(ucopy + (n < 32 ? n : 32) * ld);
+        ipvt = reinterpret_cast<int*>(ucopy + B200ODE_LSODAW_JCOLS * ld);
+        perm = ipvt + n;
     }
     LS_MFN int size() const { return n; }
     LS_MFN void sync(unsigned) {}
@@ -297,6 +309,14 @@ struct LsWarpVec {
                 WMT(k, j) = WMT(k, k);
                 WMT(k, k) = akj;
             }
+            if (fast && j != k) {
+                // full column interchange: also the multipliers of the rows above
+                for (int r = WV_LANE; r < k; r += WV_NL) {
+                    const double tr = WMT(r, j);
+                    WMT(r, j) = WMT(r, k);
+                    WMT(r, k) = tr;
+                }
+            }
             WV_SYNC();
             const double t = -1.0 / akj;
             for (int c = k + 1 + WV_LANE; c < n; c += WV_NL) WMT(k, c) = t * WMT(k, c);
@@ -307,6 +327,7 @@ struct LsWarpVec {
                     WMT(r, j) = WMT(r, k);
                     WMT(r, k) = tr;
                 }
+#pragma unroll 4
                 for (int c = k + 1; c < n; c++) WMT(r, c) = tr * WMT(k, c) + WMT(r, c);
             }
             WV_SYNC();
@@ -314,6 +335,26 @@ struct LsWarpVec {
         if (WV_LANE == 0) ipvt[n - 1] = n - 1;
         if (WMT(n - 1, n - 1) == 0.0) info = n;
         WV_SYNC();
+        if (fast) {
+            // reciprocals of the diagonal, and the composition of the interchanges:
+            // x[i] = w[perm[i]] after the swap-free back substitution
+            WV_FOR_OWN(i) {
+                rdiag[i] = 1.0 / WMT(i, i);
+                perm[i] = i;
+            }
+            WV_SYNC();
+            if (WV_LANE == 0) {
+                for (int k = n - 2; k >= 0; k--) {
+                    const int j = ipvt[k];
+                    if (j != k) {
+                        const int pk = perm[k];
+                        perm[k] = perm[j];
+                        perm[j] = pk;
+                    }
+                }
+            }
+            WV_SYNC();
+        }
         return info;
     }
 
@@ -332,7 +373,7 @@ struct LsWarpVec {
                     if (c >= n) break;
                     double bc = 0.0;
                     if (WV_LANE == cc) {
-                        bc = (b[c] - t[q]) / WMT(c, c);
+                        bc = fast ? (b[c] - t[q]) * rdiag[c] : (b[c] - t[q]) / WMT(c, c);
                         b[c] = bc;
                     }
                     bc = wv_bcast(bc, cc);
@@ -345,6 +386,47 @@ struct LsWarpVec {
             }
         }
         WV_SYNC();
+        if (fast) {
+            // swap-free column sweep: once w[c] is final every row above adds its term
+#pragma unroll
+            for (int q = 0; q < WV_NPL; q++) t[q] = 0.0;
+#pragma unroll
+            for (int q = WV_NPL - 1; q >= 0; q--) {
+                if (q * WV_NL < n) {
+                    for (int cc = WV_NL - 1; cc >= 0; cc--) {
+                        const int c = q * WV_NL + cc;
+                        if (c >= n) continue;
+                        double wc = 0.0;
+                        if (WV_LANE == cc) {
+                            wc = b[c] + t[q];
+                            b[c] = wc;
+                        }
+                        wc = wv_bcast(wc, cc);
+#pragma unroll
+                        for (int q2 = 0; q2 <= q; q2++) {
+                            const int r = WV_LANE + WV_NL * q2;
+                            if (r < c) t[q2] += WMT(r, c) * wc;
+                        }
+                    }
+                }
+            }
+            WV_SYNC();
+            // x[i] = w[perm[i]]
+            double x[WV_NPL];
+#pragma unroll
+            for (int q = 0; q < WV_NPL; q++) {
+                const int i = WV_LANE + WV_NL * q;
+                x[q] = (i < n) ? b[perm[i]] : 0.0;
+            }
+            WV_SYNC();
+#pragma unroll
+            for (int q = 0; q < WV_NPL; q++) {
+                const int i = WV_LANE + WV_NL * q;
+                if (i < n) b[i] = x[q];
+            }
+            WV_SYNC();
+            return;
+        }
         // backward: dot products over ascending c, pivot swaps in between
         for (int k = n - 2; k >= 0; k--) {
             double tk = 0.0;
@@ -372,9 +454,9 @@ struct LsWarpVec {
         const double fac0 = norm_ptr(savf);
         double r0 = 1000.0 * fabs(h) * LS_ETA * ((double)n) * fac0;
         if (r0 == 0.0) r0 = 1.0;
-        for (int j0 = 0; j0 < n; j0 += WV_NL) {
+        for (int j0 = 0; j0 < n; j0 += WV_JCOLS) {
             const int j = j0 + WV_LANE;
-            if (j < n) {
+            if (WV_LANE < WV_JCOLS && j < n) {
                 double* u = ucopy + WV_LANE * ld;
                 for (int i = 0; i < n; i++) u[i] = y[i];
                 const double yj = y[j];
@@ -390,6 +472,7 @@ struct LsWarpVec {
         double an = 0.0;
         WV_FOR_OWN(i) {
             double sum = 0.0;
+#pragma unroll 4
             for (int j = 0; j < n; j++) sum += fabs(WMT(i, j)) / ewt[j];
             an = ls_max(an, sum * ewt[i]);
         }

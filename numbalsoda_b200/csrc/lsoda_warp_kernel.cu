@@ -28,7 +28,7 @@ b200ode_lsodaw_kernel(const B200OdeLaunch L)
     const B200LsodaTables* T = &b200_lsoda_tables;
     const int n = L.neq;
     LsWarpVec v;
-    v.attach(b200_smem, n);
+    v.attach(b200_smem, n, L.strict == 0);
     const int nt = L.nt;
     const double* __restrict__ te = L.t_eval;
     // wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130)

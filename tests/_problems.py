@@ -123,3 +123,13 @@ def brusselator_sweep(B, seed=0):
 def brusselator_u0(A=1.0, Bp=3.0, m=32):
     x = (np.arange(m) + 1) / (m + 1.0)
     return np.concatenate([A + 0.5 * np.sin(np.pi * x), Bp / A + 0.5 * np.sin(2 * np.pi * x)])
+
+
+def upper_rhs(t, u, du, p):
+    """Stiff upper-bidiagonal system whose iteration matrix has super-diagonal entries
+    larger than the diagonal: the reference's row-wise pivot search (LSODA.cpp:59-77,
+    :188-224) then really interchanges columns.  p = [a, K, n]."""
+    n = int(p[2])
+    for i in range(n - 1):
+        du[i] = -p[0] * u[i] + p[1] * u[i + 1]
+    du[n - 1] = -p[0] * u[n - 1] + 1.0

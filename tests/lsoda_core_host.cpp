@@ -41,7 +41,8 @@ extern "C" void lsoda_core_host(rhs_fn f, int neq, const double* u0, void* data,
     }
     std::vector<double> store(B200ODE_LSODAW_DOUBLES(neq), 0.0);
     LsWarpVec v;
-    v.attach(store.data(), neq);
+    v.attach(store.data(), neq, (exit_on_warning & 2) != 0);  // bit 1 of the flag: fast solves
+    exit_on_warning &= 1;
 #else
     if (neq != N) {
         *success = -99;

@@ -329,3 +329,24 @@ def test_warp_kernel_failures_and_edge_cases():
         ref, okr, st = orc.lsoda(fo, u0, c["te"], d, **kw)
         assert ok == okr and list(cnt) == _cnt(st), (c, list(cnt), _cnt(st))
         assert same(us[:st.rows], ref[:st.rows]), c
+
+
+@pytest.mark.parametrize("n", [3, 12, 40])
+def test_pivoting_lu_strict_bitwise_and_fast_close(n):
+    """A stiff system whose iteration matrix makes the reference's row-wise pivot search
+    interchange columns (thread kernel n = 3, warp kernel n = 12 / 40): strict mode
+    bit-for-bit; fast mode (warp kernel: interchanges applied to the multipliers,
+    swap-free column sweep, final permutation) close to it."""
+    nb = _nb()
+    B = 7
+    u0 = np.ones(n)
+    P = np.array([[1000.0 * (1 + 0.1 * b), 5000.0, float(n)] for b in range(B)])
+    te = np.linspace(0.0, 2.0, 9)
+    us, ok, cnt = nb.lsoda(pr.upper_rhs, u0, te, P, 1e-6, 1e-9, strict=True, counters=True)
+    ref, okr, cr = orc.solve_batch("lsoda", pr.cfunc_address(pr.upper_rhs), u0, te, P, 1e-6, 1e-9)
+    assert ok.all() and okr.all() and np.array_equal(cnt, cr) and np.array_equal(us, ref)
+    assert (cnt[:, 2] > 0).all()
+    us2, ok2 = nb.lsoda(pr.upper_rhs, u0, te, P, 1e-6, 1e-9)
+    assert ok2.all()
+    err = np.abs(us2 - ref) / (1e-6 * np.abs(ref) + 1e-9)
+    assert err.max() < 50.0, err.max()

@@ -216,3 +216,59 @@ def test_brusselator_n64_bitwise():
         assert ok == okr and cnt == ocnt(st), (k, cnt, ocnt(st))
         assert same(us[:st.rows], ref[:st.rows]), k
         assert cnt[2] > 0 and cnt[7] == 2  # Jacobians were needed: it is stiff
+
+
+def test_warp_backend_fast_solves_close_to_reference_order():
+    """The fast mode's triangular solves (full column interchanges, swap-free column
+    sweep, reciprocal diagonal) are the same mathematics in another summation order:
+    on stiff problems whose LU pivots, results stay within a few error-weight units of
+    the reference-order run and the step counts stay close."""
+    if _backend != "warp":
+        pytest.skip("warp backend only")
+    f = orc.builtin_rhs("brusselator1d")
+    te = np.linspace(0.0, 10.0, 21)
+    P = pr.brusselator_sweep(6, seed=9)
+    u0 = np.ascontiguousarray(pr.brusselator_u0())
+    p = lambda a: a.ctypes.data_as(ct.c_void_p)  # noqa: E731
+    for b in range(6):
+        d = np.ascontiguousarray(P[b])
+        out = []
+        for flag in (0, 2):
+            us = np.full((len(te), 64), np.nan)
+            ok = ct.c_int(999)
+            cnt = (ct.c_int * 8)()
+            core("warp").lsoda_core_host(ct.c_void_p(f), 64, p(u0), p(d), len(te), p(te), p(us),
+                                         ct.c_double(1e-6), ct.c_double(1e-8), 10000, ct.byref(ok),
+                                         flag, cnt)
+            out.append((us, ok.value, list(cnt)))
+        (us0, ok0, c0), (us1, ok1, c1) = out
+        assert ok0 == ok1 == 1
+        err = np.abs(us1 - us0) / (1e-6 * np.abs(us0) + 1e-8)
+        assert err.max() < 5.0, err.max()
+        assert abs(c1[0] - c0[0]) <= 0.1 * c0[0] and c1[2] > 0
+
+
+@pytest.mark.parametrize("n", [3, 12, 40])
+def test_pivoting_problem_bitwise_and_fast_solves(n):
+    """A system whose LU really interchanges columns: bit parity of both backends with
+    the oracle, and the warp backend's fast solves (interchanges applied to the
+    multipliers + one final permutation) against the reference-order result."""
+    if _backend == "thread" and n > 3:
+        pytest.skip("thread backend: n <= 8")
+    fptr = pr.cfunc_address(pr.upper_rhs)
+    u0 = np.ones(n)
+    d = np.array([1000.0, 5000.0, float(n)])
+    te = np.linspace(0.0, 2.0, 9)
+    us, ok, cnt = run_core(fptr, u0, te, d, 1e-6, 1e-9)
+    ref, okr, st = orc.lsoda(fptr, u0, te, d, 1e-6, 1e-9)
+    assert ok == okr and cnt == ocnt(st) and same(us[:st.rows], ref[:st.rows])
+    assert cnt[2] > 0 and cnt[7] == 2
+    if _backend == "warp":
+        p = lambda a: a.ctypes.data_as(ct.c_void_p)  # noqa: E731
+        us1 = np.full((len(te), n), np.nan)
+        okc, c1 = ct.c_int(999), (ct.c_int * 8)()
+        core("warp").lsoda_core_host(ct.c_void_p(fptr), n, p(u0), p(d), len(te), p(te), p(us1),
+                                     ct.c_double(1e-6), ct.c_double(1e-9), 10000, ct.byref(okc), 2, c1)
+        assert okc.value == 1
+        err = np.abs(us1 - ref) / (1e-6 * np.abs(ref) + 1e-9)
+        assert err.max() < 20.0, err.max()

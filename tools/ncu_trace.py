@@ -16,7 +16,7 @@ thr = float(sys.argv[5]) if len(sys.argv) > 5 else 3.0
 import numbalsoda_b200 as nb  # noqa: E402
 from numbalsoda_b200 import _lib  # noqa: E402
 
-h = nb.get_handle(nb.builtin(rhs), _lib.LSODA if solver == "lsoda" else _lib.DOP853, neq)
+h = nb.get_handle(nb.builtin(rhs), _lib.LSODA if solver.startswith("lsoda") else _lib.DOP853, neq)
 open("/tmp/_k.cubin", "wb").write(h.cubin())
 kname = "b200ode_%s_kernel" % solver
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
