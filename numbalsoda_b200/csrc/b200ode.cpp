@@ -321,7 +321,7 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
                 if (cfgv[0] < 32 || cfgv[1] != B200ODE_DOP853_QFIELDS(H->neq))
                     return fail(B200ODE_ECUDA, "dop853 image reports an inconsistent queue geometry");
                 P.qcap = cfgv[0];
-                P.dyn_smem = ((P.threads / 32) * cfgv[1] * cfgv[0] + 4) * (int)sizeof(double);
+                P.dyn_smem = cfgv[5] * (int)sizeof(double);
             } else {
                 P.dyn_smem = cfgv[0] * (int)sizeof(double);
             }

@@ -268,6 +268,11 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
 #define SPAN_XEND span[1]
 #define SPAN_HMAX span[2]
 #define SPAN_POSNEG span[3]
+    // solout's xout = t_eval[min(row, nt-1)] of this lane's trajectory, cached in shared
+    // memory: t_eval is read once per output row instead of once per step (ncu,
+    // profiles/r1_dop853_v2: the two t_eval loads were 12 % of the stall samples), at no
+    // cost in registers (the kernel sits at the 168-register bound of 3 blocks per SM)
+#define XOUT span[4 + threadIdx.x]
 
     double y[N], y1[N], k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], k8[N], k9[N], k10[N];
     double pl[STAGED ? B200ODE_NPMAX : 1];
@@ -342,9 +347,9 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                 }
                 // first solout call (c_interface :56-58): xout = teval(1), nt = 1.  From here
                 // on xout is always t_eval[min(row, nt-1)] (it keeps its last value once
-                // every row is written, c_interface :66-68), so it is read from t_eval when
-                // needed instead of being carried in registers.
+                // every row is written, c_interface :66-68).
                 row = 0;
+                XOUT = x;
             }
         }
 
@@ -445,12 +450,17 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     naccpt++;
                     b200ode_user_rhs(xph, k5, k4, pp);
                     // (the stiffness detector, module :631-655, only prints: iprint /= 0)
-                    if (te[row < nt ? row : nt - 1] <= xph) {  // event: xout <= xph, module :657
+                    if (XOUT <= xph) {  // event: xout <= xph, module :657
                         // dense output is prepared for this step: module :658-705 costs
                         // 3 RHS evaluations; solout writes every row with t_eval <= xph
                         nevent++;
                         row_lo = row;
-                        while (row < nt && te[row] <= xph) row++;
+                        double xo;
+                        do {
+                            row++;
+                            xo = te[row < nt ? row : nt - 1];
+                        } while (row < nt && xo <= xph);
+                        XOUT = xo;
                         push = row > row_lo;
                     }
                     if (flags & F_LAST) {
@@ -554,4 +564,5 @@ extern "C" __global__ void b200ode_dop853_config(int* out)
     out[2] = B200_MINBLOCKS;
     out[3] = N;
     out[4] = B200_THREADS;
+    out[5] = (B200_THREADS / 32) * QF * QCAP + 4 + B200_THREADS;  // doubles of dynamic shared memory
 }
