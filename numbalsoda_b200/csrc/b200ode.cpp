@@ -19,6 +19,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -436,11 +438,6 @@ extern "C" int b200ode_lsoda_batched_device(b200ode_rhs_t H, long long B, int ne
 
 // ---------------------------------------------------------------- host-buffer path
 namespace {
-struct DevBuf {
-    CUdeviceptr p = 0;
-    ~DevBuf() { if (p && g_drv.ok) g_drv.cuMemFree_v2(p); }
-    int alloc(size_t n) { CU(cuMemAlloc_v2(&p, n ? n : 1)); return 0; }
-};
 struct Stream {
     CUstream s = nullptr;
     ~Stream() { if (s && g_drv.ok) g_drv.cuStreamDestroy_v2(s); }
@@ -453,8 +450,81 @@ struct Event {
 };
 }  // namespace
 
-// The ensemble is processed in chunks of trajectories with two output buffers:
-// while chunk c integrates, the rows of chunk c-1 travel back over PCIe.
+// Device scratch memory is kept between calls (per device, grow-only): cuMemAlloc /
+// cuMemFree of gigabytes cost milliseconds each and serialise with running work.
+namespace {
+struct ScratchBlock {
+    CUdeviceptr p = 0;
+    size_t size = 0;
+    bool busy = false;
+};
+struct ScratchPool {
+    std::mutex mu;
+    std::map<int, std::vector<ScratchBlock>> blocks;  // by device
+};
+ScratchPool g_pool;
+
+// One allocation carved into the buffers of a call; returned to the pool on scope exit.
+struct Scratch {
+    int device = -1;
+    size_t index = 0;
+    CUdeviceptr base = 0;
+    size_t used = 0, size = 0;
+    bool pooled = false;
+    int acquire(int dev, size_t bytes)
+    {
+        device = dev;
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        auto& v = g_pool.blocks[dev];
+        for (size_t i = 0; i < v.size(); i++)
+            if (!v[i].busy && v[i].size >= bytes) {
+                v[i].busy = true;
+                index = i, base = v[i].p, size = v[i].size, pooled = true;
+                return 0;
+            }
+        for (size_t i = 0; i < v.size(); i++)
+            if (!v[i].busy) {  // too small: replace it
+                g_drv.cuMemFree_v2(v[i].p);
+                v[i].p = 0, v[i].size = 0;
+                CU(cuMemAlloc_v2(&v[i].p, bytes));
+                v[i].size = bytes, v[i].busy = true;
+                index = i, base = v[i].p, size = bytes, pooled = true;
+                return 0;
+            }
+        ScratchBlock b;
+        CU(cuMemAlloc_v2(&b.p, bytes));
+        b.size = bytes, b.busy = true;
+        v.push_back(b);
+        index = v.size() - 1, base = b.p, size = bytes, pooled = true;
+        return 0;
+    }
+    CUdeviceptr take(size_t bytes)
+    {
+        CUdeviceptr p = base + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return p;
+    }
+    ~Scratch()
+    {
+        if (!pooled) return;
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        g_pool.blocks[device][index].busy = false;
+    }
+};
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+static double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+}  // namespace
+
+// Host-buffer entry point.  The ensemble is cut into chunks; chunk c integrates on one
+// of two kernel streams while the rows of chunk c-1 travel back over PCIe on the copy
+// stream and chunk c+1's blocks move onto SMs as chunk c's blocks retire (each chunk is
+// a persistent grid, so the tail of one launch is filled by the head of the next).
+// Output buffers form a ring of three (kernel c, kernel c+1, copy c-1).
 static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const double* u0,
                       long long u0_stride, const void* data, long long data_stride, int np,
                       int nt, const double* teval, double* usol, double rtol, double atol,
@@ -473,94 +543,121 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
         }
         return 0;
     }
+    const bool trace = getenv("B200ODE_TRACE") != nullptr;
+    const double t0 = now_ms();
     PerDevice* P;
     rc = device_state(H, device, &P);
     if (rc) return rc;
 
     const size_t row_bytes = sizeof(double) * (size_t)nt * (size_t)neq;
-    size_t free_b = 0, total_b = 0;
-    CU(cuMemGetInfo_v2(&free_b, &total_b));
-    size_t target = std::min<size_t>((size_t)2 << 30, free_b / 4);
-    long long chunk = (long long)std::max<size_t>(1, target / std::max<size_t>(row_bytes, 1));
-    // keep every SM busy within a chunk where the ensemble allows it
-    chunk = std::max<long long>(chunk, std::min<long long>(B, (long long)P->sms * P->blocks_per_sm *
-                                                               (warp_kernel(solver, neq) ? 1 : P->threads)));
-    chunk = std::min(chunk, B);
+    const size_t per_traj = row_bytes + sizeof(int) + (counters ? sizeof(int) * B200ODE_NCOUNTERS : 0);
     // record size: |data_stride| bytes, or np doubles when data_stride == 0
     const size_t rec = data_stride != 0 ? (size_t)(data_stride > 0 ? data_stride : -data_stride)
                                         : (size_t)(np > 0 ? np * 8 : 0);
-
-    Stream sk, sc;
-    if ((rc = sk.create()) || (rc = sc.create())) return rc;
-    DevBuf d_te, d_u0, d_data, d_usol[2], d_ok[2], d_cnt[2];
-    Event ev_kernel[2], ev_copied[2];
-    if ((rc = d_te.alloc(sizeof(double) * nt))) return rc;
-    if ((rc = d_u0.alloc(sizeof(double) * neq * (size_t)(u0_stride ? B : 1)))) return rc;
     const size_t data_bytes = data ? (data_stride > 0 ? (size_t)data_stride * (size_t)B : rec) : 0;
-    if ((rc = d_data.alloc(data_bytes))) return rc;
-    const int nbuf = chunk < B ? 2 : 1;
+    const size_t in_bytes = align256(sizeof(double) * nt) +
+                            align256(sizeof(double) * neq * (size_t)(u0_stride ? B : 1)) +
+                            align256(data_bytes);
+    // chunk size: at least 4 trajectories per resident lane (a persistent grid needs a few
+    // per lane to balance), about 1/8 of the ensemble, at most 1 GiB of rows per buffer
+    // (when PCIe binds, what is exposed is the first chunk's kernel and nothing else)
+    const long long resident = (long long)P->sms * P->blocks_per_sm * (warp_kernel(solver, neq) ? 1 : P->threads);
+    size_t free_b = 0, total_b = 0;
+    CU(cuMemGetInfo_v2(&free_b, &total_b));
+    long long chunk = std::max<long long>(4 * resident, (B + 7) / 8);
+    const size_t cap = std::min<size_t>((size_t)1 << 30, std::max<size_t>(free_b / 8, (size_t)64 << 20));
+    chunk = std::min<long long>(chunk, (long long)std::max<size_t>(1, cap / per_traj));
+    chunk = std::max<long long>(1, std::min(chunk, B));
+    const long long nchunks = (B + chunk - 1) / chunk;
+    const int nbuf = (int)std::min<long long>(nchunks, 3);
+
+    Scratch mem;
+    const size_t out_bytes = align256(row_bytes * (size_t)chunk) + align256(sizeof(int) * (size_t)chunk) +
+                             (counters ? align256(sizeof(int) * B200ODE_NCOUNTERS * (size_t)chunk) : 0);
+    if ((rc = mem.acquire(device, in_bytes + out_bytes * nbuf + 4096))) return rc;
+    const CUdeviceptr d_te = mem.take(sizeof(double) * nt);
+    const CUdeviceptr d_u0 = mem.take(sizeof(double) * neq * (size_t)(u0_stride ? B : 1));
+    const CUdeviceptr d_data = mem.take(data_bytes);
+    CUdeviceptr d_usol[3], d_ok[3], d_cnt[3] = {0, 0, 0};
     for (int i = 0; i < nbuf; i++) {
-        if ((rc = d_usol[i].alloc(row_bytes * (size_t)chunk))) return rc;
-        if ((rc = d_ok[i].alloc(sizeof(int) * (size_t)chunk))) return rc;
-        if (counters && (rc = d_cnt[i].alloc(sizeof(int) * B200ODE_NCOUNTERS * (size_t)chunk))) return rc;
-        if ((rc = ev_kernel[i].create()) || (rc = ev_copied[i].create())) return rc;
+        d_usol[i] = mem.take(row_bytes * (size_t)chunk);
+        d_ok[i] = mem.take(sizeof(int) * (size_t)chunk);
+        if (counters) d_cnt[i] = mem.take(sizeof(int) * B200ODE_NCOUNTERS * (size_t)chunk);
     }
-    CU(cuMemcpyHtoDAsync_v2(d_te.p, teval, sizeof(double) * nt, sk.s));
+    Stream sk[2], sc;
+    if ((rc = sk[0].create()) || (rc = sk[1].create()) || (rc = sc.create())) return rc;
+    Event ev_in, ev_kernel[3], ev_copied[3];
+    if ((rc = ev_in.create())) return rc;
+    for (int i = 0; i < nbuf; i++)
+        if ((rc = ev_kernel[i].create()) || (rc = ev_copied[i].create())) return rc;
+    const double t1 = now_ms();
+
+    CU(cuMemcpyHtoDAsync_v2(d_te, teval, sizeof(double) * nt, sk[0].s));
     if (u0_stride) {
         // gather rows if the caller's stride is wider than neq
         if (u0_stride == neq) {
-            CU(cuMemcpyHtoDAsync_v2(d_u0.p, u0, sizeof(double) * neq * (size_t)B, sk.s));
+            CU(cuMemcpyHtoDAsync_v2(d_u0, u0, sizeof(double) * neq * (size_t)B, sk[0].s));
         } else {
             for (long long b = 0; b < B; b++)
-                CU(cuMemcpyHtoDAsync_v2(d_u0.p + sizeof(double) * neq * (size_t)b,
-                                        u0 + b * u0_stride, sizeof(double) * neq, sk.s));
+                CU(cuMemcpyHtoDAsync_v2(d_u0 + sizeof(double) * neq * (size_t)b, u0 + b * u0_stride,
+                                        sizeof(double) * neq, sk[0].s));
         }
     } else {
-        CU(cuMemcpyHtoDAsync_v2(d_u0.p, u0, sizeof(double) * neq, sk.s));
+        CU(cuMemcpyHtoDAsync_v2(d_u0, u0, sizeof(double) * neq, sk[0].s));
     }
-    if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data.p, data, data_bytes, sk.s));
+    if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data, data, data_bytes, sk[0].s));
+    CU(cuEventRecord(ev_in.e, sk[0].s));
+    CU(cuStreamWaitEvent(sk[1].s, ev_in.e, 0));
 
-    long long nchunks = (B + chunk - 1) / chunk;
     auto copy_back = [&](long long c) -> int {
-        int i = (int)(c % nbuf);
-        long long b0 = c * chunk, nb = std::min(chunk, B - b0);
+        const int i = (int)(c % nbuf);
+        const long long b0 = c * chunk, nb = std::min(chunk, B - b0);
         CU(cuStreamWaitEvent(sc.s, ev_kernel[i].e, 0));
-        CU(cuMemcpyDtoHAsync_v2(usol + (size_t)b0 * nt * neq, d_usol[i].p, row_bytes * (size_t)nb, sc.s));
-        CU(cuMemcpyDtoHAsync_v2(success + b0, d_ok[i].p, sizeof(int) * (size_t)nb, sc.s));
+        CU(cuMemcpyDtoHAsync_v2(usol + (size_t)b0 * nt * neq, d_usol[i], row_bytes * (size_t)nb, sc.s));
+        CU(cuMemcpyDtoHAsync_v2(success + b0, d_ok[i], sizeof(int) * (size_t)nb, sc.s));
         if (counters)
-            CU(cuMemcpyDtoHAsync_v2(counters + b0 * B200ODE_NCOUNTERS, d_cnt[i].p,
+            CU(cuMemcpyDtoHAsync_v2(counters + b0 * B200ODE_NCOUNTERS, d_cnt[i],
                                     sizeof(int) * B200ODE_NCOUNTERS * (size_t)nb, sc.s));
         CU(cuEventRecord(ev_copied[i].e, sc.s));
         return 0;
     };
     for (long long c = 0; c < nchunks; c++) {
-        int i = (int)(c % nbuf);
-        long long b0 = c * chunk, nb = std::min(chunk, B - b0);
-        if (c >= nbuf) CU(cuStreamWaitEvent(sk.s, ev_copied[i].e, 0));
+        const int i = (int)(c % nbuf);
+        CUstream ks = sk[c & 1].s;
+        const long long b0 = c * chunk, nb = std::min(chunk, B - b0);
+        if (c >= nbuf) CU(cuStreamWaitEvent(ks, ev_copied[i].e, 0));  // buffer i is free again
         B200OdeLaunch a;
         memset(&a, 0, sizeof a);
         a.B = nb;
-        a.u0 = reinterpret_cast<const double*>(d_u0.p) + (u0_stride ? (size_t)b0 * neq : 0);
+        a.u0 = reinterpret_cast<const double*>(d_u0) + (u0_stride ? (size_t)b0 * neq : 0);
         a.u0_stride = u0_stride ? neq : 0;
-        a.data = reinterpret_cast<const char*>(d_data.p) + (data_stride > 0 ? (size_t)b0 * data_stride : 0);
+        a.data = reinterpret_cast<const char*>(d_data) + (data_stride > 0 ? (size_t)b0 * data_stride : 0);
         a.data_stride = data_stride > 0 ? data_stride : 0;
         a.np = np;
         a.nt = nt;
-        a.t_eval = reinterpret_cast<const double*>(d_te.p);
-        a.usol = reinterpret_cast<double*>(d_usol[i].p);
+        a.t_eval = reinterpret_cast<const double*>(d_te);
+        a.usol = reinterpret_cast<double*>(d_usol[i]);
         a.rtol = rtol;
         a.atol = atol;
         a.mxstep = mxstep;
         a.exit_on_warning = exit_on_warning;
-        a.success = reinterpret_cast<int*>(d_ok[i].p);
-        a.counters = counters ? reinterpret_cast<int*>(d_cnt[i].p) : nullptr;
-        if ((rc = launch(H, P, a, sk.s))) return rc;
-        CU(cuEventRecord(ev_kernel[i].e, sk.s));
+        a.success = reinterpret_cast<int*>(d_ok[i]);
+        a.counters = counters ? reinterpret_cast<int*>(d_cnt[i]) : nullptr;
+        if ((rc = launch(H, P, a, ks))) return rc;
+        CU(cuEventRecord(ev_kernel[i].e, ks));
+        // the copy of chunk c-1 is enqueued after the launch of chunk c so that a buffer's
+        // "copied" event always exists before a later chunk waits on it
         if (c >= 1 && (rc = copy_back(c - 1))) return rc;
     }
     if ((rc = copy_back(nchunks - 1))) return rc;
+    const double t2 = now_ms();
     CU(cuStreamSynchronize(sc.s));
-    CU(cuStreamSynchronize(sk.s));
+    CU(cuStreamSynchronize(sk[0].s));
+    CU(cuStreamSynchronize(sk[1].s));
+    if (trace)
+        fprintf(stderr, "[b200ode] B=%lld chunk=%lld x%lld buffers=%d scratch=%.1f MB | setup %.2f ms, "
+                        "enqueue %.2f ms, drain %.2f ms\n", B, chunk, nchunks, nbuf,
+                (in_bytes + out_bytes * nbuf) / 1048576.0, t1 - t0, t2 - t1, now_ms() - t2);
     return 0;
 }
 
