@@ -83,7 +83,16 @@ def build(force=False, verbose=False):
                 qc = int(os.environ.get("B200ODE_QCAP", QCAP.get(n, 48)))
                 ni = int(os.environ.get("B200ODE_DRAIN_NOINLINE", "0"))
                 th = int(os.environ.get("B200ODE_THREADS", THREADS.get(name, {}).get(n, 128)))
-                log = _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_NEQ=%d" % n, "-DB200_QCAP=%d" % qc,
+                # lsoda: pow out of line (one copy instead of five: +17 % on Robertson, the
+                # kernel's largest stall reason is instruction-cache misses); out-of-line
+                # division was measured slower (all sites 4.28 M, rare blocks only 4.40 M,
+                # inline 4.66 M traj/s) and stays an experiment switch
+                extra = []
+                if name == "lsoda" and os.environ.get("B200ODE_POW_NOINLINE", "1") == "1":
+                    extra.append("-DB200POW_NOINLINE")
+                if name == "lsoda" and os.environ.get("B200ODE_DIV_NOINLINE", "0") == "1":
+                    extra.append("-DB200_DIV_NOINLINE")
+                log = _run([NVCC] + ARCH + NVCC_FLAGS + extra + ["-DB200_NEQ=%d" % n, "-DB200_QCAP=%d" % qc,
                                                           "-DB200_MINBLOCKS=%d" % mb, "-DB200_DRAIN_NOINLINE=%d" % ni, "-DB200_THREADS=%d" % th,
                                                           "-o", out, srcp])
                 if verbose and log.strip():

@@ -22,6 +22,11 @@
 #define B200ODE_POW_CUH
 
 #if defined(__CUDACC__)
+#if defined(B200POW_NOINLINE)
+// one out-of-line copy: the LSODA kernels call pow from five places, and their code
+// size (instruction-cache misses are their largest stall reason) matters more than the call
+#define B200POW_ENTRY __device__ __noinline__
+#endif
 #define B200POW_FN __host__ __device__ __forceinline__
 #define B200POW_TABLE_QUAL static __device__ const
 #define B200POW_HOST_TABLES 0
@@ -83,7 +88,10 @@ B200POW_FN double b200pow_add(double a, double b)
 #endif
 }
 
-B200POW_FN double b200ode_pow(double x, double y)
+#ifndef B200POW_ENTRY
+#define B200POW_ENTRY B200POW_FN
+#endif
+B200POW_ENTRY double b200ode_pow(double x, double y)
 {
     unsigned long long ix = b200pow_bits(x);
     const unsigned topx = (unsigned)(ix >> 52);

@@ -93,6 +93,19 @@ struct LsRun {
 LS_FN double ls_max(double a, double b) { return (a < b) ? b : a; }
 LS_FN double ls_min(double a, double b) { return (b < a) ? b : a; }
 
+// IEEE division.  ls_div is inlined (the compiler's Newton sequence, ~23 instructions).
+// ls_div_rare marks the divisions of blocks that few lanes of a warp execute (Jacobian /
+// LU, rescale, coefficient reload).  With -DB200_DIV_NOINLINE it becomes one out-of-line
+// routine -- an experiment against the kernel's instruction-cache misses (ncu
+// stall_no_instruction, profiles/r1_lsoda_v3) that measured SLOWER on Robertson (4.40 M
+// vs 4.66 M traj/s; every division out of line: 4.28 M), so it is off by default.
+LS_FN double ls_div(double a, double b) { return a / b; }
+#if defined(__CUDA_ARCH__) && defined(B200_DIV_NOINLINE)
+__device__ __noinline__ double ls_div_rare(double a, double b) { return a / b; }
+#else
+LS_FN double ls_div_rare(double a, double b) { return a / b; }
+#endif
+
 // hmin / |h| with hmin = 0 (LSODA.cpp:401, :1155, :1243 ...): +0, or NaN when h is 0 or NaN
 LS_FN double ls_hmin_ratio(double h) { return 0.0 / fabs(h); }
 
@@ -113,7 +126,7 @@ LS_FN unsigned long long ls_trunc_u64(double x)
 LS_FN void ls_resetcoeff(LsLane& s, const B200LsodaTables* T)
 {
     const double el1 = ELCO(s.nq, 1);
-    s.rc = s.rc * el1 / s.el0;
+    s.rc = ls_div_rare(s.rc * el1, s.el0);
     s.el0 = el1;
 }
 
@@ -122,12 +135,12 @@ template <class V>
 LS_FN void ls_scaleh(LsLane& s, V& v, const B200LsodaTables* T, double& rh, double& pdh)
 {
     rh = ls_min(rh, s.rmax);
-    rh = rh / ls_max(1.0, fabs(s.h) * 0.0 * rh);
+    rh = ls_div_rare(rh, ls_max(1.0, fabs(s.h) * 0.0 * rh));
     if (s.meth == 1) {
         s.irflag = 0;
         pdh = ls_max(fabs(s.h) * s.pdlast, 0.000001);
         if ((rh * pdh * 1.00001) >= T->sm1[s.nq]) {
-            rh = T->sm1[s.nq] / pdh;
+            rh = ls_div_rare(T->sm1[s.nq], pdh);
             s.irflag = 1;
         }
     }
@@ -152,16 +165,16 @@ LS_FN void ls_methodswitch(LsLane& s, const B200LsodaTables* T, double dsm, doub
             rh2 = 2.0;
             nqm2 = s.nq < LS_MXORDS ? s.nq : LS_MXORDS;
         } else {
-            const double exsm = 1.0 / (double)l;
-            double rh1 = 1.0 / (1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
+            const double exsm = T->rcp[l];
+            double rh1 = ls_div(1.0, 1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
             double rh1it = 2.0 * rh1;
             pdh = s.pdlast * fabs(s.h);
-            if ((pdh * rh1) > 0.00001) rh1it = T->sm1[s.nq] / pdh;
+            if ((pdh * rh1) > 0.00001) rh1it = ls_div(T->sm1[s.nq], pdh);
             rh1 = ls_min(rh1, rh1it);
             // (nq <= 5 = mxords here, so the reference's nq > mxords branch, :1988-1994,
             // cannot be taken)
-            const double dm2 = dsm * (T->cm1[s.nq] / T->cm2[s.nq]);
-            rh2 = 1.0 / (1.2 * b200ode_pow(dm2, exsm) + 0.0000012);
+            const double dm2 = dsm * T->cm12[s.nq];
+            rh2 = ls_div(1.0, 1.2 * b200ode_pow(dm2, exsm) + 0.0000012);
             nqm2 = s.nq;
             if (rh2 < 5.0 * rh1) return;
         }
@@ -173,16 +186,16 @@ LS_FN void ls_methodswitch(LsLane& s, const B200LsodaTables* T, double dsm, doub
         return;
     }
     // currently BDF, LSODA.cpp:2026-2068 (nq <= mxords <= mxordn: :2030-2036 unreachable)
-    const double exsm = 1.0 / (double)l;
-    double dm1 = dsm * (T->cm2[s.nq] / T->cm1[s.nq]);
-    double rh1 = 1.0 / (1.2 * b200ode_pow(dm1, exsm) + 0.0000012);
+    const double exsm = T->rcp[l];
+    double dm1 = dsm * T->cm21[s.nq];
+    double rh1 = ls_div(1.0, 1.2 * b200ode_pow(dm1, exsm) + 0.0000012);
     const int nqm1 = s.nq;
     const double exm1 = exsm;
     double rh1it = 2.0 * rh1;
     pdh = s.pdnorm * fabs(s.h);
-    if ((pdh * rh1) > 0.00001) rh1it = T->sm1[nqm1] / pdh;
+    if ((pdh * rh1) > 0.00001) rh1it = ls_div(T->sm1[nqm1], pdh);
     rh1 = ls_min(rh1, rh1it);
-    const double rh2 = 1.0 / (1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
+    const double rh2 = ls_div(1.0, 1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
     if ((rh1 * 5.0) < (5.0 * rh2)) return;
     const double alpha = ls_max(0.001, rh1);
     dm1 *= b200ode_pow(alpha, exm1);
@@ -202,19 +215,19 @@ LS_FN int ls_orderswitch(LsLane& s, V& v, const B200LsodaTables* T, double rhup,
     const int l = s.nq + 1;
     const int lmax = (s.meth == 1 ? LS_MXORDN : LS_MXORDS) + 1;
     int newq;
-    const double exsm = 1.0 / (double)l;
-    double rhsm = 1.0 / (1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
+    const double exsm = T->rcp[l];
+    double rhsm = ls_div(1.0, 1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
     double rhdn = 0.0;
     if (s.nq != 1) {
-        const double ddn = v.norm_yh(l) / TESCO(s.nq, 1);
-        const double exdn = 1.0 / (double)s.nq;
-        rhdn = 1.0 / (1.3 * b200ode_pow(ddn, exdn) + 0.0000013);
+        const double ddn = ls_div(v.norm_yh(l), TESCO(s.nq, 1));
+        const double exdn = T->rcp[s.nq];
+        rhdn = ls_div(1.0, 1.3 * b200ode_pow(ddn, exdn) + 0.0000013);
     }
     if (s.meth == 1) {
         pdh = ls_max(fabs(s.h) * s.pdlast, 0.000001);
-        if (l < lmax) rhup = ls_min(rhup, T->sm1[l] / pdh);
-        rhsm = ls_min(rhsm, T->sm1[s.nq] / pdh);
-        if (s.nq > 1) rhdn = ls_min(rhdn, T->sm1[s.nq - 1] / pdh);
+        if (l < lmax) rhup = ls_min(rhup, ls_div(T->sm1[l], pdh));
+        rhsm = ls_min(rhsm, ls_div(T->sm1[s.nq], pdh));
+        if (s.nq > 1) rhdn = ls_min(rhdn, ls_div(T->sm1[s.nq - 1], pdh));
         s.pdest = 0.0;
     }
     if (rhsm >= rhup) {
@@ -234,7 +247,7 @@ LS_FN int ls_orderswitch(LsLane& s, V& v, const B200LsodaTables* T, double rhup,
         } else {
             rh = rhup;
             if (rh >= 1.1) {
-                const double r = ELCO(s.nq, l) / (double)l;
+                const double r = ls_div_rare(ELCO(s.nq, l), (double)l);
                 s.nq = l;
                 v.yh_from_acor_scaled(s.nq + 1, r);
                 return 2;
@@ -418,7 +431,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
                         v.store_y(usol + (size_t)R.row * n);
                     } else {
                         // intdy with k = 0, LSODA.cpp:1435-1453
-                        v.intdy(s.nq, (tout - s.tn) / s.h, usol + (size_t)R.row * n);
+                        v.intdy(s.nq, ls_div(tout - s.tn, s.h), usol + (size_t)R.row * n);
                     }
                     first_in_step = false;
                     R.nslast = s.nst;
@@ -494,7 +507,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
                         // (cannot happen in this driver -- nothing changes h between steps --
                         // but kept: the rescale is done at the top of the lane's next pass,
                         // and this pass ends here)
-                        s.rh = s.h / s.hold;
+                        s.rh = ls_div_rare(s.h, s.hold);
                         s.h = s.hold;
                         s.flags |= LS_F_RESCALE;
                     }
@@ -553,13 +566,13 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
         } else if (s.m != 0 || s.meth != 1) {
             if (s.m != 0) {
                 double rm = 1024.0;
-                if (s.del <= (1024.0 * s.delp)) rm = s.del / s.delp;
+                if (s.del <= (1024.0 * s.delp)) rm = ls_div(s.del, s.delp);
                 s.rate = ls_max(s.rate, rm);
                 s.crate = ls_max(0.2 * s.crate, rm);
             }
-            const double dcon = s.del * ls_min(1.0, 1.5 * s.crate) / (TESCO(s.nq, 2) * T->conit[s.nq]);
+            const double dcon = ls_div(s.del * ls_min(1.0, 1.5 * s.crate), TESCO(s.nq, 2) * T->conit[s.nq]);
             if (dcon <= 1.0) {
-                s.pdest = ls_max(s.pdest, s.rate / fabs(s.h * el1));
+                s.pdest = ls_max(s.pdest, ls_div(s.rate, fabs(s.h * el1)));
                 if (s.pdest != 0.0) s.pdlast = s.pdest;
                 converged = true;
             }
@@ -588,8 +601,8 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
     bool accepted = false, select_order = false;
     if (converged) {
         s.jcur = 0;
-        if (s.m == 0) dsm = s.del / TESCO(s.nq, 2);
-        if (s.m > 0) dsm = v.norm_acor() / TESCO(s.nq, 2);
+        if (s.m == 0) dsm = ls_div(s.del, TESCO(s.nq, 2));
+        if (s.m > 0) dsm = ls_div(v.norm_acor(), TESCO(s.nq, 2));
         accepted = dsm <= 1.0;
     }
     if (accepted) {
@@ -618,9 +631,9 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
             if (s.ialth == 0) {
                 if (l != lmax) {
                     // savf = acor - yh[lmax], :1222-1228
-                    const double dup = v.norm_acor_minus_yh(lmax) / TESCO(s.nq, 3);
-                    const double exup = 1.0 / (double)(l + 1);
-                    rhup = 1.0 / (1.4 * b200ode_pow(dup, exup) + 0.0000014);
+                    const double dup = ls_div(v.norm_acor_minus_yh(lmax), TESCO(s.nq, 3));
+                    const double exup = T->rcp[l + 1];
+                    rhup = ls_div(1.0, 1.4 * b200ode_pow(dup, exup) + 0.0000014);
                 }
                 select_order = true;
             } else if (!(s.ialth > 1 || l == lmax)) {

@@ -74,7 +74,7 @@ struct LsThreadVec {
         LS_FOR_N {
             ewt[i] = rtol * fabs(YH(1, i)) + atol;
             if (ewt[i] <= 0.0) bad = true;
-            ewt[i] = 1.0 / ewt[i];
+            ewt[i] = ls_div(1.0, ewt[i]);
         }
         return bad;
     }
@@ -226,7 +226,7 @@ struct LsThreadVec {
                 WM(k, j) = WM(k, k);
                 WM(k, k) = akj;
             }
-            double t = -1.0 / akj;
+            double t = ls_div_rare(-1.0, akj);
             double rowk[N];
 #pragma unroll
             for (int c = k + 1; c < N; c++) {
@@ -258,7 +258,7 @@ struct LsThreadVec {
             double t = 0.0;
 #pragma unroll
             for (int c = 0; c < k; c++) t += WM(k, c) * b[c];
-            b[k] = (b[k] - t) / WM(k, k);
+            b[k] = ls_div(b[k] - t, WM(k, k));
         }
 #pragma unroll
         for (int k = N - 2; k >= 0; k--) {
@@ -296,10 +296,10 @@ struct LsThreadVec {
                     ewtj = ewt[i];
                 }
             }
-            const double r = ls_max(LS_SQRTETA * fabs(yj), r0 / ewtj);
+            const double r = ls_max(LS_SQRTETA * fabs(yj), ls_div_rare(r0, ewtj));
             double yp[N];
             LS_FOR_N yp[i] = (i == j) ? y[i] + r : y[i];
-            fac = -hl0 / r;
+            fac = ls_div_rare(-hl0, r);
             b200ode_user_rhs(tn, yp, acor, pp);
             LS_FOR_N WM(i, j) = (acor[i] - savf[i]) * fac;
         }
@@ -308,10 +308,10 @@ struct LsThreadVec {
         for (int r = 0; r < N; r++) {
             double sum = 0.0;
 #pragma unroll
-            for (int c = 0; c < N; c++) sum += fabs(WM(r, c)) / ewt[c];
+            for (int c = 0; c < N; c++) sum += ls_div_rare(fabs(WM(r, c)), ewt[c]);
             an = ls_max(an, sum * ewt[r]);
         }
-        pdnorm = an / fabs(hl0);
+        pdnorm = ls_div_rare(an, fabs(hl0));
         LS_FOR_N WM(i, i) = WM(i, i) + 1.0;
         return dgefa() != 0 ? 1 : 0;
     }

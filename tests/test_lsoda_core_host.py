@@ -95,7 +95,8 @@ def test_tables_equal_cfode_of_the_oracle():
     class T(ct.Structure):
         _fields_ = [("elco", ct.c_double * 14 * 13 * 2), ("tesco", ct.c_double * 4 * 13 * 2),
                     ("cm1", ct.c_double * 13), ("cm2", ct.c_double * 6), ("sm1", ct.c_double * 13),
-                    ("conit", ct.c_double * 13), ("pad", ct.c_double * 3)]
+                    ("conit", ct.c_double * 13), ("rcp", ct.c_double * 16),
+                    ("cm12", ct.c_double * 13), ("cm21", ct.c_double * 13), ("pad", ct.c_double * 1)]
     lib = BACKEND[_backend](2)
     lib.lsoda_core_tables.restype = ct.POINTER(T)
     t = lib.lsoda_core_tables().contents
@@ -105,6 +106,9 @@ def test_tables_equal_cfode_of_the_oracle():
     assert np.array_equal(np.array(t.tesco[1]), np.array(t2))
     assert list(t.cm1) == cm1 and list(t.cm2) == cm2
     assert list(t.conit)[1:] == [0.5 / (q + 2) for q in range(1, 13)]
+    assert list(t.rcp)[1:] == [1.0 / k for k in range(1, 16)]
+    assert list(t.cm12)[1:6] == [cm1[q] / cm2[q] for q in range(1, 6)]
+    assert list(t.cm21)[1:6] == [cm2[q] / cm1[q] for q in range(1, 6)]
     # spot values every LSODA implementation shares
     assert t.elco[1][1][1] == 1.0 and t.elco[1][2][1] == 2.0 / 3.0 and t.elco[0][2][1] == 0.5
 
