@@ -117,6 +117,13 @@ int b200ode_lsoda_batched_device(b200ode_rhs_t rhs, long long B, int neq, const 
                                  int* success, int* counters, int exit_on_warning,
                                  void* stream);
 
+/* Page-locked host memory for usol / success / counters: with it the device-to-host
+ * copies of b200ode_*_batched run at full PCIe speed and overlap the kernels (with pageable
+ * memory the driver stages them).  The reference's driver allocates usol with np.empty
+ * (numbalsoda/driver.py:35); numbalsoda_b200 allocates it here.  Needs a CUDA driver. */
+int b200ode_host_alloc(size_t bytes, void** ptr);
+int b200ode_host_free(void* ptr);
+
 /* Launch geometry and resource usage of the kernel behind `rhs` on the current
  * device: info = {registers/thread, local bytes/thread, static smem bytes,
  * threads/block, blocks/SM, SM count, grid size of the last launch, kernel launches

@@ -3,7 +3,7 @@
 from .driver import lsoda_sig, lsoda, address_as_void_pointer
 from .driver_dop853 import dop853
 from .rhs import builtin, register, get_handle
-from ._lib import B200OdeError
+from ._lib import B200OdeError, pinned_empty
 
 __all__ = ["lsoda_sig", "lsoda", "dop853", "address_as_void_pointer", "builtin", "register",
-           "get_handle", "B200OdeError"]
+           "get_handle", "B200OdeError", "pinned_empty"]

@@ -16,11 +16,17 @@ class B200OdeError(RuntimeError):
     pass
 
 
-def _load():
+def _load(rebuilt=False):
     if not os.path.exists(LIBPATH):
         from . import build as _build
         _build.build()
+        rebuilt = True
     lib = ct.CDLL(LIBPATH)
+    if not hasattr(lib, "b200ode_host_alloc") and not rebuilt:
+        # a library built from older sources: rebuild it once
+        from . import build as _build
+        _build.build(force=True)
+        return _load(rebuilt=True)
     vp, ll, i, d, sz = ct.c_void_p, ct.c_longlong, ct.c_int, ct.c_double, ct.c_size_t
     lib.b200ode_last_error.restype = ct.c_char_p
     lib.b200ode_link_rhs.argtypes = [i, i, vp, sz, i, ct.c_uint, ct.POINTER(vp)]
@@ -33,6 +39,8 @@ def _load():
     lib.b200ode_dop853_batched_device.argtypes = common + [vp]
     lib.b200ode_lsoda_batched_device.argtypes = common + [i, vp]
     lib.b200ode_kernel_info.argtypes = [vp, ct.POINTER(i * 8)]
+    lib.b200ode_host_alloc.argtypes = [sz, ct.POINTER(vp)]
+    lib.b200ode_host_free.argtypes = [vp]
     return lib
 
 
@@ -42,3 +50,27 @@ lib = _load()
 def check(rc):
     if rc != 0:
         raise B200OdeError("libb200ode error %d: %s" % (rc, lib.b200ode_last_error().decode()))
+
+
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib.b200ode_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """np.empty in page-locked memory (falls back to pageable memory without a driver)."""
+    import numpy as np
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = ct.c_void_p()
+    if n == 0 or lib.b200ode_host_alloc(n, ct.byref(p)) != 0 or not p.value:
+        return np.empty(shape, dtype)
+    buf = (ct.c_char * n).from_address(p.value)
+    buf._owner = _PinnedOwner(p)  # freed when the last array viewing the buffer goes away
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)

@@ -37,7 +37,7 @@ def _data_layout(data, B_hint):
 
 
 def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning=False,
-          strict=False, device=None, counters=False):
+          strict=False, device=None, counters=False, out=None):
     u0 = _as_f64(u0, "u0")
     t_eval = _as_f64(t_eval, "t_eval")
     if data is None:
@@ -55,7 +55,15 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
     n = u0.shape[-1]
     nt = t_eval.shape[0]
     handle = _rhs.get_handle(funcptr, solver, n, strict=strict)
-    usol = np.empty((B, nt, n), dtype=np.float64)
+    if out is not None:
+        # caller-owned result buffer, ideally page-locked (numbalsoda_b200.pinned_empty) and
+        # reused across calls: allocating and first touching a fresh multi-gigabyte array
+        # costs more than integrating the ensemble
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != B * nt * n:
+            raise ValueError("out must be a C-contiguous float64 array of %d elements" % (B * nt * n))
+        usol = out.reshape(B, nt, n)
+    else:
+        usol = np.empty((B, nt, n), dtype=np.float64)  # as the reference, driver.py:35
     ok = np.full(B, 999, dtype=np.int32)
     cnt = np.zeros((B, _lib.NCOUNTERS), dtype=np.int32) if counters else None
 

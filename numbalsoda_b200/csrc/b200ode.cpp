@@ -69,7 +69,7 @@ extern "C" int b200ode_version(void) { return B200ODE_VERSION; }
     X(cuMemFree_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)      \
     X(cuStreamCreate) X(cuStreamDestroy_v2) X(cuStreamSynchronize) X(cuStreamWaitEvent)     \
     X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord) X(cuEventSynchronize)            \
-    X(cuGetErrorString) X(cuMemGetInfo_v2)
+    X(cuGetErrorString) X(cuMemGetInfo_v2) X(cuMemHostAlloc) X(cuMemFreeHost)
 
 struct Driver {
     void* lib = nullptr;
@@ -681,6 +681,34 @@ extern "C" int b200ode_lsoda_batched(b200ode_rhs_t H, long long B, int neq, cons
 {
     return solve_host(B200ODE_LSODA, H, B, neq, u0, u0_stride, data, data_stride, np, nt, teval,
                       usol, rtol, atol, mxstep, success, counters, exit_on_warning, device);
+}
+
+// ---------------------------------------------------------------- pinned host memory
+extern "C" int b200ode_host_alloc(size_t bytes, void** ptr)
+{
+    if (!ptr) return fail(B200ODE_EINVAL, "ptr is NULL");
+    *ptr = nullptr;
+    if (!driver())
+        return fail(B200ODE_ENODEV, "CUDA driver (libcuda.so.1) not available");
+    CUcontext cur = nullptr;
+    CU(cuCtxGetCurrent(&cur));
+    if (!cur) {
+        CUdevice dev;
+        CU(cuDeviceGet(&dev, 0));
+        CU(cuDevicePrimaryCtxRetain(&cur, dev));
+        CU(cuCtxSetCurrent(cur));
+    }
+    CU(cuMemHostAlloc(ptr, bytes ? bytes : 1, CU_MEMHOSTALLOC_PORTABLE));
+    return 0;
+}
+
+extern "C" int b200ode_host_free(void* ptr)
+{
+    if (!ptr) return 0;
+    if (!driver())
+        return fail(B200ODE_ENODEV, "CUDA driver (libcuda.so.1) not available");
+    CU(cuMemFreeHost(ptr));
+    return 0;
 }
 
 // ---------------------------------------------------------------- self test

@@ -19,17 +19,19 @@ except Exception:  # numba absent: built-in right-hand sides still work
 
 
 def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, atol=1.0e-6,
-          mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False):
+          mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False, out=None):
     """Integrate with the LSODA kernel on the GPU.
 
     funcptr: address of a numba @cfunc(lsoda_sig) (as in the reference), the cfunc, the
     Python function, or numbalsoda_b200.builtin(name).
     Extra keyword-only arguments: strict (FMA contraction off: bit-for-bit the CPU
     arithmetic), device (index, list of indices or "all"), counters (also return
-    [nst, nfe, nje, nswitch, nqu, istate, rows, meth] per trajectory)."""
+    [nst, nfe, nje, nswitch, nqu, istate, rows, meth] per trajectory), out (a preallocated
+    C-contiguous float64 result buffer of B*nt*n elements -- e.g. from
+    numbalsoda_b200.pinned_empty -- to reuse across calls instead of a fresh np.empty)."""
     return solve(_lib.LSODA, funcptr, u0, t_eval, data, rtol, atol, mxstep,
                  exit_on_warning=exit_on_warning, strict=strict, device=device,
-                 counters=counters)
+                 counters=counters, out=out)
 
 
 def address_as_void_pointer(addr):

@@ -6,8 +6,8 @@ from ._solve import solve
 
 
 def dop853(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, atol=1.0e-6,
-           mxstep=10000, *, strict=False, device=None, counters=False):
+           mxstep=10000, *, strict=False, device=None, counters=False, out=None):
     """Integrate with the DOP853 kernel on the GPU; arguments as lsoda().  counters:
     [nstep, nfcn, naccpt, nrejct, nevent, idid, rows, 0] per trajectory."""
     return solve(_lib.DOP853, funcptr, u0, t_eval, data, rtol, atol, mxstep, strict=strict,
-                 device=device, counters=counters)
+                 device=device, counters=counters, out=out)

@@ -350,3 +350,52 @@ def test_pivoting_lu_strict_bitwise_and_fast_close(n):
     assert ok2.all()
     err = np.abs(us2 - ref) / (1e-6 * np.abs(ref) + 1e-9)
     assert err.max() < 50.0, err.max()
+
+
+def test_data_record_passed_by_address():
+    """Records of more than 16 doubles are not staged into registers: the RHS gets the
+    record's device address (the kernels' `_ptr` entry points), as it would a C struct."""
+    nb = _nb()
+
+    def rhs(t, u, du, p):
+        du[0] = u[0] - u[0] * u[1] * p[19]
+        du[1] = u[0] * u[1] - u[1] * p[0] + p[7]
+
+    import numba
+    cf = numba.cfunc(nb.lsoda_sig)(rhs)
+    rng = np.random.default_rng(1)
+    B = 70
+    P = np.zeros((B, 20))
+    P[:, 0] = rng.uniform(0.5, 2.0, B)
+    P[:, 7] = rng.uniform(0.0, 0.1, B)
+    P[:, 19] = rng.uniform(0.8, 1.2, B)
+    u0 = np.array([5.0, 0.8])
+    te = np.linspace(0.0, 20.0, 41)
+    for solver, name in ((nb.lsoda, "lsoda"), (nb.dop853, "dop853")):
+        us, ok, cnt = solver(rhs, u0, te, P, 1e-7, 1e-9, strict=True, counters=True)
+        ref, okr, cr = orc.solve_batch(name, cf.address, u0, te, P, 1e-7, 1e-9)
+        assert ok.all() and okr.all()
+        assert np.array_equal(cnt[:, :7], cr[:, :7]) and np.array_equal(us, ref), name
+    # one shared 20-double record
+    us, ok = nb.lsoda(rhs, u0, te, P[3], 1e-7, 1e-9, strict=True)
+    ref, okr, _ = orc.lsoda(cf.address, u0, te, P[3], 1e-7, 1e-9)
+    assert ok and np.array_equal(us, ref)
+
+
+def test_out_buffer_and_pinned_memory():
+    nb = _nb()
+    B = 300
+    P = pr.robertson_sweep(B)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 1e5, 100)
+    ref, ok0 = nb.lsoda(nb.builtin("robertson"), u0, te, P, 1e-8, 1e-8)
+    buf = nb.pinned_empty((B, 100, 3), np.float64)
+    for _ in range(2):
+        buf[:] = -1.0
+        us, ok = nb.lsoda(nb.builtin("robertson"), u0, te, P, 1e-8, 1e-8, out=buf)
+        assert ok.all() and np.shares_memory(us, buf) and np.array_equal(us, ref)
+    us, ok = nb.dop853(nb.builtin("robertson"), u0, np.linspace(0, 40, 100), P, 1e-8, 1e-8,
+                       mxstep=100000, out=buf)
+    assert np.shares_memory(us, buf) and np.isfinite(us[ok]).all()
+    with pytest.raises(ValueError):
+        nb.lsoda(nb.builtin("robertson"), u0, te, P, 1e-8, 1e-8, out=np.empty((B, 99, 3)))
