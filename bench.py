@@ -48,6 +48,9 @@ WORKLOADS = {
 }
 
 
+MIXED = ["lorenz_dop853", "robertson_lsoda"]  # BASELINE.json configs[4]
+
+
 def sweep(name, B, seed):
     import _problems as pr
     if name == "lorenz":
@@ -235,15 +238,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lorenz_dop853", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="lorenz_dop853", choices=sorted(WORKLOADS) + ["mixed"])
     ap.add_argument("--batch", type=int, default=0, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--strict", action="store_true", help="FMA contraction off (parity mode)")
     a = ap.parse_args()
-    wl = dict(WORKLOADS[a.workload])
-    if a.batch:
-        wl["batch"] = a.batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -257,8 +257,54 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    "--nproc-per-node", str(a.gpus), "--master-addr", "127.0.0.1",
                                    "--master-port", str(port)] + sys.argv)
+    names = MIXED if a.workload == "mixed" else [a.workload]
+    ranks = None
+    if a.impl == "ours":
+        import torch
+        from numbalsoda_b200._dist import Ranks
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+        torch.cuda.set_device(local)
+        ranks = Ranks(backend="nccl" if world > 1 else None)  # plumbing only: no data-path collective
+    lines = [bench_one(a, nm, ranks, rank, world, local) for nm in names]
+    if ranks is not None:
+        ranks.close()
+    if rank != 0:
+        return
+    if len(lines) == 1:
+        print(json.dumps(lines[0]))
+        return
+    # BASELINE.json configs[4]: the mixed sweep is two homogeneous launches per GPU (one
+    # linked kernel per solver / right-hand side); aggregate = all trajectories / all time
+    # (per step: every kind's ensemble once; time of a kind = its trajectories / its rate)
+    tot_traj = sum(l["config"]["trajectories_per_gpu"] * l["n_gpus"] for l in lines)
+    tot_s = sum(l["config"]["trajectories_per_gpu"] * l["n_gpus"] / l["value"] for l in lines)
+    slow = min(lines, key=lambda l: l["value"])
+    line = dict(slow)
+    line.update({"value": tot_traj / tot_s, "ms_per_step": 1e3 * tot_s,
+                 "config": {"workload": "mixed: " + " + ".join(l["config"]["workload"] for l in lines),
+                            "reference_config": "BASELINE.json configs[4] (SURVEY 8d C5), weak scaling",
+                            "trajectories_per_gpu": sum(l["config"]["trajectories_per_gpu"] for l in lines),
+                            "sharding": "by trajectory, no collective", "l2": lines[0]["config"]["l2"]},
+                 "gpu_launches": sum(l.get("gpu_launches", 0) for l in lines),
+                 "parts": [{k: l.get(k) for k in ("value", "ms_per_step", "roofline", "e2e", "cpu_baseline")}
+                           for l in lines]})
+    if all("e2e" in l for l in lines):
+        e_s = sum(l["config"]["trajectories_per_gpu"] * l["n_gpus"] / l["e2e"]["value"] for l in lines)
+        line["e2e"] = {"value": sum(l["config"]["trajectories_per_gpu"] * l["n_gpus"] for l in lines) / e_s,
+                       "unit": "traj/s",
+                       "h2d_bytes_per_step": sum(l["e2e"]["h2d_bytes_per_step"] for l in lines),
+                       "d2h_bytes_per_step": sum(l["e2e"]["d2h_bytes_per_step"] for l in lines)}
+    print(json.dumps(line))
+
+
+def bench_one(a, workload, ranks, rank, world, local):
+    """One workload on this rank; returns the JSON line (rank 0) or None."""
+    wl = dict(WORKLOADS[workload])
+    if a.batch:
+        wl["batch"] = a.batch
     cfg = {"workload": "%s: %s n=%d sweep, %s, t_eval=linspace(%g,%g,%d), rtol=atol=%g, "
-                       "%d trajectories per GPU" % (a.workload, wl["rhs"], wl["n"], wl["solver"],
+                       "%d trajectories per GPU" % (workload, wl["rhs"], wl["n"], wl["solver"],
                                                     *wl["t_eval"], wl["rtol"], wl["batch"]),
            "reference_config": wl["config"], "trajectories_per_gpu": wl["batch"],
            "sharding": "by trajectory, no collective",
@@ -269,7 +315,7 @@ def main():
 
     if a.impl == "reference":
         if rank != 0:
-            return
+            return None
         vals = []
         for _ in range(a.warmup):
             cpu_arm(wl, 1.0)
@@ -289,19 +335,13 @@ def main():
                                  "sample": info[3]},
                 "e2e": {"value": v, "unit": "traj/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
+        return line
 
     import torch
     import numbalsoda_b200 as nb
     from numbalsoda_b200 import _lib
-    from numbalsoda_b200._dist import Ranks
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    ranks = Ranks(backend="nccl" if world > 1 else None)  # plumbing only: no data-path collective
 
     B, n, nt = wl["batch"], wl["n"], wl["t_eval"][2]
     solver = _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
@@ -395,8 +435,7 @@ def main():
         del out
 
     if rank != 0:
-        ranks.close()
-        return
+        return None
 
     cnt_h = cnt.cpu().numpy()
     flops = (dop853_flops if wl["solver"] == "dop853" else lsoda_flops)(cnt_h, n, F_RHS[wl["rhs"]], nt)
@@ -404,7 +443,7 @@ def main():
     achieved_tf = flops / per_launch_s / 1e12
     peaks = measured_peaks()
     out_bytes = B * (nt * n * 8 + (n + wl["p"]) * 8 + 4)
-    tr = NCU_TRAFFIC.get(a.workload)
+    tr = NCU_TRAFFIC.get(workload)
     roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf if peak_tf else None,
             "traffic": (tr[0] / tr[2] * B) if tr else None,
@@ -433,8 +472,9 @@ def main():
         v, cores, kind, sample, secs = cpu_arm(wl, 12.0)
         line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": kind,
                                 "sample": sample, "seconds": secs}
-    print(json.dumps(line))
-    ranks.close()
+    del usol, cnt, ok, flush
+    torch.cuda.empty_cache()
+    return line
 
 
 if __name__ == "__main__":

@@ -399,3 +399,15 @@ def test_out_buffer_and_pinned_memory():
     assert np.shares_memory(us, buf) and np.isfinite(us[ok]).all()
     with pytest.raises(ValueError):
         nb.lsoda(nb.builtin("robertson"), u0, te, P, 1e-8, 1e-8, out=np.empty((B, 99, 3)))
+
+
+def test_empty_and_tiny_ensembles():
+    nb = _nb()
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 1e5, 10)
+    for solver in (nb.lsoda, nb.dop853):
+        us, ok = solver(nb.builtin("robertson"), u0, te, np.empty((0, 3)), 1e-6, 1e-8)
+        assert us.shape == (0, 10, 3) and ok.shape == (0,)
+    us, ok = nb.lsoda(nb.builtin("robertson"), u0, te, np.array([[0.04, 3e7, 1e4]]), 1e-6, 1e-8, strict=True)
+    ref, okr, _ = orc.lsoda(orc.builtin_rhs("robertson"), u0, te, [0.04, 3e7, 1e4], 1e-6, 1e-8)
+    assert us.shape == (1, 10, 3) and ok[0] == okr and np.array_equal(us[0], ref)
