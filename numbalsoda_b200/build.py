@@ -102,7 +102,7 @@ def build(force=False, verbose=False):
     srcp = os.path.join(CSRC, "lsoda_warp_kernel.cu")
     out = os.path.join(OBJ, "lsodaw.fatbin")
     if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
-        _run([NVCC] + ARCH + NVCC_FLAGS + ["-o", out, srcp])
+        _run([NVCC] + ARCH + NVCC_FLAGS + os.environ.get("B200ODE_EXTRA_DEFS", "").split() + ["-o", out, srcp])
     images.append(("lsodaw", out))
     srcp = os.path.join(CSRC, "rhs_builtin.cu")
     for r in BUILTIN_RHS:
