@@ -132,6 +132,13 @@ struct PerDevice {
     int regs = 0, local_bytes = 0, smem = 0, blocks_per_sm = 0, sms = 0;
     int dyn_smem = 0;  // dynamic shared memory per block
     int qcap = 0;      // dop853: records per warp queue
+    // warp lsoda: per-block iteration matrices in global memory (L2 resident), one set per
+    // launch that may be in flight; a set is reused only after its previous launch finished
+    static const int kScratchSets = 4;
+    CUdeviceptr wm_scratch = 0;
+    size_t wm_set_bytes = 0;
+    CUevent wm_done[kScratchSets] = {nullptr, nullptr, nullptr, nullptr};
+    bool wm_used[kScratchSets] = {false, false, false, false};
     int threads = B200ODE_THREADS;  // threads per block the image was built for
 };
 
@@ -248,6 +255,7 @@ extern "C" void b200ode_rhs_free(b200ode_rhs_t H)
         for (auto& kv : H->dev) {
             g_drv.cuCtxSetCurrent(kv.second.ctx);
             if (kv.second.next) g_drv.cuMemFree_v2(kv.second.next);
+            if (kv.second.wm_scratch) g_drv.cuMemFree_v2(kv.second.wm_scratch);
             if (kv.second.mod) g_drv.cuModuleUnload(kv.second.mod);
         }
     }
@@ -304,6 +312,10 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         if (warp) {
             P.threads = 32;
             P.dyn_smem = B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double);
+            // B200ODE_WM=global: iteration matrices in global memory (more warps per SM)
+            const char* wm = getenv("B200ODE_WM");
+            if (wm && !strcmp(wm, "global"))
+                P.dyn_smem -= B200ODE_LSODAW_MATRIX(H->neq) * (int)sizeof(double);
         } else {
             // ask the image for its build-time geometry (queue / storage sizes, threads)
             const bool dop = H->solver == B200ODE_DOP853;
@@ -336,6 +348,12 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
         CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
         if (P.blocks_per_sm < 1) P.blocks_per_sm = 1;
+        if (warp && P.dyn_smem < B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double)) {
+            P.wm_set_bytes = (size_t)P.sms * P.blocks_per_sm * B200ODE_LSODAW_MATRIX(H->neq) * sizeof(double);
+            CU(cuMemAlloc_v2(&P.wm_scratch, P.wm_set_bytes * PerDevice::kScratchSets));
+            for (int i = 0; i < PerDevice::kScratchSets; i++)
+                CU(cuEventCreate(&P.wm_done[i], CU_EVENT_DISABLE_TIMING));
+        }
     }
     *out = &P;
     return 0;
@@ -372,11 +390,20 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
     const bool warp = warp_kernel(H->solver, H->neq);
     args.neq = H->neq;
     args.strict = (H->flags & B200ODE_STRICT_FP) ? 1 : 0;
+
     long long want = warp ? args.B : (args.B + kThreads - 1) / kThreads;
     long long resident = (long long)P->sms * P->blocks_per_sm;
     int grid = (int)std::min(want, resident);
+    const int set = (int)(slot % PerDevice::kScratchSets);
+    if (P->wm_scratch) {
+        std::lock_guard<std::mutex> lk(H->mu);
+        if (P->wm_used[set]) CU(cuStreamWaitEvent(stream, P->wm_done[set], 0));
+        P->wm_used[set] = true;
+        args.scratch = reinterpret_cast<double*>(P->wm_scratch + P->wm_set_bytes * set);
+    }
     void* params[] = {&args};
     CU(cuLaunchKernel((args.np >= 0 && !warp) ? P->fn : P->fn_ptr, grid, 1, 1, kThreads, 1, 1, (unsigned)P->dyn_smem, stream, params, nullptr));
+    if (P->wm_scratch) CU(cuEventRecord(P->wm_done[set], stream));
     H->last_grid = grid;
     H->launches++;
     return 0;

@@ -19,8 +19,9 @@
 #define B200ODE_THREAD_NMAX 8
 #define B200ODE_WARP_NMAX 128
 #define B200ODE_LSODAW_JCOLS 8 /* Jacobian columns evaluated concurrently */
+#define B200ODE_LSODAW_MATRIX(n) ((n) * ((n) + 1)) /* the transposed, padded iteration matrix */
 #define B200ODE_LSODAW_DOUBLES(n) \
-    (18 * (n) + (n) * ((n) + 1) + B200ODE_LSODAW_JCOLS * ((n) + 1) + (n) + 1)
+    (18 * (n) + B200ODE_LSODAW_MATRIX(n) + B200ODE_LSODAW_JCOLS * ((n) + 1) + (n) + 1)
 
 typedef struct B200OdeLaunch {
     long long B;              /* trajectories in this launch */
@@ -41,6 +42,8 @@ typedef struct B200OdeLaunch {
     int* success;             /* [B] 1 / 0, as the reference's *success */
     int* counters;            /* [B,8] or null */
     unsigned long long* next; /* work queue head (zeroed before the launch) */
+    double* scratch;          /* warp kernel: per-block iteration matrices in global memory
+                                 (B200ODE_LSODAW_MATRIX(neq) doubles each), or null = shared */
 } B200OdeLaunch;
 
 #endif

@@ -18,7 +18,7 @@
 //    contain a t_eval point, but in a warp of 32 trajectories almost every
 //    iteration has *some* lane in that case, so doing the 3 extra stages and the
 //    interpolation in line ran that code on every iteration at ~9 active lanes
-//    (ncu, profiles/r1_dop853_notes.md).  Instead a lane whose step passed output
+//    (ncu, profiles/r1_dop853_v0_inline_events.txt).  Instead a lane whose step passed output
 //    times pushes the step's stage values (4+11n doubles) into a per-warp queue in
 //    shared memory and goes on stepping; when 32 records are queued the whole
 //    warp pops one record per lane and does the dense-output work fully converged;

@@ -361,7 +361,7 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int
 // The reference nests three loops -- lsoda's step loop (LSODA.cpp:774), stoda's retry
 // loop (:1127) and the corrector iteration (:1763) -- and a warp that runs them as
 // written spends most of its time with a few lanes in an inner loop while the others
-// wait (ncu, profiles/r1_lsoda_v0: 5.1 of 32 lanes active).  Here the nest is
+// wait (ncu, profiles/r1_lsoda_v0_thread_per_traj.txt: 5.1 of 32 lanes active).  Here the nest is
 // flattened: every pass performs exactly ONE corrector iteration (one RHS evaluation),
 // preceded, for the lanes that need it, by the end of the previous step (rescale,
 // output rows), the start of a new step (weights, stop tests) and the prediction, and
@@ -372,7 +372,7 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int
 //
 // The function is written without early exits: a `return` inside a divergent branch
 // moves the branch's re-convergence point to the end of the function, and the warp
-// then runs everything after it once per group of lanes (ncu, profiles/r1_lsoda_v1:
+// then runs everything after it once per group of lanes (ncu, profiles/r1_lsoda_v1_flat_unsynced.txt:
 // the blocks below were executed 2-3 times per pass, 7 lanes at a time).  `fin` carries
 // the exits instead, and v.sync(lanes) -- __syncwarp over the lanes that entered; a
 // no-op in the host build and for the warp backend, whose 32 lanes run one trajectory

@@ -95,7 +95,9 @@ struct LsWarpVec {
     double *yh, *y, *savf, *acor, *ewt, *rdiag, *wmT, *ucopy;
     int *ipvt, *perm;
 
-    LS_MFN void attach(double* base, int neq, bool fast_mode)
+    // `matrix`: storage of the iteration matrix outside `base` (the kernel's L2-resident
+    // per-block scratch), or null to keep it with the vectors in shared memory
+    LS_MFN void attach(double* base, int neq, bool fast_mode, double* matrix = nullptr)
     {
         n = neq;
         ld = neq + 1;
@@ -106,8 +108,14 @@ struct LsWarpVec {
         acor = savf + n;
         ewt = acor + n;
         rdiag = ewt + n;
-        wmT = rdiag + n;
-        ucopy = wmT + n * ld;
+        double* next = rdiag + n;
+        if (matrix) {
+            wmT = matrix;
+        } else {
+            wmT = next;
+            next += n * ld;
+        }
+        ucopy = next;
         ipvt = reinterpret_cast<int*>(ucopy + B200ODE_LSODAW_JCOLS * ld);
         perm = ipvt + n;
     }

@@ -11,8 +11,10 @@
 //
 //  * one block = one warp; a persistent grid pulls trajectories from a global counter;
 //  * all solver storage of the trajectory in dynamic shared memory
-//    (B200ODE_LSODAW_DOUBLES(n) doubles: 58.9 KB at n = 64 -> 3 warps per SM); nothing
-//    of it ever touches HBM;
+//    (B200ODE_LSODAW_DOUBLES(n) doubles: 47 KB at n = 64 -> 4 warps per SM), or -- when the
+//    launch provides `scratch` -- the iteration matrix (70 % of it) in a per-block slice of
+//    global memory that stays L2 resident, leaving 14 KB per warp -> 16 warps per SM;
+//    nothing is ever re-read from HBM;
 //  * method-coefficient tables in constant memory (every lane reads the same entry);
 //  * `data` is passed to the RHS by address (the record stays in global memory / L1);
 //  * n is a run-time argument: one image serves every size.
@@ -28,7 +30,8 @@ b200ode_lsodaw_kernel(const B200OdeLaunch L)
     const B200LsodaTables* T = &b200_lsoda_tables;
     const int n = L.neq;
     LsWarpVec v;
-    v.attach(b200_smem, n, L.strict == 0);
+    v.attach(b200_smem, n, L.strict == 0,
+             L.scratch ? L.scratch + (size_t)blockIdx.x * B200ODE_LSODAW_MATRIX(n) : nullptr);
     const int nt = L.nt;
     const double* __restrict__ te = L.t_eval;
     // wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130)

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Small runs of every kernel for compute-sanitizer (memcheck / racecheck):
+   compute-sanitizer --tool racecheck python tools/sanitize_small.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _problems as pr  # noqa: E402
+import numbalsoda_b200 as nb  # noqa: E402
+
+which = sys.argv[1:] or ["dop853", "lsoda", "lsodaw"]
+u0 = np.array([1.0, 0.0, 0.0])
+if "dop853" in which:
+    us, ok = nb.dop853(nb.builtin("lorenz"), u0, np.linspace(0, 2, 21), pr.lorenz_sweep(200), 1e-8, 1e-8)
+    print("dop853", ok.all())
+if "lsoda" in which:
+    us, ok = nb.lsoda(nb.builtin("robertson"), u0, np.linspace(0, 1e3, 20), pr.robertson_sweep(200), 1e-8, 1e-8)
+    print("lsoda", ok.all())
+if "lsodaw" in which:
+    for strict in (False, True):
+        us, ok = nb.lsoda(nb.builtin("brusselator1d"), pr.brusselator_u0(), np.linspace(0, 1.0, 6),
+                          pr.brusselator_sweep(6), 1e-6, 1e-8, strict=strict)
+        print("lsodaw strict=%s" % strict, ok.all())
+    us, ok = nb.lsoda(pr.upper_rhs, np.ones(12), np.linspace(0, 0.5, 5),
+                      np.array([[1000.0, 5000.0, 12.0]] * 3), 1e-6, 1e-9)
+    print("lsodaw pivoting", ok.all())
