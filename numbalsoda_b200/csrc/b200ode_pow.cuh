@@ -88,10 +88,7 @@ B200POW_FN double b200pow_add(double a, double b)
 #endif
 }
 
-#ifndef B200POW_ENTRY
-#define B200POW_ENTRY B200POW_FN
-#endif
-B200POW_ENTRY double b200ode_pow(double x, double y)
+B200POW_FN double b200ode_pow_impl(double x, double y)
 {
     unsigned long long ix = b200pow_bits(x);
     const unsigned topx = (unsigned)(ix >> 52);
@@ -171,6 +168,11 @@ B200POW_ENTRY double b200ode_pow(double x, double y)
     return b200pow_fma(t, scale, scale);
 }
 
-B200POW_FN double b200ode_pow_eighth(double x) { return b200ode_pow(x, 0.125); }
+#ifndef B200POW_ENTRY
+#define B200POW_ENTRY B200POW_FN
+#endif
+B200POW_ENTRY double b200ode_pow(double x, double y) { return b200ode_pow_impl(x, y); }
+
+B200POW_FN double b200ode_pow_eighth(double x) { return b200ode_pow_impl(x, 0.125); }
 
 #endif

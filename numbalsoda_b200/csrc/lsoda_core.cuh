@@ -106,6 +106,18 @@ __device__ __noinline__ double ls_div_rare(double a, double b) { return a / b; }
 LS_FN double ls_div_rare(double a, double b) { return a / b; }
 #endif
 
+// The step-size ratio formula of stoda / methodswitch / orderswitch,
+// 1 / (c * x^e + c * 1e-6)  (LSODA.cpp:1229, :1983, :1994, :2037, :2051, :2106, :2111),
+// six call sites: out of line together with pow in the thread-per-trajectory kernels.
+#if defined(__CUDA_ARCH__) && defined(B200POW_NOINLINE)
+__device__ __noinline__ double ls_rhfun(double c1, double x, double e, double c2)
+#else
+LS_FN double ls_rhfun(double c1, double x, double e, double c2)
+#endif
+{
+    return 1.0 / (c1 * b200ode_pow_impl(x, e) + c2);
+}
+
 // hmin / |h| with hmin = 0 (LSODA.cpp:401, :1155, :1243 ...): +0, or NaN when h is 0 or NaN
 LS_FN double ls_hmin_ratio(double h) { return 0.0 / fabs(h); }
 
@@ -166,7 +178,7 @@ LS_FN void ls_methodswitch(LsLane& s, const B200LsodaTables* T, double dsm, doub
             nqm2 = s.nq < LS_MXORDS ? s.nq : LS_MXORDS;
         } else {
             const double exsm = T->rcp[l];
-            double rh1 = ls_div(1.0, 1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
+            double rh1 = ls_rhfun(1.2, dsm, exsm, 0.0000012);
             double rh1it = 2.0 * rh1;
             pdh = s.pdlast * fabs(s.h);
             if ((pdh * rh1) > 0.00001) rh1it = ls_div(T->sm1[s.nq], pdh);
@@ -174,7 +186,7 @@ LS_FN void ls_methodswitch(LsLane& s, const B200LsodaTables* T, double dsm, doub
             // (nq <= 5 = mxords here, so the reference's nq > mxords branch, :1988-1994,
             // cannot be taken)
             const double dm2 = dsm * T->cm12[s.nq];
-            rh2 = ls_div(1.0, 1.2 * b200ode_pow(dm2, exsm) + 0.0000012);
+            rh2 = ls_rhfun(1.2, dm2, exsm, 0.0000012);
             nqm2 = s.nq;
             if (rh2 < 5.0 * rh1) return;
         }
@@ -188,14 +200,14 @@ LS_FN void ls_methodswitch(LsLane& s, const B200LsodaTables* T, double dsm, doub
     // currently BDF, LSODA.cpp:2026-2068 (nq <= mxords <= mxordn: :2030-2036 unreachable)
     const double exsm = T->rcp[l];
     double dm1 = dsm * T->cm21[s.nq];
-    double rh1 = ls_div(1.0, 1.2 * b200ode_pow(dm1, exsm) + 0.0000012);
+    double rh1 = ls_rhfun(1.2, dm1, exsm, 0.0000012);
     const int nqm1 = s.nq;
     const double exm1 = exsm;
     double rh1it = 2.0 * rh1;
     pdh = s.pdnorm * fabs(s.h);
     if ((pdh * rh1) > 0.00001) rh1it = ls_div(T->sm1[nqm1], pdh);
     rh1 = ls_min(rh1, rh1it);
-    const double rh2 = ls_div(1.0, 1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
+    const double rh2 = ls_rhfun(1.2, dsm, exsm, 0.0000012);
     if ((rh1 * 5.0) < (5.0 * rh2)) return;
     const double alpha = ls_max(0.001, rh1);
     dm1 *= b200ode_pow(alpha, exm1);
@@ -216,12 +228,12 @@ LS_FN int ls_orderswitch(LsLane& s, V& v, const B200LsodaTables* T, double rhup,
     const int lmax = (s.meth == 1 ? LS_MXORDN : LS_MXORDS) + 1;
     int newq;
     const double exsm = T->rcp[l];
-    double rhsm = ls_div(1.0, 1.2 * b200ode_pow(dsm, exsm) + 0.0000012);
+    double rhsm = ls_rhfun(1.2, dsm, exsm, 0.0000012);
     double rhdn = 0.0;
     if (s.nq != 1) {
         const double ddn = ls_div(v.norm_yh(l), TESCO(s.nq, 1));
         const double exdn = T->rcp[s.nq];
-        rhdn = ls_div(1.0, 1.3 * b200ode_pow(ddn, exdn) + 0.0000013);
+        rhdn = ls_rhfun(1.3, ddn, exdn, 0.0000013);
     }
     if (s.meth == 1) {
         pdh = ls_max(fabs(s.h) * s.pdlast, 0.000001);
@@ -633,7 +645,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
                     // savf = acor - yh[lmax], :1222-1228
                     const double dup = ls_div(v.norm_acor_minus_yh(lmax), TESCO(s.nq, 3));
                     const double exup = T->rcp[l + 1];
-                    rhup = ls_div(1.0, 1.4 * b200ode_pow(dup, exup) + 0.0000014);
+                    rhup = ls_rhfun(1.4, dup, exup, 0.0000014);
                 }
                 select_order = true;
             } else if (!(s.ialth > 1 || l == lmax)) {
