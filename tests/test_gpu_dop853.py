@@ -182,3 +182,33 @@ def test_device_resident_entry_point():
     assert bool((ok == 1).all()) and np.array_equal(usol.cpu().numpy(), ref)
     info = h.kernel_info()
     assert info["local_bytes"] == 0 and info["launches"] >= 1
+
+
+def test_reference_benchmark_rhs_verbatim_with_carray():
+    """benchmark/benchmark_lorenz.py:8-16 of the reference, verbatim (it views the raw
+    pointers with nb.carray): must compile for the device and reproduce the CPU cfunc."""
+    import numba as nb_
+    from numba import types
+    nb = _nb()
+
+    def f_(t, u_, du_, p_):
+        u = nb_.carray(u_, (3,))
+        p = nb_.carray(p_, (3,))
+        sigma, rho, beta = p
+        x, y, z = u
+        du_[0] = sigma * (y - x)
+        du_[1] = x * (rho - z) - y
+        du_[2] = x * y - beta * z
+
+    sig = types.void(types.double, types.CPointer(types.double), types.CPointer(types.double),
+                     types.CPointer(types.double))
+    cf = nb_.cfunc(sig)(f_)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0.0, 10.0, 101)
+    P = pr.lorenz_sweep(33)
+    us, ok = nb.dop853(cf.address, u0, te, P, 1e-8, 1e-8, strict=True)
+    ref, okr, _ = orc.solve_batch("dop853", cf.address, u0, te, P, 1e-8, 1e-8)
+    assert ok.all() and okr.all() and np.array_equal(us, ref)
+    us, ok = nb.lsoda(cf.address, u0, te, P, 1e-8, 1e-8, strict=True)
+    ref, okr, _ = orc.solve_batch("lsoda", cf.address, u0, te, P, 1e-8, 1e-8)
+    assert ok.all() and okr.all() and np.array_equal(us, ref)
