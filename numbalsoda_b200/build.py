@@ -104,6 +104,12 @@ def build(force=False, verbose=False):
     if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
         _run([NVCC] + ARCH + NVCC_FLAGS + os.environ.get("B200ODE_EXTRA_DEFS", "").split() + ["-o", out, srcp])
     images.append(("lsodaw", out))
+    # DOP853, one warp per trajectory
+    srcp = os.path.join(CSRC, "dop853_warp_kernel.cu")
+    out = os.path.join(OBJ, "dop853w.fatbin")
+    if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
+        _run([NVCC] + ARCH + NVCC_FLAGS + ["-o", out, srcp])
+    images.append(("dop853w", out))
     srcp = os.path.join(CSRC, "rhs_builtin.cu")
     for r in BUILTIN_RHS:
         out = os.path.join(OBJ, "rhs_%s.fatbin" % r)

@@ -153,15 +153,17 @@ struct b200ode_rhs_s {
     int last_grid = 0;
 };
 
-// LSODA systems larger than B200ODE_THREAD_NMAX run one trajectory per warp
-// (lsoda_warp_kernel.cu: a single image, system size passed at run time).
+// Systems larger than B200ODE_THREAD_NMAX run one trajectory per warp
+// (dop853_warp_kernel.cu, lsoda_warp_kernel.cu: one image each, size passed at run time).
 static bool warp_kernel(int solver, int neq)
 {
-    return solver == B200ODE_LSODA && neq > B200ODE_THREAD_NMAX;
+    (void)solver;
+    return neq > B200ODE_THREAD_NMAX;
 }
 static const char* kernel_name(int solver, int neq)
 {
-    if (solver == B200ODE_DOP853) return "b200ode_dop853_kernel";
+    if (solver == B200ODE_DOP853)
+        return warp_kernel(solver, neq) ? "b200ode_dop853w_kernel" : "b200ode_dop853_kernel";
     return warp_kernel(solver, neq) ? "b200ode_lsodaw_kernel" : "b200ode_lsoda_kernel";
 }
 
@@ -177,8 +179,8 @@ extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t s
     char name[64];
     if (warp_kernel(solver, neq)) {
         if (neq > B200ODE_WARP_NMAX)
-            return fail(B200ODE_ENOSYS, "lsoda: neq = %d exceeds %d", neq, B200ODE_WARP_NMAX);
-        snprintf(name, sizeof name, "lsodaw");
+            return fail(B200ODE_ENOSYS, "neq = %d exceeds %d", neq, B200ODE_WARP_NMAX);
+        snprintf(name, sizeof name, solver == B200ODE_DOP853 ? "dop853w" : "lsodaw");
     } else {
         snprintf(name, sizeof name, "%s_n%d", solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq);
     }
@@ -309,10 +311,14 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
         CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
         CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
-        if (warp) {
+        if (warp && H->solver == B200ODE_DOP853) {
+            P.threads = 32;
+            P.dyn_smem = B200ODE_DOP853W_DOUBLES(H->neq) * (int)sizeof(double);
+        } else if (warp) {
             P.threads = 32;
             P.dyn_smem = B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double);
-            // B200ODE_WM=global: iteration matrices in global memory (more warps per SM)
+            // B200ODE_WM=global: iteration matrices in global memory (more warps per SM;
+            // measured slower at n = 64: 50 k vs 64 k traj/s, the LU then waits on L2)
             const char* wm = getenv("B200ODE_WM");
             if (wm && !strcmp(wm, "global"))
                 P.dyn_smem -= B200ODE_LSODAW_MATRIX(H->neq) * (int)sizeof(double);
@@ -348,7 +354,8 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
         CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
         if (P.blocks_per_sm < 1) P.blocks_per_sm = 1;
-        if (warp && P.dyn_smem < B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double)) {
+        if (warp && H->solver == B200ODE_LSODA &&
+            P.dyn_smem < B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double)) {
             P.wm_set_bytes = (size_t)P.sms * P.blocks_per_sm * B200ODE_LSODAW_MATRIX(H->neq) * sizeof(double);
             CU(cuMemAlloc_v2(&P.wm_scratch, P.wm_set_bytes * PerDevice::kScratchSets));
             for (int i = 0; i < PerDevice::kScratchSets; i++)

@@ -12,10 +12,12 @@
 #define B200ODE_DOP853_QFIELDS(n) (4 + 11 * (n))
 #define B200ODE_THREADS 128 /* threads per block of every solver kernel */
 
-/* LSODA: systems of up to B200ODE_THREAD_NMAX equations run one trajectory per thread
- * (lsoda_kernel.cu, one image per size), larger ones -- up to B200ODE_WARP_NMAX -- one
- * trajectory per warp (lsoda_warp_kernel.cu, a single image, size at run time) with this
- * many doubles of dynamic shared memory per warp (lsoda_vec_warp.cuh). */
+/* Systems of up to B200ODE_THREAD_NMAX equations run one trajectory per thread
+ * (dop853_kernel.cu, lsoda_kernel.cu: one image per size), larger ones -- up to
+ * B200ODE_WARP_NMAX -- one trajectory per warp (dop853_warp_kernel.cu, lsoda_warp_kernel.cu:
+ * a single image each, size at run time) with this many doubles of dynamic shared memory
+ * per warp. */
+#define B200ODE_DOP853W_DOUBLES(n) (22 * (n)) /* dop853_warp.cuh: shared memory of one trajectory */
 #define B200ODE_THREAD_NMAX 8
 #define B200ODE_WARP_NMAX 128
 #define B200ODE_LSODAW_JCOLS 8 /* Jacobian columns evaluated concurrently */

@@ -1,0 +1,54 @@
+// Warp-level primitives shared by the warp-per-trajectory kernels (lsoda_vec_warp.cuh,
+// dop853_warp.cuh): one warp owns one trajectory, lane i owns components i, i + 32, ...
+// The same headers compile as host C++ for the CPU parity harnesses (tests/*_host.cpp):
+// there a single "lane" walks every component in order.
+#ifndef B200ODE_WARP_CUH
+#define B200ODE_WARP_CUH
+
+#if defined(__CUDACC__)
+#define WV_FN __device__ __forceinline__
+#else
+#define WV_FN static inline
+#endif
+
+// std::max semantics (a NaN second operand is ignored): the reduction of per-lane
+// partial maxima that started from 0 and ignored NaNs the same way is order independent
+WV_FN double wv_stdmax(double a, double b) { return (a < b) ? b : a; }
+
+#if defined(__CUDA_ARCH__)
+#define WV_LANE ((int)(threadIdx.x & 31u))
+#define WV_NL 32
+#define WV_SYNC() __syncwarp()
+WV_FN double wv_bcast(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+WV_FN double wv_max(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = wv_stdmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+WV_FN bool wv_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+// first position of the largest value: larger v wins, ties go to the smaller index
+WV_FN void wv_argmax(unsigned long long& v, int& j)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+        if (ov > v || (ov == v && oj < j)) {
+            v = ov;
+            j = oj;
+        }
+    }
+}
+#else
+// host build (tests/lsoda_core_host.cpp): one "lane" walks every component in order
+#define WV_LANE 0
+#define WV_NL 1
+#define WV_SYNC() (void)0
+WV_FN double wv_bcast(double x, int) { return x; }
+WV_FN double wv_max(double x) { return x; }
+WV_FN bool wv_any(bool p) { return p; }
+WV_FN void wv_argmax(unsigned long long&, int&) {}
+#endif
+
+#endif

@@ -41,41 +41,7 @@
 
 #include "lsoda_core.cuh"
 
-#if defined(__CUDA_ARCH__)
-#define WV_LANE ((int)(threadIdx.x & 31u))
-#define WV_NL 32
-#define WV_SYNC() __syncwarp()
-LS_FN double wv_bcast(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
-LS_FN double wv_max(double x)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = ls_max(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
-}
-LS_FN bool wv_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
-// first position of the largest value: larger v wins, ties go to the smaller index
-LS_FN void wv_argmax(unsigned long long& v, int& j)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
-        if (ov > v || (ov == v && oj < j)) {
-            v = ov;
-            j = oj;
-        }
-    }
-}
-#else
-// host build (tests/lsoda_core_host.cpp): one "lane" walks every component in order
-#define WV_LANE 0
-#define WV_NL 1
-#define WV_SYNC() (void)0
-LS_FN double wv_bcast(double x, int) { return x; }
-LS_FN double wv_max(double x) { return x; }
-LS_FN bool wv_any(bool p) { return p; }
-LS_FN void wv_argmax(unsigned long long&, int&) {}
-#endif
+#include "b200ode_warp.cuh"
 
 #define WV_NMAX 128
 // Jacobian columns evaluated concurrently (each needs a private copy of y in shared

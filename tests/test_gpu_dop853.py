@@ -212,3 +212,52 @@ def test_reference_benchmark_rhs_verbatim_with_carray():
     us, ok = nb.lsoda(cf.address, u0, te, P, 1e-8, 1e-8, strict=True)
     ref, okr, _ = orc.solve_batch("lsoda", cf.address, u0, te, P, 1e-8, 1e-8)
     assert ok.all() and okr.all() and np.array_equal(us, ref)
+
+
+# ---------------------------------------------------------------- warp-per-trajectory kernel
+def test_warp_kernel_n64_strict_bitwise_and_fast():
+    """Systems of more than 8 equations run one trajectory per warp (dop853_warp_kernel.cu):
+    n = 64 Brusselator with mild diffusion (non-stiff), states and counters bit for bit."""
+    nb = _nb()
+    B = 80
+    rng = np.random.default_rng(3)
+    P = np.stack([rng.uniform(0.8, 1.2, B), rng.uniform(2.5, 3.5, B), 10.0 ** rng.uniform(-1, 0.7, B)], axis=1)
+    u0 = np.stack([pr.brusselator_u0(P[b, 0], P[b, 1]) for b in range(B)])
+    te = np.linspace(0.0, 5.0, 51)
+    us, ok, cnt = nb.dop853(nb.builtin("brusselator1d"), u0, te, P, 1e-7, 1e-9, strict=True, counters=True)
+    ref, okr, cr = orc.solve_batch("dop853", orc.builtin_rhs("brusselator1d"), u0, te, P, 1e-7, 1e-9)
+    assert ok.all() and okr.all() and us.shape == (B, 51, 64)
+    assert np.array_equal(cnt[:, :7], cr[:, :7]) and np.array_equal(us, ref)
+    us2, ok2 = nb.dop853(nb.builtin("brusselator1d"), u0, te, P, 1e-7, 1e-9)
+    assert ok2.all() and np.abs(us2 - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_warp_kernel_numba_rhs_sizes_and_edge_cases():
+    import numba
+    nb = _nb()
+
+    def chain(t, u, du, p):
+        n = int(p[1])
+        k = p[0]
+        du[0] = -k * u[0] + 0.5 * u[1] * u[1]
+        for i in range(1, n - 1):
+            du[i] = k * (u[i - 1] - u[i]) / (1.0 + i) + 0.1 * u[i + 1] - 0.1 * u[i] * u[i]
+        du[n - 1] = k * (u[n - 2] - u[n - 1]) / n
+
+    cf = numba.cfunc(nb.lsoda_sig)(chain)
+    for n in (9, 20, 33):
+        u0n = 1.0 + 0.1 * np.arange(n)
+        Pn = np.array([[2.0 * (1 + b), float(n)] for b in range(5)])
+        ten = np.linspace(0.0, 5.0, 11)
+        us, ok, cnt = nb.dop853(chain, u0n, ten, Pn, 1e-7, 1e-9, strict=True, counters=True)
+        ref, okr, cr = orc.solve_batch("dop853", cf.address, u0n, ten, Pn, 1e-7, 1e-9)
+        assert list(ok) == list(okr) and np.array_equal(cnt[:, :7], cr[:, :7]) and np.array_equal(us, ref), n
+    f, fo = nb.builtin("brusselator1d"), orc.builtin_rhs("brusselator1d")
+    u0, d, te = pr.brusselator_u0(), np.array([1.0, 3.0, 0.5]), np.linspace(0, 2, 21)
+    for kw in (dict(mxstep=0), dict(mxstep=7), dict(te=np.array([0.0])), dict(te=np.linspace(2, 0, 5)),
+               dict(te=np.array([0.0, 1e-4, 1e-4, 2e-4, 0.5]))):
+        te2 = kw.pop("te", te)
+        us, ok, cnt = nb.dop853(f, u0, te2, d, 1e-7, 1e-9, strict=True, counters=True, **kw)
+        ref, okr, st = orc.dop853(fo, u0, te2, d, 1e-7, 1e-9, **kw)
+        assert ok == okr and cnt[5] == st.idid and cnt[6] == st.rows, (kw, list(cnt))
+        assert np.array_equal(us[:st.rows], ref[:st.rows])
