@@ -301,7 +301,8 @@ struct LsWarpVec {
                     WMT(r, j) = WMT(r, k);
                     WMT(r, k) = tr;
                 }
-                // (a hand-pipelined pointer-walking version of this loop measured 6 % slower)
+                // (measured slower at n = 64: a hand-pipelined pointer-walking version of this
+                // loop, -6 %; a lane per column with the pivot-row entry in a register, -7 %)
 #pragma unroll 4
                 for (int c = k + 1; c < n; c++) WMT(r, c) = tr * WMT(k, c) + WMT(r, c);
             }
