@@ -102,7 +102,8 @@ def build(force=False, verbose=False):
     srcp = os.path.join(CSRC, "lsoda_warp_kernel.cu")
     out = os.path.join(OBJ, "lsodaw.fatbin")
     if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
-        _run([NVCC] + ARCH + NVCC_FLAGS + os.environ.get("B200ODE_EXTRA_DEFS", "").split() + ["-o", out, srcp])
+        _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200POW_NOINLINE"] +
+             os.environ.get("B200ODE_EXTRA_DEFS", "").split() + ["-o", out, srcp])
     images.append(("lsodaw", out))
     # DOP853, one warp per trajectory
     srcp = os.path.join(CSRC, "dop853_warp_kernel.cu")

@@ -15,12 +15,31 @@
 // partial maxima that started from 0 and ignored NaNs the same way is order independent
 WV_FN double wv_stdmax(double a, double b) { return (a < b) ? b : a; }
 
+// The user's right-hand side, called from one place: with link-time optimisation every
+// call site would get its own inlined copy of the RHS (a method-of-lines RHS is thousands
+// of instructions), and the warp kernels -- a few warps per SM, each in a different part
+// of a large program -- are bound by instruction fetch before anything else.
+#if defined(__CUDA_ARCH__)
+extern "C" __device__ long long b200ode_user_rhs(double t, double* u, double* du, double* p);
+__device__ __noinline__ void wv_user_rhs(double t, double* u, double* du, double* p)
+{
+    b200ode_user_rhs(t, u, du, p);
+}
+#else
+#define wv_user_rhs(t, u, du, p) b200ode_user_rhs(t, u, du, p)
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define WV_LANE ((int)(threadIdx.x & 31u))
 #define WV_NL 32
 #define WV_SYNC() __syncwarp()
 WV_FN double wv_bcast(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
-WV_FN double wv_max(double x)
+#if defined(WV_MAX_NOINLINE)
+__device__ __noinline__
+#else
+WV_FN
+#endif
+double wv_max(double x)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = wv_stdmax(x, __shfl_xor_sync(0xffffffffu, x, o));

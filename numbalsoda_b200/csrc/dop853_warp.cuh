@@ -72,7 +72,7 @@ WV_FN void dop853_warp_solve(int n, double* w, const double* u0, double* pp, int
 #define DW_RHS(t, u, du)                                \
     do {                                                \
         WV_SYNC();                                      \
-        if (WV_LANE == 0) b200ode_user_rhs(t, u, du, pp); \
+        if (WV_LANE == 0) wv_user_rhs(t, u, du, pp);      \
         WV_SYNC();                                      \
     } while (0)
     // set_parameters: nmax <= 0 is rejected, module :243-246 -> c_interface :106-109

@@ -99,8 +99,12 @@ LS_FN double ls_min(double a, double b) { return (b < a) ? b : a; }
 // routine -- an experiment against the kernel's instruction-cache misses (ncu
 // stall_no_instruction, profiles/r1_lsoda_v3) that measured SLOWER on Robertson (4.40 M
 // vs 4.66 M traj/s; every division out of line: 4.28 M), so it is off by default.
+#if defined(__CUDA_ARCH__) && defined(B200_DIV_NOINLINE_ALL)
+__device__ __noinline__ double ls_div(double a, double b) { return a / b; }
+#else
 LS_FN double ls_div(double a, double b) { return a / b; }
-#if defined(__CUDA_ARCH__) && defined(B200_DIV_NOINLINE)
+#endif
+#if defined(__CUDA_ARCH__) && (defined(B200_DIV_NOINLINE) || defined(B200_DIV_NOINLINE_ALL))
 __device__ __noinline__ double ls_div_rare(double a, double b) { return a / b; }
 #else
 LS_FN double ls_div_rare(double a, double b) { return a / b; }

@@ -55,6 +55,20 @@
 
 #include "b200ode_launch.h"  // B200ODE_LSODAW_DOUBLES(n): shared memory of one trajectory
 
+// vmnorm (LSODA.cpp:1705-1712): max_i |v_i| w_i; one out-of-line copy (it is used from a
+// dozen places and the warp kernel is bound by instruction fetch)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+static inline
+#endif
+double wv_wmax_norm(const double* v, const double* w, int n)
+{
+    double vm = 0.0;
+    WV_FOR_OWN(i) vm = ls_max(vm, fabs(v[i]) * w[i]);
+    return wv_max(vm);
+}
+
 struct LsWarpVec {
     int n, ld;
     bool fast;  // parallel triangular solves (see above); false = the reference's summation order
@@ -88,12 +102,7 @@ struct LsWarpVec {
     LS_MFN int size() const { return n; }
     LS_MFN void sync(unsigned) {}
 
-    LS_MFN double norm_ptr(const double* v) const
-    {
-        double vm = 0.0;
-        WV_FOR_OWN(i) vm = ls_max(vm, fabs(v[i]) * ewt[i]);
-        return wv_max(vm);
-    }
+    LS_MFN double norm_ptr(const double* v) const { return wv_wmax_norm(v, ewt, n); }
     LS_MFN double norm_yh(int j) const { return norm_ptr(yh + (j - 1) * n); }
     LS_MFN double norm_acor() const { return norm_ptr(acor); }
     LS_MFN double norm_acor_minus_yh(int j)
@@ -108,7 +117,7 @@ struct LsWarpVec {
         WV_FOR_OWN(i) {
             double w = rtol * fabs(WYH(1, i)) + atol;
             if (w <= 0.0) bad = true;
-            ewt[i] = 1.0 / w;
+            ewt[i] = ls_div(1.0, w);
         }
         bad = wv_any(bad);
         WV_SYNC();
@@ -149,7 +158,7 @@ struct LsWarpVec {
     LS_MFN void rhs_to(double t, double* out, double* pp)
     {
         WV_SYNC();
-        if (WV_LANE == 0) b200ode_user_rhs(t, y, out, pp);
+        if (WV_LANE == 0) wv_user_rhs(t, y, out, pp);
         WV_SYNC();
     }
     LS_MFN void rhs_savf(double t, double* pp) { rhs_to(t, savf, pp); }
@@ -242,6 +251,7 @@ struct LsWarpVec {
     }
     LS_MFN double tol_floor(double atol, double tol) const
     {
+#pragma unroll 1
         WV_FOR_OWN(i) {
             const double ayi = fabs(y[i]);
             if (ayi != 0.0) tol = ls_max(tol, atol / ayi);
@@ -292,7 +302,7 @@ struct LsWarpVec {
                 }
             }
             WV_SYNC();
-            const double t = -1.0 / akj;
+            const double t = ls_div(-1.0, akj);
             for (int c = k + 1 + WV_LANE; c < n; c += WV_NL) WMT(k, c) = t * WMT(k, c);
             WV_SYNC();
             for (int r = k + 1 + WV_LANE; r < n; r += WV_NL) {
@@ -315,7 +325,7 @@ struct LsWarpVec {
             // reciprocals of the diagonal, and the composition of the interchanges:
             // x[i] = w[perm[i]] after the swap-free back substitution
             WV_FOR_OWN(i) {
-                rdiag[i] = 1.0 / WMT(i, i);
+                rdiag[i] = ls_div(1.0, WMT(i, i));
                 perm[i] = i;
             }
             WV_SYNC();
@@ -349,7 +359,7 @@ struct LsWarpVec {
                     if (c >= n) break;
                     double bc = 0.0;
                     if (WV_LANE == cc) {
-                        bc = fast ? (b[c] - t[q]) * rdiag[c] : (b[c] - t[q]) / WMT(c, c);
+                        bc = fast ? (b[c] - t[q]) * rdiag[c] : ls_div(b[c] - t[q], WMT(c, c));
                         b[c] = bc;
                     }
                     bc = wv_bcast(bc, cc);
@@ -436,11 +446,11 @@ struct LsWarpVec {
                 double* u = ucopy + WV_LANE * ld;
                 for (int i = 0; i < n; i++) u[i] = y[i];
                 const double yj = y[j];
-                const double r = ls_max(LS_SQRTETA * fabs(yj), r0 / ewt[j]);
+                const double r = ls_max(LS_SQRTETA * fabs(yj), ls_div(r0, ewt[j]));
                 u[j] = yj + r;
-                const double fac = -hl0 / r;
+                const double fac = ls_div(-hl0, r);
                 double* col = wmT + j * ld;
-                b200ode_user_rhs(tn, u, col, pp);
+                wv_user_rhs(tn, u, col, pp);
                 for (int i = 0; i < n; i++) col[i] = (col[i] - savf[i]) * fac;
             }
             WV_SYNC();
@@ -449,11 +459,11 @@ struct LsWarpVec {
         WV_FOR_OWN(i) {
             double sum = 0.0;
 #pragma unroll 4
-            for (int j = 0; j < n; j++) sum += fabs(WMT(i, j)) / ewt[j];
+            for (int j = 0; j < n; j++) sum += ls_div(fabs(WMT(i, j)), ewt[j]);
             an = ls_max(an, sum * ewt[i]);
         }
         an = wv_max(an);
-        pdnorm = an / fabs(hl0);
+        pdnorm = ls_div(an, fabs(hl0));
         WV_FOR_OWN(i) WMT(i, i) = WMT(i, i) + 1.0;
         WV_SYNC();
         return dgefa() != 0 ? 1 : 0;

@@ -25,7 +25,9 @@ extern "C" __device__ long long b200ode_user_rhs(double t, double* u, double* du
 #elif defined(B200_RHS_BRUSSELATOR1D)
     const double A = p[0], B = p[1], D = p[2];
     const int m = 32;
-#pragma unroll
+    // (not unrolled: in the warp-per-trajectory kernels one lane evaluates this, and code
+    // size -- instruction fetch -- is what binds them; numba emits a loop as well)
+#pragma unroll 1
     for (int i = 0; i < m; i++) {
         const double uu = u[i], v = u[m + i];
         const double ul = (i == 0) ? A : u[i - 1];
