@@ -117,6 +117,36 @@ int b200ode_lsoda_batched_device(b200ode_rhs_t rhs, long long B, int neq, const 
                                  int* success, int* counters, int exit_on_warning,
                                  void* stream);
 
+/* The same two calls with every argument in one structure, plus what the positional
+ * entry points cannot express: per-trajectory tolerances (SURVEY.md section 8f, rank 1 --
+ * the reference takes one scalar rtol / atol, numbalsoda/driver.py:29; its ewset supports
+ * more, LSODA.cpp:1368-1390).  The solver is the one `rhs` was linked for.  Zero-initialise
+ * the structure and set `size = sizeof(b200ode_problem)`. */
+typedef struct b200ode_problem {
+    size_t size;
+    long long B;
+    int neq;
+    const double* u0;       /* [B,neq] (u0_stride = neq) or [neq] shared (u0_stride = 0) */
+    long long u0_stride;
+    const void* data;       /* as b200ode_dop853_batched */
+    long long data_stride;
+    int np;
+    int nt;
+    const double* teval;    /* [nt] */
+    double* usol;           /* [B,nt,neq] */
+    double rtol, atol;      /* used where the arrays below are NULL */
+    const double* rtol_b;   /* [B] or NULL */
+    const double* atol_b;   /* [B] or NULL */
+    int mxstep;
+    int exit_on_warning;    /* lsoda only */
+    int* success;           /* [B] */
+    int* counters;          /* [B,8] or NULL */
+} b200ode_problem;
+/* host pointers; copies to / from `device` */
+int b200ode_solve(b200ode_rhs_t rhs, const b200ode_problem* problem, int device);
+/* device pointers on the current device; asynchronous on `stream` */
+int b200ode_solve_device(b200ode_rhs_t rhs, const b200ode_problem* problem, void* stream);
+
 /* Page-locked host memory for usol / success / counters: with it the device-to-host
  * copies of b200ode_*_batched run at full PCIe speed and overlap the kernels (with pageable
  * memory the driver stages them).  The reference's driver allocates usol with np.empty

@@ -16,6 +16,17 @@ class B200OdeError(RuntimeError):
     pass
 
 
+class Problem(ct.Structure):
+    """b200ode_problem (include/b200ode.h)."""
+    _fields_ = [("size", ct.c_size_t), ("B", ct.c_longlong), ("neq", ct.c_int),
+                ("u0", ct.c_void_p), ("u0_stride", ct.c_longlong), ("data", ct.c_void_p),
+                ("data_stride", ct.c_longlong), ("np", ct.c_int), ("nt", ct.c_int),
+                ("teval", ct.c_void_p), ("usol", ct.c_void_p), ("rtol", ct.c_double),
+                ("atol", ct.c_double), ("rtol_b", ct.c_void_p), ("atol_b", ct.c_void_p),
+                ("mxstep", ct.c_int), ("exit_on_warning", ct.c_int), ("success", ct.c_void_p),
+                ("counters", ct.c_void_p)]
+
+
 def _load(rebuilt=False):
     if not os.path.exists(LIBPATH):
         from . import build as _build
@@ -39,6 +50,8 @@ def _load(rebuilt=False):
     lib.b200ode_dop853_batched_device.argtypes = common + [vp]
     lib.b200ode_lsoda_batched_device.argtypes = common + [i, vp]
     lib.b200ode_kernel_info.argtypes = [vp, ct.POINTER(i * 8)]
+    lib.b200ode_solve.argtypes = [vp, ct.POINTER(Problem), i]
+    lib.b200ode_solve_device.argtypes = [vp, ct.POINTER(Problem), vp]
     lib.b200ode_host_alloc.argtypes = [sz, ct.POINTER(vp)]
     lib.b200ode_host_free.argtypes = [vp]
     return lib

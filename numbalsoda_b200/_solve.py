@@ -66,6 +66,17 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
         usol = np.empty((B, nt, n), dtype=np.float64)  # as the reference, driver.py:35
     ok = np.full(B, 999, dtype=np.int32)
     cnt = np.zeros((B, _lib.NCOUNTERS), dtype=np.int32) if counters else None
+    # rtol / atol: the reference's scalars, or one value per trajectory (shape [B])
+    rtol_b = atol_b = None
+    if np.ndim(rtol) > 0:
+        rtol_b = np.ascontiguousarray(rtol, dtype=np.float64)
+        rtol = 0.0
+    if np.ndim(atol) > 0:
+        atol_b = np.ascontiguousarray(atol, dtype=np.float64)
+        atol = 0.0
+    for name, arr in (("rtol", rtol_b), ("atol", atol_b)):
+        if arr is not None and arr.shape != (B,):
+            raise ValueError("%s must be a scalar or have shape (%d,)" % (name, B))
 
     devices = _device_list(device)
 
@@ -75,15 +86,19 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
             return
         u0p = u0[b0:b1] if batched_u0 else u0
         dp = dbuf[b0:b1] if batched_data else dbuf
-        args = [handle.ptr, nb, n, u0p.ctypes.data, n if batched_u0 else 0, dp.ctypes.data,
-                rec if batched_data else -rec, nps, nt, t_eval.ctypes.data,
-                usol[b0:b1].ctypes.data, float(rtol), float(atol), int(mxstep),
-                ok[b0:b1].ctypes.data, cnt[b0:b1].ctypes.data if counters else None]
-        if solver == _lib.DOP853:
-            rc = _lib.lib.b200ode_dop853_batched(*args, dev)
-        else:
-            rc = _lib.lib.b200ode_lsoda_batched(*args, int(bool(exit_on_warning)), dev)
-        _lib.check(rc)
+        pb = _lib.Problem()
+        pb.size = ct.sizeof(_lib.Problem)
+        pb.B, pb.neq, pb.nt, pb.np = nb, n, nt, nps
+        pb.u0, pb.u0_stride = u0p.ctypes.data, (n if batched_u0 else 0)
+        pb.data, pb.data_stride = dp.ctypes.data, (rec if batched_data else -rec)
+        pb.teval, pb.usol = t_eval.ctypes.data, usol[b0:b1].ctypes.data
+        pb.rtol, pb.atol = float(rtol), float(atol)
+        pb.rtol_b = rtol_b[b0:b1].ctypes.data if rtol_b is not None else None
+        pb.atol_b = atol_b[b0:b1].ctypes.data if atol_b is not None else None
+        pb.mxstep, pb.exit_on_warning = int(mxstep), int(bool(exit_on_warning))
+        pb.success = ok[b0:b1].ctypes.data
+        pb.counters = cnt[b0:b1].ctypes.data if counters else None
+        _lib.check(_lib.lib.b200ode_solve(handle.ptr, ct.byref(pb), dev))
 
     if len(devices) == 1 or B < 2 * len(devices):
         run(devices[0], 0, B)

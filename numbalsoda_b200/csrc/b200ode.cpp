@@ -420,7 +420,8 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
                         long long u0_stride, const void* data, long long data_stride, int np,
                         int nt, const double* teval, double* usol, double rtol, double atol,
                         int mxstep, int* success, int* counters, int exit_on_warning,
-                        void* stream)
+                        void* stream, const double* rtol_b = nullptr,
+                        const double* atol_b = nullptr)
 {
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
@@ -440,6 +441,8 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
     a.usol = usol;
     a.rtol = rtol;
     a.atol = atol;
+    a.rtol_b = rtol_b;
+    a.atol_b = atol_b;
     a.mxstep = mxstep;
     a.exit_on_warning = exit_on_warning;
     a.success = success;
@@ -562,7 +565,8 @@ static double now_ms()
 static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const double* u0,
                       long long u0_stride, const void* data, long long data_stride, int np,
                       int nt, const double* teval, double* usol, double rtol, double atol,
-                      int mxstep, int* success, int* counters, int exit_on_warning, int device)
+                      int mxstep, int* success, int* counters, int exit_on_warning, int device,
+                      const double* rtol_b = nullptr, const double* atol_b = nullptr)
 {
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
@@ -589,9 +593,11 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     const size_t rec = data_stride != 0 ? (size_t)(data_stride > 0 ? data_stride : -data_stride)
                                         : (size_t)(np > 0 ? np * 8 : 0);
     const size_t data_bytes = data ? (data_stride > 0 ? (size_t)data_stride * (size_t)B : rec) : 0;
+    const size_t tol_bytes = sizeof(double) * (size_t)B;
     const size_t in_bytes = align256(sizeof(double) * nt) +
                             align256(sizeof(double) * neq * (size_t)(u0_stride ? B : 1)) +
-                            align256(data_bytes);
+                            align256(data_bytes) + (rtol_b ? align256(tol_bytes) : 0) +
+                            (atol_b ? align256(tol_bytes) : 0);
     // chunk size: at least 4 trajectories per resident lane (a persistent grid needs a few
     // per lane to balance), about 1/8 of the ensemble, at most 1 GiB of rows per buffer
     // (when PCIe binds, what is exposed is the first chunk's kernel and nothing else)
@@ -612,6 +618,8 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     const CUdeviceptr d_te = mem.take(sizeof(double) * nt);
     const CUdeviceptr d_u0 = mem.take(sizeof(double) * neq * (size_t)(u0_stride ? B : 1));
     const CUdeviceptr d_data = mem.take(data_bytes);
+    const CUdeviceptr d_rtol = rtol_b ? mem.take(tol_bytes) : 0;
+    const CUdeviceptr d_atol = atol_b ? mem.take(tol_bytes) : 0;
     CUdeviceptr d_usol[3], d_ok[3], d_cnt[3] = {0, 0, 0};
     for (int i = 0; i < nbuf; i++) {
         d_usol[i] = mem.take(row_bytes * (size_t)chunk);
@@ -640,6 +648,8 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
         CU(cuMemcpyHtoDAsync_v2(d_u0, u0, sizeof(double) * neq, sk[0].s));
     }
     if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data, data, data_bytes, sk[0].s));
+    if (rtol_b) CU(cuMemcpyHtoDAsync_v2(d_rtol, rtol_b, tol_bytes, sk[0].s));
+    if (atol_b) CU(cuMemcpyHtoDAsync_v2(d_atol, atol_b, tol_bytes, sk[0].s));
     CU(cuEventRecord(ev_in.e, sk[0].s));
     CU(cuStreamWaitEvent(sk[1].s, ev_in.e, 0));
 
@@ -673,6 +683,8 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
         a.usol = reinterpret_cast<double*>(d_usol[i]);
         a.rtol = rtol;
         a.atol = atol;
+        a.rtol_b = rtol_b ? reinterpret_cast<const double*>(d_rtol) + b0 : nullptr;
+        a.atol_b = atol_b ? reinterpret_cast<const double*>(d_atol) + b0 : nullptr;
         a.mxstep = mxstep;
         a.exit_on_warning = exit_on_warning;
         a.success = reinterpret_cast<int*>(d_ok[i]);
@@ -715,6 +727,38 @@ extern "C" int b200ode_lsoda_batched(b200ode_rhs_t H, long long B, int neq, cons
 {
     return solve_host(B200ODE_LSODA, H, B, neq, u0, u0_stride, data, data_stride, np, nt, teval,
                       usol, rtol, atol, mxstep, success, counters, exit_on_warning, device);
+}
+
+// ---------------------------------------------------------------- structure-based entry points
+static int check_problem(b200ode_rhs_t H, const b200ode_problem* p)
+{
+    if (!H) return fail(B200ODE_EINVAL, "rhs handle is NULL");
+    if (!p) return fail(B200ODE_EINVAL, "problem is NULL");
+    if (p->size != sizeof(b200ode_problem))
+        return fail(B200ODE_EINVAL, "problem.size = %zu, expected sizeof(b200ode_problem) = %zu",
+                    p->size, sizeof(b200ode_problem));
+    return 0;
+}
+
+extern "C" int b200ode_solve(b200ode_rhs_t H, const b200ode_problem* p, int device)
+{
+    int rc = check_problem(H, p);
+    if (rc) return rc;
+    return solve_host(H->solver, H, p->B, p->neq, p->u0, p->u0_stride, p->data, p->data_stride,
+                      p->np, p->nt, p->teval, p->usol, p->rtol, p->atol, p->mxstep, p->success,
+                      p->counters, H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, device,
+                      p->rtol_b, p->atol_b);
+}
+
+extern "C" int b200ode_solve_device(b200ode_rhs_t H, const b200ode_problem* p, void* stream)
+{
+    int rc = check_problem(H, p);
+    if (rc) return rc;
+    return solve_device(H->solver, H, p->B, p->neq, p->u0, p->u0_stride, p->data,
+                        p->data_stride, p->np, p->nt, p->teval, p->usol, p->rtol, p->atol,
+                        p->mxstep, p->success, p->counters,
+                        H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, stream, p->rtol_b,
+                        p->atol_b);
 }
 
 // ---------------------------------------------------------------- pinned host memory

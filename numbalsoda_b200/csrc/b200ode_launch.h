@@ -36,6 +36,8 @@ typedef struct B200OdeLaunch {
     const double* t_eval;     /* [nt] */
     double* usol;             /* [B,nt,n], the reference's row layout per trajectory */
     double rtol, atol;
+    const double* rtol_b;     /* [B] per-trajectory tolerances, or null: the scalars apply */
+    const double* atol_b;
     int mxstep;
     int exit_on_warning;      /* lsoda only */
     int neq;                  /* system size (run-time for the warp-per-trajectory kernel) */

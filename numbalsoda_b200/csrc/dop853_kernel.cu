@@ -273,6 +273,10 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     // profiles/r1_dop853_v2: the two t_eval loads were 12 % of the stall samples), at no
     // cost in registers (the kernel sits at the 168-register bound of 3 blocks per SM)
 #define XOUT span[4 + threadIdx.x]
+    // the tolerances of this lane's trajectory (scalars, or per trajectory: rtol_b / atol_b),
+    // also in shared memory for the same reason
+#define RTOL span[4 + B200_THREADS + threadIdx.x]
+#define ATOL span[4 + 2 * B200_THREADS + threadIdx.x]
 
     double y[N], y1[N], k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], k8[N], k9[N], k10[N];
     double pl[STAGED ? B200ODE_NPMAX : 1];
@@ -284,7 +288,6 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     unsigned flags = 0;
     int b = -1;  // trajectory index of this lane, -1 = idle
 
-    const double rtol = L.rtol, atol = L.atol;
     const double facc1 = 1.0 / DP_FAC1;  // module :505
     const double facc2 = 1.0 / DP_FAC2;  // module :506
     const int nt = L.nt;
@@ -309,6 +312,10 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                 } else {
                     pp = const_cast<double*>(pg);
                 }
+                const double rtol = L.rtol_b ? L.rtol_b[b] : L.rtol;
+                const double atol = L.atol_b ? L.atol_b[b] : L.atol;
+                RTOL = rtol;
+                ATOL = atol;
                 x = SPAN_X0;
                 const double hmax = SPAN_HMAX, posneg = SPAN_POSNEG;
                 flags = 0;
@@ -424,6 +431,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     k5[i] = y[i] + h * k4[i];
                 }
                 // error estimation, module :591-616
+                const double rtol = RTOL, atol = ATOL;
                 double err = 0.0, err2 = 0.0;
                 FOR_N {
                     double sk = atol + rtol * fmax_(fabs(y[i]), fabs(k5[i]));
@@ -564,5 +572,5 @@ extern "C" __global__ void b200ode_dop853_config(int* out)
     out[2] = B200_MINBLOCKS;
     out[3] = N;
     out[4] = B200_THREADS;
-    out[5] = (B200_THREADS / 32) * QF * QCAP + 4 + B200_THREADS;  // doubles of dynamic shared memory
+    out[5] = (B200_THREADS / 32) * QF * QCAP + 4 + 3 * B200_THREADS;  // doubles of dynamic shared memory
 }

@@ -55,7 +55,7 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
     bool exhausted = false;
     const int nt = L.nt;
     const double* __restrict__ te = L.t_eval;
-    const double rtol = L.rtol, atol = L.atol;
+    double rtol = L.rtol, atol = L.atol;  // of this lane's trajectory
     // wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130)
     const unsigned long long mxstep_u = (unsigned long long)(long long)L.mxstep;
 
@@ -67,6 +67,8 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
                 exhausted = true;
             } else {
                 b = bn;
+                if (L.rtol_b) rtol = L.rtol_b[b];
+                if (L.atol_b) atol = L.atol_b[b];
                 const double* pg = reinterpret_cast<const double*>(L.data + b * L.data_stride);
                 if (STAGED) {
 #pragma unroll

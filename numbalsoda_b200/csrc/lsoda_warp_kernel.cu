@@ -43,11 +43,13 @@ b200ode_lsodaw_kernel(const B200OdeLaunch L)
         if (b >= L.B) break;
         double* pp = reinterpret_cast<double*>(const_cast<char*>(L.data + b * L.data_stride));
         double* usol = L.usol + (size_t)b * (size_t)nt * (size_t)n;
+        const double rtol = L.rtol_b ? L.rtol_b[b] : L.rtol;
+        const double atol = L.atol_b ? L.atol_b[b] : L.atol;
         LsLane s;
         LsRun R;
-        bool done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te, usol, L.rtol, L.atol);
+        bool done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te, usol, rtol, atol);
         while (!done)
-            done = ls_advance(s, R, v, T, pp, nt, te, usol, L.rtol, L.atol, mxstep_u,
+            done = ls_advance(s, R, v, T, pp, nt, te, usol, rtol, atol, mxstep_u,
                               L.exit_on_warning, 0xffffffffu);
         if (WV_LANE == 0) {
             // wrapper.cpp:41-45: istate <= 0 -> success = 0

@@ -411,3 +411,41 @@ def test_empty_and_tiny_ensembles():
     us, ok = nb.lsoda(nb.builtin("robertson"), u0, te, np.array([[0.04, 3e7, 1e4]]), 1e-6, 1e-8, strict=True)
     ref, okr, _ = orc.lsoda(orc.builtin_rhs("robertson"), u0, te, [0.04, 3e7, 1e4], 1e-6, 1e-8)
     assert us.shape == (1, 10, 3) and ok[0] == okr and np.array_equal(us[0], ref)
+
+
+@pytest.mark.parametrize("solver", ["lsoda", "dop853"])
+def test_per_trajectory_tolerances(solver):
+    """rtol / atol as arrays of shape [B]: each trajectory must equal
+    the reference-order solve with its own scalar tolerances, bit for bit -- thread kernel
+    (n = 2) and warp kernel (n = 64)."""
+    nb = _nb()
+    api = nb.lsoda if solver == "lsoda" else nb.dop853
+    rng = np.random.default_rng(12)
+    B = 40
+    rt = 10.0 ** rng.uniform(-9, -4, B)
+    at = 10.0 ** rng.uniform(-11, -6, B)
+    u0 = np.array([5.0, 0.8])
+    te = np.linspace(0.0, 20.0, 21)
+    P = rng.uniform(0.5, 2.0, (B, 1))
+    us, ok, cnt = api(nb.builtin("lotka_volterra"), u0, te, P, rt, at, strict=True, counters=True)
+    f = orc.builtin_rhs("lotka_volterra")
+    ofun = orc.lsoda if solver == "lsoda" else orc.dop853
+    for b in range(B):
+        ref, okr, st = ofun(f, u0, te, P[b], rt[b], at[b])
+        assert ok[b] == okr and np.array_equal(us[b], ref), b
+        assert cnt[b, 0] == (st.nst if solver == "lsoda" else st.nstep)
+    # mixed: array rtol, scalar atol; warp kernel
+    Bw = 6
+    Pw = pr.brusselator_sweep(Bw, seed=2)
+    if solver == "dop853":
+        Pw[:, 2] = 0.5
+    u0w = pr.brusselator_u0()
+    tew = np.linspace(0.0, 2.0, 9)
+    rtw = 10.0 ** rng.uniform(-7, -4, Bw)
+    us, ok = api(nb.builtin("brusselator1d"), u0w, tew, Pw, rtw, 1e-9, strict=True)
+    fw = orc.builtin_rhs("brusselator1d")
+    for b in range(Bw):
+        ref, okr, st = ofun(fw, u0w, tew, Pw[b], rtw[b], 1e-9)
+        assert ok[b] == okr and np.array_equal(us[b], ref), b
+    with pytest.raises(ValueError):
+        api(nb.builtin("lotka_volterra"), u0, te, P, rt[:5], 1e-8)
