@@ -92,6 +92,8 @@ def build(force=False, verbose=False):
                     extra.append("-DB200POW_NOINLINE")
                 if name == "lsoda" and os.environ.get("B200ODE_DIV_NOINLINE", "0") == "1":
                     extra.append("-DB200_DIV_NOINLINE")
+                if name == "lsoda":
+                    extra += os.environ.get("B200ODE_LSODA_DEFS", "").split()
                 log = _run([NVCC] + ARCH + NVCC_FLAGS + extra + ["-DB200_NEQ=%d" % n, "-DB200_QCAP=%d" % qc,
                                                           "-DB200_MINBLOCKS=%d" % mb, "-DB200_DRAIN_NOINLINE=%d" % ni, "-DB200_THREADS=%d" % th,
                                                           "-o", out, srcp])

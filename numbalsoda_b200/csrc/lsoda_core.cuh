@@ -56,6 +56,12 @@
 #define LS_MSBP 20    // LSODA.cpp:565
 #define LS_MXHNIL 10  // LSODA.cpp:294
 #define LS_CCMAX 0.3  // LSODA.cpp:563
+#ifndef LS_ITERS_PER_PASS
+// corrector iterations one pass of ls_advance may take.  3 = maxcor: a pass is then a whole
+// attempt unless the corrector restarts with a fresh Jacobian.  Measured on Robertson
+// (M traj/s): 1 -> 4.79, 2 -> 4.58, 3 -> 5.35, 4 -> 4.30, 6 -> 4.47.
+#define LS_ITERS_PER_PASS 3
+#endif
 
 // tables of the method in use (cfode is re-run for `meth` at :1086 before any use)
 #define ELCO(q, k) T->elco[s.meth - 1][q][k]
@@ -550,68 +556,78 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
         s.phase = LS_P_ITER;
     }
     LS_SYNC();
-    // ---- (4) one corrector iteration, LSODA.cpp:1763-1900
+    // ---- (4) corrector iterations, LSODA.cpp:1763-1900: up to LS_ITERS_PER_PASS of them, the
+    //      later ones only for the lanes that have not converged yet.  (With one iteration
+    //      per pass, a third of the lanes was in its second iteration at any time and every
+    //      other block of the pass -- start of step, prediction, error test, step / order /
+    //      method selection -- ran with two thirds of its lanes: ncu, profiles/r1_lsoda_v3.
+    //      The loop is one code site: the kernel does not grow.)
     bool corfail = false, converged = false;
-    if (go) {
-        v.rhs_savf(s.tn, pp);
-        s.nfe++;
-        if (s.m == 0 && s.ipup > 0) {
-            // prja (LSODA.cpp:1633-1696): finite-difference Jacobian, P = I - h el0 J, LU
-            s.nje++;
-            s.jcur = 1;
-            const int ierpj = v.prja(s.tn, s.h, s.h * s.el0, pp, s.pdnorm);
-            s.nfe += n;
-            s.ipup = 0;
-            s.rc = 1.0;
-            s.nslp = s.nst;
-            s.crate = 0.7;
-            if (ierpj != 0) corfail = true;
-        }
-    }
-    LS_SYNC();
-    if (go && !corfail) {
-        if (s.m == 0) v.acor_zero();
-        const double el1 = ELCO(s.nq, 1);
-        if (miter == 0)
-            s.del = v.functional(s.h, el1);  // functional iteration, :1792-1809
-        else
-            s.del = v.chord(s.h, el1);  // chord iteration, :1816-1829
-        // convergence test, :1842-1862
-        if (s.del <= 100.0 * s.pnorm * LS_ETA) {
-            converged = true;
-        } else if (s.m != 0 || s.meth != 1) {
-            if (s.m != 0) {
-                double rm = 1024.0;
-                if (s.del <= (1024.0 * s.delp)) rm = ls_div(s.del, s.delp);
-                s.rate = ls_max(s.rate, rm);
-                s.crate = ls_max(0.2 * s.crate, rm);
+    bool iterate = go;
+#pragma unroll 1
+    for (int it = 0; it < LS_ITERS_PER_PASS; it++) {
+        if (iterate) {
+            v.rhs_savf(s.tn, pp);
+            s.nfe++;
+            if (s.m == 0 && s.ipup > 0) {
+                // prja (LSODA.cpp:1633-1696): finite-difference Jacobian, P = I - h el0 J, LU
+                s.nje++;
+                s.jcur = 1;
+                const int ierpj = v.prja(s.tn, s.h, s.h * s.el0, pp, s.pdnorm);
+                s.nfe += n;
+                s.ipup = 0;
+                s.rc = 1.0;
+                s.nslp = s.nst;
+                s.crate = 0.7;
+                if (ierpj != 0) corfail = true;
             }
-            const double dcon = ls_div(s.del * ls_min(1.0, 1.5 * s.crate), TESCO(s.nq, 2) * T->conit[s.nq]);
-            if (dcon <= 1.0) {
-                s.pdest = ls_max(s.pdest, ls_div(s.rate, fabs(s.h * el1)));
-                if (s.pdest != 0.0) s.pdlast = s.pdest;
+        }
+        LS_SYNC();
+        if (iterate && !corfail) {
+            if (s.m == 0) v.acor_zero();
+            const double el1 = ELCO(s.nq, 1);
+            if (miter == 0)
+                s.del = v.functional(s.h, el1);  // functional iteration, :1792-1809
+            else
+                s.del = v.chord(s.h, el1);  // chord iteration, :1816-1829
+            // convergence test, :1842-1862
+            if (s.del <= 100.0 * s.pnorm * LS_ETA) {
                 converged = true;
-            }
-        }
-        if (!converged) {
-            s.m++;
-            if (s.m == LS_MAXCOR || (s.m >= 2 && s.del > 2.0 * s.delp)) {
-                // :1871-1891
-                if (miter == 0 || s.jcur == 1) {
-                    corfail = true;
-                } else {
-                    s.ipup = miter;
-                    s.m = 0;
-                    s.rate = 0.0;
-                    s.del = 0.0;
-                    v.y_from_yh1();
+            } else if (s.m != 0 || s.meth != 1) {
+                if (s.m != 0) {
+                    double rm = 1024.0;
+                    if (s.del <= (1024.0 * s.delp)) rm = ls_div(s.del, s.delp);
+                    s.rate = ls_max(s.rate, rm);
+                    s.crate = ls_max(0.2 * s.crate, rm);
                 }
-            } else {
-                s.delp = s.del;
+                const double dcon = ls_div(s.del * ls_min(1.0, 1.5 * s.crate), TESCO(s.nq, 2) * T->conit[s.nq]);
+                if (dcon <= 1.0) {
+                    s.pdest = ls_max(s.pdest, ls_div(s.rate, fabs(s.h * el1)));
+                    if (s.pdest != 0.0) s.pdlast = s.pdest;
+                    converged = true;
+                }
+            }
+            if (!converged) {
+                s.m++;
+                if (s.m == LS_MAXCOR || (s.m >= 2 && s.del > 2.0 * s.delp)) {
+                    // :1871-1891
+                    if (miter == 0 || s.jcur == 1) {
+                        corfail = true;
+                    } else {
+                        s.ipup = miter;
+                        s.m = 0;
+                        s.rate = 0.0;
+                        s.del = 0.0;
+                        v.y_from_yh1();
+                    }
+                } else {
+                    s.delp = s.del;
+                }
             }
         }
+        iterate = iterate && !converged && !corfail;
+        LS_SYNC();
     }
-    LS_SYNC();
     // ---- (5) the attempt is over: local error test, LSODA.cpp:1170-1177
     double dsm = 0.0, rhup = 0.0;
     bool accepted = false, select_order = false;
