@@ -449,3 +449,38 @@ def test_per_trajectory_tolerances(solver):
         assert ok[b] == okr and np.array_equal(us[b], ref), b
     with pytest.raises(ValueError):
         api(nb.builtin("lotka_volterra"), u0, te, P, rt[:5], 1e-8)
+
+
+def test_concurrent_calls_from_host_threads():
+    """The reference's wrappers are reentrant (safe from prange); so are the
+    library's entry points: several host threads solving different ensembles on the same
+    handle and device at once get the results of serial calls."""
+    import threading
+    nb = _nb()
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 1e5, 50)
+    Ps = [pr.robertson_sweep(3000, seed=s) for s in range(4)]
+    serial = [nb.lsoda(nb.builtin("robertson"), u0, te, P, 1e-8, 1e-8, strict=True)[0] for P in Ps]
+    out = [None] * 4
+
+    def work(k):
+        out[k] = nb.lsoda(nb.builtin("robertson"), u0, te, Ps[k], 1e-8, 1e-8, strict=True)[0]
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for k in range(4):
+        assert np.array_equal(out[k], serial[k]), k
+    # the warp kernel keeps nothing per launch outside its shared memory either
+    Pw = pr.brusselator_sweep(40, seed=5)
+    u0w, tew = pr.brusselator_u0(), np.linspace(0, 2.0, 5)
+    ser = nb.lsoda(nb.builtin("brusselator1d"), u0w, tew, Pw, 1e-6, 1e-8)[0]
+    outw = [None] * 3
+
+    def workw(k):
+        outw[k] = nb.lsoda(nb.builtin("brusselator1d"), u0w, tew, Pw, 1e-6, 1e-8)[0]
+
+    th = [threading.Thread(target=workw, args=(k,)) for k in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert all(np.array_equal(o, ser) for o in outw)
