@@ -133,3 +133,14 @@ def upper_rhs(t, u, du, p):
     for i in range(n - 1):
         du[i] = -p[0] * u[i] + p[1] * u[i + 1]
     du[n - 1] = -p[0] * u[n - 1] + 1.0
+
+
+def chain_rhs(t, u, du, p):
+    """A nonlinear reaction chain of any size n = int(p[1]) (stiff for large k = p[0]):
+    exercises every system size the kernels are built for."""
+    n = int(p[1])
+    k = p[0]
+    du[0] = -k * u[0] + 0.5 * u[1] * u[1]
+    for i in range(1, n - 1):
+        du[i] = k * (u[i - 1] - u[i]) / (1.0 + i) + 0.1 * u[i + 1] - 0.1 * u[i] * u[i]
+    du[n - 1] = k * (u[n - 2] - u[n - 1]) / n

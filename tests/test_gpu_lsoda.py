@@ -484,3 +484,35 @@ def test_concurrent_calls_from_host_threads():
     [t.start() for t in th]
     [t.join() for t in th]
     assert all(np.array_equal(o, ser) for o in outw)
+
+
+@pytest.mark.parametrize("n", [1, 4, 5, 6, 7, 8])
+def test_every_thread_kernel_size(n):
+    """One kernel image per system size n = 1..8 (both solvers): each is run on a stiff
+    nonlinear chain (numba RHS with a loop) and, for LSODA, on the pivoting problem."""
+    import numba
+    nb = _nb()
+    B = 9
+    if n == 1:
+        def rhs(t, u, du, p):
+            # (polynomial: a transcendental in the RHS is libdevice on the GPU and glibc on
+            # the CPU, which are not bit-identical -- SURVEY.md appendix A)
+            du[0] = -p[0] * u[0] + 0.1 * t * t - u[0] * u[0] * u[0]
+        P = np.array([[0.5 + 50.0 * b] for b in range(B)])
+        cases = [(rhs, P, np.array([1.0]), np.linspace(0, 5, 11))]
+    else:
+        P = np.array([[20.0 * (1 + b), float(n)] for b in range(B)])
+        Pu = np.array([[1000.0 * (1 + 0.1 * b), 5000.0, float(n)] for b in range(B)])
+        cases = [(pr.chain_rhs, P, 1.0 + 0.1 * np.arange(n), np.linspace(0, 5, 11)),
+                 (pr.upper_rhs, Pu, np.ones(n), np.linspace(0, 2, 9))]
+    for rhs, Pk, u0, te in cases:
+        cf = numba.cfunc(nb.lsoda_sig)(rhs)
+        us, ok, cnt = nb.lsoda(rhs, u0, te, Pk, 1e-7, 1e-9, strict=True, counters=True)
+        ref, okr, cr = orc.solve_batch("lsoda", cf.address, u0, te, Pk, 1e-7, 1e-9)
+        assert list(ok) == list(okr) and np.array_equal(cnt, cr), (n, rhs.__name__)
+        assert np.array_equal(us, ref)
+        if rhs is not pr.upper_rhs:
+            us, ok, cnt = nb.dop853(rhs, u0, te, Pk, 1e-7, 1e-9, mxstep=200000, strict=True, counters=True)
+            ref, okr, cr = orc.solve_batch("dop853", cf.address, u0, te, Pk, 1e-7, 1e-9, mxstep=200000)
+            assert list(ok) == list(okr) and np.array_equal(cnt[:, :7], cr[:, :7]), (n, "dop853")
+            assert np.array_equal(us, ref)

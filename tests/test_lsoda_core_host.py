@@ -276,3 +276,17 @@ def test_pivoting_problem_bitwise_and_fast_solves(n):
         assert okc.value == 1
         err = np.abs(us1 - ref) / (1e-6 * np.abs(ref) + 1e-9)
         assert err.max() < 20.0, err.max()
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 8])
+def test_every_thread_kernel_size_bitwise(n):
+    """The thread backend is compiled per system size (n = 1..8): sizes 4..8 on a stiff
+    chain and on the pivoting problem, both backends."""
+    for rhs, d, te, tol in ((pr.chain_rhs, [80.0, float(n)], np.linspace(0, 5, 11), (1e-7, 1e-9)),
+                            (pr.upper_rhs, [1000.0, 5000.0, float(n)], np.linspace(0, 2, 9), (1e-6, 1e-9))):
+        fptr = pr.cfunc_address(rhs)
+        u0 = 1.0 + 0.1 * np.arange(n)
+        us, ok, cnt = run_core(fptr, u0, te, d, *tol)
+        ref, okr, st = orc.lsoda(fptr, u0, te, d, *tol)
+        assert ok == okr and cnt == ocnt(st), (n, cnt, ocnt(st))
+        assert same(us[:st.rows], ref[:st.rows])
