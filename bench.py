@@ -9,13 +9,17 @@ A "step" is one pass of the solver over one ensemble of synthetic inputs:
                   rtol = atol = 1e-8, 2^20 trajectories per GPU
   robertson_lsoda (configs[2], "C3") Robertson n=3, LSODA, t_eval = linspace(0,1e5,100),
                   rtol = atol = 1e-8, 2^20 trajectories per GPU
+  brusselator_lsoda (configs[3], "C4") 1-D Brusselator n=64, LSODA (warp per trajectory),
+                  t_eval = linspace(0,10,100), rtol = 1e-6, atol = 1e-8, 100 000 trajectories
+  mixed           (configs[4], "C5") the Lorenz and the Robertson ensembles as two
+                  homogeneous launches per GPU; value = all trajectories / all time
 Multi-GPU: one process per GPU (torchrun), the ensemble is sharded by trajectory, no
 data-path collective; `value` = trajectories of all ranks / max-over-ranks time.
 
 Prints ONE JSON line (rank 0).  `value` is measured with inputs and outputs resident
-in HBM (CUDA events on the launch stream); `e2e` is the same workload through the
-numbalsoda-compatible host API (pinned host buffers, H2D + D2H inside the timed
-region).  `--impl reference` times the reference's CPU implementation of the path on
+in HBM (CUDA events on the launch stream); `e2e` is the same workload through the call a
+user makes -- numbalsoda_b200.lsoda / dop853 with numpy inputs and a page-locked `out=`
+result buffer: H2D, kernels and D2H of every row inside the timed region.  `--impl reference` times the reference's CPU implementation of the path on
 the host cores on a bounded sample (oracle/_ref when it compiled -- LSODA --, else the
 oracle port -- DOP853, whose reference is Fortran).
 """
