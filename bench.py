@@ -103,7 +103,8 @@ def lsoda_flops(cnt, n, f_rhs, nt):
 # `ncu --set full` captures summarised under profiles/ (bytes, capture, trajectories in it)
 NCU_TRAFFIC = {
     "lorenz_dop853": (848.322304e6 + 13.346549e9, "profiles/r1_dop853_v1_queue_8warps.txt", 524288),
-    "robertson_lsoda": (17.270784e6 + 280.736e6, "profiles/r1_lsoda_v2_flat_synced.txt", 131072),
+    "robertson_lsoda": (16.3008e6 + 280.787968e6, "profiles/r1_lsoda_v4_attempt_per_pass.txt", 131072),
+    "brusselator_lsoda": (4.124928e6 + 150.701824e6, "profiles/r1_lsodaw_v1_fast_solves.txt", 4000),
 }
 
 F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6, "brusselator1d": 608}

@@ -94,6 +94,8 @@ def build(force=False, verbose=False):
                     extra.append("-DB200_DIV_NOINLINE")
                 if name == "lsoda":
                     extra += os.environ.get("B200ODE_LSODA_DEFS", "").split()
+                if name == "dop853":
+                    extra += os.environ.get("B200ODE_DOP853_DEFS", "").split()
                 log = _run([NVCC] + ARCH + NVCC_FLAGS + extra + ["-DB200_NEQ=%d" % n, "-DB200_QCAP=%d" % qc,
                                                           "-DB200_MINBLOCKS=%d" % mb, "-DB200_DRAIN_NOINLINE=%d" % ni, "-DB200_THREADS=%d" % th,
                                                           "-o", out, srcp])
