@@ -271,6 +271,8 @@ def main():
             raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
         torch.cuda.set_device(local)
         ranks = Ranks(backend="nccl" if world > 1 else None)  # plumbing only: no data-path collective
+        if world > 1 and os.environ.get("B200ODE_NUMA_BIND", "1") == "1":
+            ranks.bind_to_gpu_numa_node()  # host buffers next to each rank's GPU
     lines = [bench_one(a, nm, ranks, rank, world, local) for nm in names]
     if ranks is not None:
         ranks.close()
