@@ -248,6 +248,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--strict", action="store_true", help="FMA contraction off (parity mode)")
+    ap.add_argument("--exact-ctrl", action="store_true",
+                    help="FMA mode with the reference's controller arithmetic (B200ODE_EXACT_CTRL)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -352,7 +354,7 @@ def bench_one(a, workload, ranks, rank, world, local):
 
     B, n, nt = wl["batch"], wl["n"], wl["t_eval"][2]
     solver = _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
-    h = nb.get_handle(nb.builtin(wl["rhs"]), solver, n, strict=a.strict)
+    h = nb.get_handle(nb.builtin(wl["rhs"]), solver, n, strict=a.strict, exact_ctrl=a.exact_ctrl)
     Ph = sweep(wl["rhs"], B, seed=rank)  # every rank integrates its own shard of the sweep
     teh = np.linspace(*wl["t_eval"][:2], nt)
     P = torch.tensor(Ph, device=dev)
@@ -426,7 +428,7 @@ def bench_one(a, workload, ranks, rank, world, local):
 
         def e2e_step():
             us, okh = api(rhs, u0h, teh, Pe, wl["rtol"], wl["atol"], wl["mxstep"],
-                          strict=a.strict, device=local, out=out)
+                          strict=a.strict, exact_ctrl=a.exact_ctrl, device=local, out=out)
             return int(okh.sum())  # the host reads the step's result
 
         e2e_step()
@@ -474,7 +476,7 @@ def bench_one(a, workload, ranks, rank, world, local):
     line = {"metric": "trajectories/s", "value": value, "unit": "traj/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s_max / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": cfg, "mode": "strict" if a.strict else "fast (FMA)",
+            "data": "synthetic", "config": cfg, "mode": "strict" if a.strict else ("FMA, exact controller" if a.exact_ctrl else "fast (FMA, fast controller)"),
             "success_fraction": n_ok / (B * world), "wall_s_timed_region": t_wall,
             "mean_steps_per_trajectory": float(cnt_h[:, 0].mean()),
             "roofline": roof, "clocks": clocks, "gpu_launches": launches,

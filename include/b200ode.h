@@ -49,6 +49,13 @@ extern "C" {
 #define B200ODE_STRICT_FP 1u /* no FMA contraction anywhere: arithmetic identical to the
                                 reference's x86-64 build (parity mode).  Default (0) lets
                                 the compiler fuse multiply-adds (throughput mode). */
+#define B200ODE_EXACT_CTRL 2u /* throughput mode only: keep the reference's step-size
+                                controller arithmetic (IEEE divisions, sqrt, libm-exact pow).
+                                Default (0): DOP853's error norm and controller
+                                (dop853_module.f90:603-623, :725) use reciprocals and a
+                                single-precision err**(1/8) -- the accept/reject test stays in
+                                double precision, the new step size differs from the
+                                reference's by ~1e-7 relative.  Implied by STRICT_FP. */
 
 /* error codes */
 #define B200ODE_EINVAL -1  /* bad argument */

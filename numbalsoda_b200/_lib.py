@@ -9,6 +9,7 @@ LIBPATH = os.path.join(HERE, "libb200ode.so")
 DOP853, LSODA = 0, 1
 IMG_LTOIR, IMG_PTX, IMG_FATBIN, IMG_BUILTIN = 0, 1, 2, 3
 STRICT_FP = 1
+EXACT_CTRL = 2
 NCOUNTERS = 8
 
 

@@ -37,7 +37,7 @@ def _data_layout(data, B_hint):
 
 
 def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning=False,
-          strict=False, device=None, counters=False, out=None):
+          strict=False, device=None, counters=False, out=None, exact_ctrl=False):
     u0 = _as_f64(u0, "u0")
     t_eval = _as_f64(t_eval, "t_eval")
     if data is None:
@@ -54,7 +54,7 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
     B = u0.shape[0] if batched_u0 else (dbuf.shape[0] if batched_data else 1)
     n = u0.shape[-1]
     nt = t_eval.shape[0]
-    handle = _rhs.get_handle(funcptr, solver, n, strict=strict)
+    handle = _rhs.get_handle(funcptr, solver, n, strict=strict, exact_ctrl=exact_ctrl)
     if out is not None:
         # caller-owned result buffer, ideally page-locked (numbalsoda_b200.pinned_empty) and
         # reused across calls: allocating and first touching a fresh multi-gigabyte array

@@ -122,6 +122,14 @@ def build(force=False, verbose=False):
             _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_RHS_%s" % r.upper(), "-o", out, srcp])
         images.append(("rhs_" + r, out))
 
+    # the handle's link flags as a link-time constant (link_flags.cu)
+    srcp = os.path.join(CSRC, "link_flags.cu")
+    for k in range(4):
+        out = os.path.join(OBJ, "flags_%d.fatbin" % k)
+        if force or _newer(out, [srcp]):
+            _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_LINK_FLAGS=%du" % k, "-o", out, srcp])
+        images.append(("flags_%d" % k, out))
+
     # self-test kernels: a plain sm_100a cubin (no LTO link needed)
     srcp = os.path.join(CSRC, "selftest_kernel.cu")
     out = os.path.join(OBJ, "selftest.cubin")

@@ -230,6 +230,18 @@ extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t s
     if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(solver)", r);
     r = nvJitLinkAddData(h, rhs_type, rhs_data, rhs_size, "b200ode_user_rhs");
     if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(rhs)", r);
+    {
+        // the flags as a device-side link-time constant (link_flags.cu)
+        char fname[32];
+        snprintf(fname, sizeof fname, "flags_%u", flags & 3u);
+        const B200EmbeddedImage* f = find_image(fname);
+        if (!f) {
+            nvJitLinkDestroy(&h);
+            return fail(B200ODE_ENOSYS, "image %s missing", fname);
+        }
+        r = nvJitLinkAddData(h, NVJITLINK_INPUT_FATBIN, f->begin, (size_t)(f->end - f->begin), fname);
+        if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(flags)", r);
+    }
     r = nvJitLinkComplete(h);
     if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkComplete", r);
     size_t n = 0;

@@ -27,6 +27,7 @@
 //    L2 merges them into full-sector HBM writes.
 #include "b200ode_device.cuh"
 #include "b200ode_pow.cuh"
+#include "b200ode_fastmath.cuh"
 #include "dop853_tableau.cuh"
 
 #define N B200_NEQ
@@ -433,25 +434,48 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                 // error estimation, module :591-616
                 const double rtol = RTOL, atol = ATOL;
                 double err = 0.0, err2 = 0.0;
-                FOR_N {
-                    double sk = atol + rtol * fmax_(fabs(y[i]), fabs(k5[i]));
-                    double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
-                    double qq = erri / sk;
-                    err2 = err2 + qq * qq;
-                    erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] +
-                           DP_ER9 * k9[i] + DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
-                    qq = erri / sk;
-                    err = err + qq * qq;
+                double fac11 = 0.0, ifac = 0.0;
+                if (B200ODE_FAST_CTRL()) {
+                    // throughput mode (b200ode_fastmath.cuh): the same quantities through
+                    // reciprocals; err holds the *square* of the reference's err (the test
+                    // err <= 1 is unchanged by that), ifac = safe / err**(1/8)
+                    FOR_N {
+                        const double isk = b200_rcp(atol + rtol * fmax_(fabs(y[i]), fabs(k5[i])));
+                        double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
+                        double qq = erri * isk;
+                        err2 = err2 + qq * qq;
+                        erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] +
+                               DP_ER9 * k9[i] + DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
+                        qq = erri * isk;
+                        err = err + qq * qq;
+                    }
+                    double deno = err + 0.01 * err2;
+                    if (deno <= 0.0) deno = 1.0;
+                    err = (h * h) * (err * err) * b200_rcp((double)N * deno);
+                    ifac = DP_SAFE * b200_inv_root16(err);
+                    // fac = max(facc2, min(facc1, fac11/safe)); hnew = h/fac   (module :620-623)
+                    hnew = h * fmin_(DP_FAC2, fmax_(DP_FAC1, ifac));
+                } else {
+                    FOR_N {
+                        double sk = atol + rtol * fmax_(fabs(y[i]), fabs(k5[i]));
+                        double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
+                        double qq = erri / sk;
+                        err2 = err2 + qq * qq;
+                        erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] +
+                               DP_ER9 * k9[i] + DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
+                        qq = erri / sk;
+                        err = err + qq * qq;
+                    }
+                    double deno = err + 0.01 * err2;
+                    if (deno <= 0.0) deno = 1.0;
+                    err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
+                    // step size controller, module :618-623 (facold**beta == 1 for beta = 0,
+                    // which also makes facold, module :626, dead)
+                    fac11 = b200ode_pow_eighth(err);
+                    double fac = fac11 / 1.0;
+                    fac = fmax_(facc2, fmin_(facc1, fac / DP_SAFE));
+                    hnew = h / fac;
                 }
-                double deno = err + 0.01 * err2;
-                if (deno <= 0.0) deno = 1.0;
-                err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
-                // step size controller, module :618-623 (facold**beta == 1 for beta = 0,
-                // which also makes facold, module :626, dead)
-                const double fac11 = b200ode_pow_eighth(err);
-                double fac = fac11 / 1.0;
-                fac = fmax_(facc2, fmin_(facc1, fac / DP_SAFE));
-                hnew = h / fac;
                 if (err <= 1.0) {
                     // ---- accepted, module :625-722
                     accepted = true;
@@ -481,7 +505,8 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     }
                 } else {
                     // ---- rejected, module :724-728
-                    hnew = h / fmin_(facc1, fac11 / DP_SAFE);
+                    if (B200ODE_FAST_CTRL()) hnew = h * fmax_(DP_FAC1, ifac);
+                    else hnew = h / fmin_(facc1, fac11 / DP_SAFE);
                     if (naccpt >= 1) nrejct++;
                     flags = F_REJECT;  // and last = .false.
                 }

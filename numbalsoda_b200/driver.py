@@ -19,7 +19,8 @@ except Exception:  # numba absent: built-in right-hand sides still work
 
 
 def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, atol=1.0e-6,
-          mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False, out=None):
+          mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False, out=None,
+          exact_ctrl=False):
     """Integrate with the LSODA kernel on the GPU.
 
     funcptr: address of a numba @cfunc(lsoda_sig) (as in the reference), the cfunc, the
@@ -31,7 +32,7 @@ def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, at
     numbalsoda_b200.pinned_empty -- to reuse across calls instead of a fresh np.empty)."""
     return solve(_lib.LSODA, funcptr, u0, t_eval, data, rtol, atol, mxstep,
                  exit_on_warning=exit_on_warning, strict=strict, device=device,
-                 counters=counters, out=out)
+                 counters=counters, out=out, exact_ctrl=exact_ctrl)
 
 
 def address_as_void_pointer(addr):

@@ -162,9 +162,9 @@ def compile_ltoir(pyfunc):
         return build(rewritten)
 
 
-def get_handle(rhs, solver, neq, strict=False):
+def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False):
     """Link (once per right-hand side, solver, size and mode) and return the handle."""
-    flags = _lib.STRICT_FP if strict else 0
+    flags = _lib.STRICT_FP if strict else (_lib.EXACT_CTRL if exact_ctrl else 0)
     if isinstance(rhs, RhsHandle):
         return rhs
     if isinstance(rhs, Builtin):
