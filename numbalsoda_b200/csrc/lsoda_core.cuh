@@ -37,6 +37,7 @@
 #define B200ODE_LSODA_CORE_CUH
 
 #include "b200ode_pow.cuh"
+#include "b200ode_fastmath.cuh"
 #include "lsoda_tables.cuh"
 
 #if defined(__CUDACC__)
@@ -99,6 +100,18 @@ struct LsRun {
 LS_FN double ls_max(double a, double b) { return (a < b) ? b : a; }
 LS_FN double ls_min(double a, double b) { return (b < a) ? b : a; }
 
+// Throughput mode (default link flags, include/b200ode.h): divisions through a reciprocal and
+// one residual correction (within an ulp, 6 instructions without a slow path instead of ~23),
+// the step / order / method ratios through a single-precision pow: b200ode_fastmath.cuh.
+// A link-time constant on the device; on the host (tests/lsoda_core_host.cpp) a build flag.
+#if defined(__CUDA_ARCH__)
+#define LS_FAST() B200ODE_FAST_CTRL()
+#elif defined(B200_HOST_FAST)
+#define LS_FAST() true
+#else
+#define LS_FAST() false
+#endif
+
 // IEEE division.  ls_div is inlined (the compiler's Newton sequence, ~23 instructions).
 // ls_div_rare marks the divisions of blocks that few lanes of a warp execute (Jacobian /
 // LU, rescale, coefficient reload).  With -DB200_DIV_NOINLINE it becomes one out-of-line
@@ -106,26 +119,44 @@ LS_FN double ls_min(double a, double b) { return (b < a) ? b : a; }
 // stall_no_instruction, profiles/r1_lsoda_v3) that measured SLOWER on Robertson (4.40 M
 // vs 4.66 M traj/s; every division out of line: 4.28 M), so it is off by default.
 #if defined(__CUDA_ARCH__) && defined(B200_DIV_NOINLINE_ALL)
-__device__ __noinline__ double ls_div(double a, double b) { return a / b; }
+__device__ __noinline__ double ls_div_ieee(double a, double b) { return a / b; }
 #else
-LS_FN double ls_div(double a, double b) { return a / b; }
+LS_FN double ls_div_ieee(double a, double b) { return a / b; }
 #endif
 #if defined(__CUDA_ARCH__) && (defined(B200_DIV_NOINLINE) || defined(B200_DIV_NOINLINE_ALL))
-__device__ __noinline__ double ls_div_rare(double a, double b) { return a / b; }
+__device__ __noinline__ double ls_div_rare_ieee(double a, double b) { return a / b; }
 #else
-LS_FN double ls_div_rare(double a, double b) { return a / b; }
+LS_FN double ls_div_rare_ieee(double a, double b) { return a / b; }
 #endif
+LS_FN double ls_div(double a, double b) { return LS_FAST() ? b200_div(a, b) : ls_div_ieee(a, b); }
+LS_FN double ls_div_rare(double a, double b)
+{
+    return LS_FAST() ? b200_div(a, b) : ls_div_rare_ieee(a, b);
+}
 
 // The step-size ratio formula of stoda / methodswitch / orderswitch,
 // 1 / (c * x^e + c * 1e-6)  (LSODA.cpp:1229, :1983, :1994, :2037, :2051, :2106, :2111),
 // six call sites: out of line together with pow in the thread-per-trajectory kernels.
 #if defined(__CUDA_ARCH__) && defined(B200POW_NOINLINE)
-__device__ __noinline__ double ls_rhfun(double c1, double x, double e, double c2)
+__device__ __noinline__ double ls_rhfun_exact(double c1, double x, double e, double c2)
 #else
-LS_FN double ls_rhfun(double c1, double x, double e, double c2)
+LS_FN double ls_rhfun_exact(double c1, double x, double e, double c2)
 #endif
 {
     return 1.0 / (c1 * b200ode_pow_impl(x, e) + c2);
+}
+LS_FN double ls_rhfun(double c1, double x, double e, double c2)
+{
+    if (LS_FAST()) {
+        if (!(x <= 1.7976931348623157e308)) return 0.0 / x;  // +inf -> 0, NaN -> NaN as 1/(c*pow+c)
+        return b200_rcp(c1 * b200_pow_fast(x, e) + c2);
+    }
+    return ls_rhfun_exact(c1, x, e, c2);
+}
+LS_FN double ls_pow(double x, double e)
+{
+    if (LS_FAST()) return (x <= 1.7976931348623157e308) ? b200_pow_fast(x, e) : x;
+    return b200ode_pow(x, e);
 }
 
 // hmin / |h| with hmin = 0 (LSODA.cpp:401, :1155, :1243 ...): +0, or NaN when h is 0 or NaN
@@ -220,7 +251,7 @@ LS_FN void ls_methodswitch(LsLane& s, const B200LsodaTables* T, double dsm, doub
     const double rh2 = ls_rhfun(1.2, dsm, exsm, 0.0000012);
     if ((rh1 * 5.0) < (5.0 * rh2)) return;
     const double alpha = ls_max(0.001, rh1);
-    dm1 *= b200ode_pow(alpha, exm1);
+    dm1 *= ls_pow(alpha, exm1);
     if (dm1 <= 1000.0 * LS_ETA * pnorm) return;
     rh = rh1;
     s.icount = 20;
