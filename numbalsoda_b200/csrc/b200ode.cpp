@@ -131,6 +131,7 @@ struct PerDevice {
     CUdeviceptr next = 0;  // kCounterSlots work-queue heads
     int regs = 0, local_bytes = 0, smem = 0, blocks_per_sm = 0, sms = 0;
     int dyn_smem = 0;  // dynamic shared memory per block
+    int max_dyn_smem = 0;  // what the kernels were allowed (CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES)
     int qcap = 0;      // dop853: records per warp queue
     // warp lsoda: per-block iteration matrices in global memory (L2 resident), one set per
     // launch that may be in flight; a set is reused only after its previous launch finished
@@ -358,10 +359,17 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
                 P.dyn_smem = cfgv[0] * (int)sizeof(double);
             }
         }
-        if (P.dyn_smem > 48 * 1024) {
-            CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));
+        P.max_dyn_smem = P.dyn_smem;
+        if (!warp && H->solver == B200ODE_DOP853) {
+            // room for a per-block copy of t_eval (launch(): te_shared)
+            int optin = 0;
+            CU(cuDeviceGetAttribute(&optin, CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN, dev));
+            P.max_dyn_smem = std::max(P.dyn_smem, optin - P.smem);
+        }
+        if (P.max_dyn_smem > 48 * 1024) {
+            CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
             if (P.fn_ptr != P.fn)
-                CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.dyn_smem));
+                CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
         }
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
         CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
@@ -420,8 +428,22 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
         P->wm_used[set] = true;
         args.scratch = reinterpret_cast<double*>(P->wm_scratch + P->wm_set_bytes * set);
     }
+    CUfunction fn = (args.np >= 0 && !warp) ? P->fn : P->fn_ptr;
+    int dyn_smem = P->dyn_smem;
+    args.te_shared = 0;
+    if (!warp && H->solver == B200ODE_DOP853) {
+        // a copy of t_eval per block, if it costs no resident block (dop853_kernel.cu)
+        const long long with_te = (long long)P->dyn_smem + (long long)args.nt * (long long)sizeof(double);
+        int nb = 0;
+        if (with_te <= P->max_dyn_smem &&
+            g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, (size_t)with_te) == CUDA_SUCCESS &&
+            nb >= P->blocks_per_sm) {
+            args.te_shared = 1;
+            dyn_smem = (int)with_te;
+        }
+    }
     void* params[] = {&args};
-    CU(cuLaunchKernel((args.np >= 0 && !warp) ? P->fn : P->fn_ptr, grid, 1, 1, kThreads, 1, 1, (unsigned)P->dyn_smem, stream, params, nullptr));
+    CU(cuLaunchKernel(fn, grid, 1, 1, kThreads, 1, 1, (unsigned)dyn_smem, stream, params, nullptr));
     if (P->wm_scratch) CU(cuEventRecord(P->wm_done[set], stream));
     H->last_grid = grid;
     H->launches++;

@@ -48,6 +48,8 @@ typedef struct B200OdeLaunch {
     unsigned long long* next; /* work queue head (zeroed before the launch) */
     double* scratch;          /* warp kernel: per-block iteration matrices in global memory
                                  (B200ODE_LSODAW_MATRIX(neq) doubles each), or null = shared */
+    int te_shared;            /* dop853 thread kernel: the launch carries nt more doubles of dynamic
+                                 shared memory and every block keeps its own copy of t_eval there */
 } B200OdeLaunch;
 
 #endif

@@ -79,7 +79,8 @@ __device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b);
 // (c_interface :60-68) with contd8 (module :861-869).
 template <bool STAGED>
 __device__ DRAIN_INLINE void dop853_drain(const char* data, long long data_stride, int np_,
-                                          const double* __restrict__ te, double* usol, int nt,
+                                          const double* __restrict__ te_g,
+                                          const double* te_s, double* usol, int nt,
                                           const double* q, int qhead, int m)
 {
     const int lane = threadIdx.x & 31;
@@ -92,6 +93,9 @@ __device__ DRAIN_INLINE void dop853_drain(const char* data, long long data_strid
     const unsigned long long rows = (unsigned long long)__double_as_longlong(r[3 * QCAP]);
     int row = (int)(rows & 0xffffffffu);
     const int row_end = (int)(rows >> 32);
+    // t_eval from the block's copy in shared memory if there is one (te_s), else from global
+#define DRAIN_TE(i) (te_s ? te_s[(i)] : te_g[(i)])
+
     // Parameters of the record's trajectory (the queue holds steps of other lanes).
     double pl[STAGED ? B200ODE_NPMAX : 1];
     double* pp;
@@ -232,13 +236,15 @@ __device__ DRAIN_INLINE void dop853_drain(const char* data, long long data_strid
     // solout rows [row, row_end): xold = x, hout = h
     double* out = usol + ((size_t)b * (size_t)nt + (size_t)row) * N;
     for (; row < row_end; row++, out += N) {
-        const double s = (te[row] - x) / h;
+        const double tq = DRAIN_TE(row);
+        const double s = B200ODE_FAST_CTRL() ? b200_div(tq - x, h) : (tq - x) / h;
         const double s1 = 1.0 - s;
         FOR_N {
             double conpar = c4[i] + s * (c5[i] + s1 * (c6[i] + s * c7[i]));
             out[i] = c0[i] + s * (c1[i] + s1 * (c2[i] + s * (c3[i] + s1 * conpar)));
         }
     }
+#undef DRAIN_TE
 }
 
 // STAGED: the first L.np doubles of the trajectory's data record are copied into
@@ -264,6 +270,17 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
         span[2] = fabs(xe - x0);
         span[3] = copysign(1.0, xe - x0);
     }
+    // t_eval is read once per output row by the event test below and once more by the dense
+    // output; from global memory those loads were the two largest stall sites of the kernel
+    // (ncu source page, profiles/r1_dop853_v3: 7.4 % + 2.0 % of the samples on the compare /
+    // subtract that consume them).  When nt doubles more fit the block's shared memory
+    // without costing a resident block (the host decides: b200ode.cpp launch()), every block
+    // reads its own copy.
+    // (no pointer is kept: both candidates are rematerialised from the constant bank)
+#define TE_S (span + 4 + 3 * B200_THREADS)
+#define TE(i) (L.te_shared ? TE_S[(i)] : L.t_eval[(i)])
+    if (L.te_shared)
+        for (int i = threadIdx.x; i < L.nt; i += B200_THREADS) TE_S[i] = L.t_eval[i];
     __syncthreads();
 #define SPAN_X0 span[0]
 #define SPAN_XEND span[1]
@@ -292,7 +309,6 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     const double facc1 = 1.0 / DP_FAC1;  // module :505
     const double facc2 = 1.0 / DP_FAC2;  // module :506
     const int nt = L.nt;
-    const double* __restrict__ te = L.t_eval;
 
     for (;;) {
         if (b < 0 && !(flags & F_EXHAUSTED)) {
@@ -364,7 +380,8 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
         // ---- dense output for queued steps, converged across the warp
         if (qcount >= QDRAIN_AT || (qcount > 0 && !__any_sync(FULL, b >= 0))) {
             const int m = qcount < 32 ? qcount : 32;
-            dop853_drain<STAGED>(L.data, L.data_stride, L.np, te, L.usol, nt, WARP_Q, qhead, m);
+            dop853_drain<STAGED>(L.data, L.data_stride, L.np, L.t_eval,
+                                 L.te_shared ? TE_S : nullptr, L.usol, nt, WARP_Q, qhead, m);
             qhead += m;
             if (qhead >= QCAP) qhead -= QCAP;
             qcount -= m;
@@ -490,7 +507,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                         double xo;
                         do {
                             row++;
-                            xo = te[row < nt ? row : nt - 1];
+                            xo = TE(row < nt ? row : nt - 1);
                         } while (row < nt && xo <= xph);
                         XOUT = xo;
                         push = row > row_lo;
@@ -598,4 +615,5 @@ extern "C" __global__ void b200ode_dop853_config(int* out)
     out[3] = N;
     out[4] = B200_THREADS;
     out[5] = (B200_THREADS / 32) * QF * QCAP + 4 + 3 * B200_THREADS;  // doubles of dynamic shared memory
+                                                                      // (+ nt with te_shared)
 }

@@ -54,12 +54,15 @@ def test_link_builtin_and_numba_rhs(solver, strict):
 
 
 @pytest.mark.parametrize("solver", ["dop853", "lsoda"])
-def test_linked_kernel_keeps_state_in_registers(tmp_path, solver):
-    """cuobjdump on the linked cubin: no local-memory spills, no stack, the user RHS
-    inlined (no CALL to b200ode_user_rhs survives)."""
+@pytest.mark.parametrize("mode", ["fast", "exact_ctrl", "strict"])
+def test_linked_kernel_keeps_state_in_registers(tmp_path, solver, mode):
+    """cuobjdump on the linked cubin, every link mode: no local-memory spills, no stack, the
+    user RHS inlined (no CALL to b200ode_user_rhs survives); the libm-exact pow (its tables)
+    is linked out of the default mode's thread kernels."""
     import numbalsoda_b200 as nb
     from numbalsoda_b200 import _lib
-    h = nb.get_handle(pr.lorenz_rhs, _lib.DOP853 if solver == "dop853" else _lib.LSODA, 3)
+    h = nb.get_handle(pr.lorenz_rhs, _lib.DOP853 if solver == "dop853" else _lib.LSODA, 3,
+                      strict=mode == "strict", exact_ctrl=mode == "exact_ctrl")
     f = tmp_path / "k.cubin"
     f.write_bytes(h.cubin())
     res = subprocess.run(["cuobjdump", "-res-usage", str(f)], capture_output=True, text=True).stdout
@@ -70,6 +73,7 @@ def test_linked_kernel_keeps_state_in_registers(tmp_path, solver):
     sass = subprocess.run(["cuobjdump", "-sass", str(f)], capture_output=True, text=True).stdout
     assert "b200ode_user_rhs" not in sass
     assert "DFMA" in sass
+    assert "b200ode_link_flags" not in sass  # the mode is a link-time constant
 
 
 def test_cfunc_address_is_resolved():

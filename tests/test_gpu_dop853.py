@@ -90,6 +90,25 @@ def test_batched_u0_and_shared_data():
     assert ok.all() and np.array_equal(us, ref) and np.array_equal(cnt[:, :7], cr[:, :7])
 
 
+@pytest.mark.parametrize("nt", [2, 1001, 1100, 40000])
+def test_output_grids_in_shared_and_global_memory(nt):
+    """The kernel keeps a per-block copy of t_eval in shared memory when that costs no
+    resident block (nt = 1001 of config C2 just fits) and reads global memory otherwise:
+    both paths, all modes, many rows per step (nt = 40000: ~100 rows per step)."""
+    nb = _nb()
+    B = 96
+    P = pr.lorenz_sweep(B)
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 3, nt)
+    ref, okr, cr = orc.solve_batch("dop853", orc.builtin_rhs("lorenz"), u0, te, P, 1e-8, 1e-8)
+    us, ok, cnt = nb.dop853(nb.builtin("lorenz"), u0, te, P, 1e-8, 1e-8, strict=True, counters=True)
+    assert ok.all() and np.array_equal(us, ref) and np.array_equal(cnt[:, :7], cr[:, :7])
+    for kw in (dict(), dict(exact_ctrl=True)):
+        us, ok = nb.dop853(nb.builtin("lorenz"), u0, te, P, 1e-8, 1e-8, **kw)
+        assert ok.all()
+        assert (np.abs(us - ref) / (np.abs(ref) + 1.0)).max() <= 10 * 1e-8
+
+
 def test_failures_and_edge_cases():
     nb = _nb()
     f = nb.builtin("lotka_volterra")
