@@ -41,6 +41,15 @@
 static int g_scipy_reject_rule = 0;
 void oracle_dop853_set_scipy_reject_rule(int on) { g_scipy_reject_rule = on; }
 
+/* Test-only knob: emulate the controller arithmetic of the product's default
+ * (throughput) link mode -- numbalsoda_b200/csrc/b200ode_fastmath.cuh, dop853_kernel.cu:
+ * the squared error and a single-precision err**(-1/8) (libm's log2f / exp2f stand in for
+ * the GPU's MUFU.LG2 / EX2: same accuracy class, not the same bits).  With it
+ * tests/test_oracle_dop853.py measures, without a GPU, how far that mode moves the solution
+ * from the reference arithmetic.  Off (the reference's arithmetic) everywhere else. */
+static int g_fast_ctrl = 0;
+void oracle_dop853_set_fast_ctrl(int on) { g_fast_ctrl = on; }
+
 /* gfortran's MAX/MIN for reals (trans-intrinsic.c, gfc_conv_intrinsic_minmax):
  * m = a; if (b > m || isnan(m)) m = b;   i.e. a NaN operand is ignored.  This is
  * what lets the reference recover from an overflowing trial step (err = NaN ->
@@ -96,7 +105,7 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
     oracle_dop853_stats local;
     double *w, *y, *y1, *k1, *k2, *k3, *k4, *k5, *k6, *k7, *k8, *k9, *k10, *cont;
     double x, xend, h, hmax, hnew, posneg, xph, xold = 0.0, hout = 1.0, xout;
-    double facold, expo1, facc1, facc2, err, err2, erri, sk, deno, fac, fac11;
+    double facold, expo1, facc1, facc2, err, err2, erri, sk, deno, fac, fac11, ifac = 0.0;
     const double safe = 0.9, fac1 = 0.333, fac2 = 6.0, beta = 0.0; /* module :55-62 */
     int i, row, last = 0, reject = 0, event;
 
@@ -233,12 +242,33 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
         deno = err + 0.01 * err2;
         if (deno <= 0.0)
             deno = 1.0;
+        if (g_fast_ctrl) {
+            /* throughput-mode emulation: err holds the square of the reference's err */
+            double e2 = (h * h) * (err * err) * (1.0 / ((double)n * deno)), m;
+            int ex;
+            err = e2;
+            if (e2 != e2) {
+                ifac = e2;
+            } else {
+                if (e2 > 1.0e300)
+                    e2 = 1.0e300;
+                if (e2 < 2.2250738585072014e-308) {
+                    ifac = safe * (double)exp2f(1023.0f * 0.0625f);
+                } else {
+                    m = 2.0 * frexp(e2, &ex);
+                    ifac = safe * (double)exp2f((log2f((float)m) + (float)(ex - 1)) * -0.0625f);
+                }
+            }
+            fac11 = 0.0;
+            hnew = h * dmin(fac2, dmax(fac1, ifac));
+        } else {
         err = fabs(h) * err * sqrt(1.0 / ((double)n * deno));
         /* step size controller, module :618-623 */
         fac11 = pow(err, expo1);
         fac = fac11 / pow(facold, beta);
         fac = dmax(facc2, dmin(facc1, fac / safe));
         hnew = h / fac;
+        }
         if (err <= 1.0) {
             /* accepted, module :625-722 */
             facold = dmax(err, 1.0e-4);
@@ -342,7 +372,10 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
             reject = 0;
         } else {
             /* rejected, module :724-728 */
-            hnew = g_scipy_reject_rule ? h / facc1 : h / dmin(facc1, fac11 / safe);
+            if (g_fast_ctrl)
+                hnew = h * dmax(fac1, ifac);
+            else
+                hnew = g_scipy_reject_rule ? h / facc1 : h / dmin(facc1, fac11 / safe);
             reject = 1;
             if (st->naccpt >= 1)
                 st->nrejct++;

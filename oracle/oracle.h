@@ -52,6 +52,7 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
 
 /* test-only, see dop853_oracle.c */
 void oracle_dop853_set_scipy_reject_rule(int on);
+void oracle_dop853_set_fast_ctrl(int on);
 
 /* Same contract as the reference's lsoda_wrapper (src/wrapper.cpp:10-57) plus an
  * optional statistics block. */

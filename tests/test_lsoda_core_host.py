@@ -18,22 +18,26 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "lsoda_core_host.cpp")
 HDRS = [os.path.join(ROOT, "numbalsoda_b200", "csrc", f)
         for f in ("lsoda_core.cuh", "lsoda_vec_thread.cuh", "lsoda_vec_warp.cuh", "lsoda_tables.cuh",
-                  "b200ode_pow.cuh") if os.path.exists(os.path.join(ROOT, "numbalsoda_b200", "csrc", f))]
+                  "b200ode_pow.cuh", "b200ode_fastmath.cuh") if os.path.exists(os.path.join(ROOT, "numbalsoda_b200", "csrc", f))]
 _libs = {}
 
 
-def core(n):
-    """n = system size for the thread backend, "warp" for the warp backend (any size)."""
-    if n not in _libs:
+def core(n, fast=False):
+    """n = system size for the thread backend, "warp" for the warp backend (any size).
+    fast: the throughput link mode's arithmetic (b200ode_fastmath.cuh) with libm stand-ins."""
+    key = (n, fast)
+    if key not in _libs:
         os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
-        so = os.path.join(HERE, "_build", "liblsoda_core_%s.so" % ("n%d" % n if n != "warp" else n))
+        so = os.path.join(HERE, "_build", "liblsoda_core_%s%s.so" % ("n%d" % n if n != "warp" else n,
+                                                                       "_fast" if fast else ""))
         deps = [SRC] + HDRS
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             flag = "-DB200_NEQ=%d" % n if n != "warp" else "-DB200_WARP_BACKEND"
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared",
-                                   "-Wno-unknown-pragmas", flag, "-o", so, SRC])
-        _libs[n] = ct.CDLL(so)
-    return _libs[n]
+                                   "-Wno-unknown-pragmas", flag] + (["-DB200_HOST_FAST"] if fast else []) +
+                                  ["-o", so, SRC])
+        _libs[key] = ct.CDLL(so)
+    return _libs[key]
 
 
 BACKEND = {"thread": lambda n: core(n), "warp": lambda n: core("warp")}
@@ -49,7 +53,7 @@ def backend(request):
     _backend = "thread"
 
 
-def run_core(fptr, u0, te, data, rtol, atol, mxstep=10000, exit_on_warning=False):
+def run_core(fptr, u0, te, data, rtol, atol, mxstep=10000, exit_on_warning=False, fast=False):
     u0 = np.ascontiguousarray(u0, dtype=np.float64)
     te = np.ascontiguousarray(te, dtype=np.float64)
     data = np.ascontiguousarray(data, dtype=np.float64)
@@ -57,7 +61,8 @@ def run_core(fptr, u0, te, data, rtol, atol, mxstep=10000, exit_on_warning=False
     ok = ct.c_int(999)
     cnt = (ct.c_int * 8)()
     p = lambda a: a.ctypes.data_as(ct.c_void_p)  # noqa: E731
-    BACKEND[_backend](len(u0)).lsoda_core_host(ct.c_void_p(fptr), len(u0), p(u0), p(data), len(te), p(te),
+    lib = core(len(u0) if _backend == "thread" else "warp", fast)
+    lib.lsoda_core_host(ct.c_void_p(fptr), len(u0), p(u0), p(data), len(te), p(te),
                                   p(us), ct.c_double(rtol), ct.c_double(atol), int(mxstep),
                                   ct.byref(ok), int(exit_on_warning), cnt)
     return us, ok.value == 1, list(cnt)
@@ -290,3 +295,38 @@ def test_every_thread_kernel_size_bitwise(n):
         ref, okr, st = orc.lsoda(fptr, u0, te, d, *tol)
         assert ok == okr and cnt == ocnt(st), (n, cnt, ocnt(st))
         assert same(us[:st.rows], ref[:st.rows])
+
+
+def test_fast_mode_robertson_close_to_oracle():
+    """The throughput link mode (divisions by reciprocal, single-precision step / order /
+    method ratios; libm stand-ins on the host) against the oracle on config C3's sweep: the
+    same bound as the GPU fast-mode test (tests/test_gpu_lsoda.py), no bias in the step count."""
+    B = 64
+    P = pr.robertson_sweep(B)
+    f = orc.builtin_rhs("robertson")
+    u0 = np.array([1.0, 0.0, 0.0])
+    te = np.linspace(0, 1e5, 100)
+    worst, dn = 0.0, []
+    for b in range(B):
+        ref, okr, st = orc.lsoda(f, u0, te, P[b], 1e-8, 1e-8)
+        us, ok, cnt = run_core(f, u0, te, P[b], 1e-8, 1e-8, fast=True)
+        assert ok and okr
+        worst = max(worst, (np.abs(us - ref) / (1e-8 * np.abs(ref) + 1e-8)).max())
+        dn.append(cnt[0] - st.nst)
+    assert worst <= 100.0
+    assert abs(np.mean(dn)) < 10 and np.abs(dn).mean() < 40
+
+
+def test_fast_mode_failure_paths_match():
+    """Failure semantics do not depend on the arithmetic mode."""
+    f = orc.builtin_rhs("lotka_volterra")
+    u0, d = np.array([5.0, 0.8]), np.array([1.0])
+    for kw in (dict(te=np.linspace(0, 10, 11), rtol=1e-8, atol=1e-8, mxstep=5),
+               dict(te=np.array([0.0, 0.0, 1.0]), rtol=1e-8, atol=1e-8),
+               dict(te=np.array([0.0, 1.0, 0.5, 2.0]), rtol=1e-8, atol=1e-8),
+               dict(te=np.linspace(0, 10, 11), rtol=0.0, atol=0.0),
+               dict(te=np.linspace(0, 10, 11), rtol=1e-17, atol=1e-20)):
+        te = kw.pop("te")
+        ref, okr, st = orc.lsoda(f, u0, te, d, **kw)
+        us, ok, cnt = run_core(f, u0, te, d, fast=True, **kw)
+        assert ok == okr and cnt[5] == st.istate and cnt[6] == st.rows

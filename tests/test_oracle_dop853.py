@@ -133,3 +133,27 @@ def test_batch_driver():
     assert ok.all()
     a, _, st = orc.dop853(f, np.array([1.0, 0, 0]), te, P[5], 1e-8, 1e-8)
     assert np.array_equal(a, us[5]) and cnt[5, 0] == st.nstep
+
+
+@pytest.mark.parametrize("rtol,atol", [(1e-3, 1e-6), (1e-6, 1e-8), (1e-8, 1e-8), (1e-10, 1e-12)])
+def test_throughput_mode_controller_stays_within_tolerance(rtol, atol):
+    """The product's default link mode takes the step-size controller through reciprocals and a
+    single-precision power.  Emulated in the oracle (test-only knob): the
+    solution moves by a small fraction of rtol and the accept / reject sequence is unchanged on
+    the reference's Lotka-Volterra problem; a Lorenz sweep (short horizon) stays within 1e-10."""
+    f = orc.builtin_rhs("lotka_volterra")
+    te = np.linspace(0, 50, 1000)
+    ref, ok, st = orc.dop853(f, [5.0, 0.8], te, [1.0], rtol, atol)
+    orc.lib.oracle_dop853_set_fast_ctrl(1)
+    try:
+        us, ok2, st2 = orc.dop853(f, [5.0, 0.8], te, [1.0], rtol, atol)
+        lz = [orc.dop853(orc.builtin_rhs("lorenz"), [1.0, 0.0, 0.0], np.linspace(0, 5, 51), P, 1e-8, 1e-8)
+              for P in pr.lorenz_sweep(20)]
+    finally:
+        orc.lib.oracle_dop853_set_fast_ctrl(0)
+    assert ok and ok2
+    assert (st.nstep, st.naccpt, st.nrejct) == (st2.nstep, st2.naccpt, st2.nrejct)
+    assert (np.abs(us - ref) / np.abs(ref)).max() <= 0.1 * rtol
+    for (a, oka, _), P in zip(lz, pr.lorenz_sweep(20)):
+        b, okb, _ = orc.dop853(orc.builtin_rhs("lorenz"), [1.0, 0.0, 0.0], np.linspace(0, 5, 51), P, 1e-8, 1e-8)
+        assert oka and okb and (np.abs(a - b) / (np.abs(b) + 1.0)).max() <= 1e-10
