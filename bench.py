@@ -102,8 +102,8 @@ def lsoda_flops(cnt, n, f_rhs, nt):
 # dram__bytes_read.sum + dram__bytes_write.sum per trajectory of the solver kernel, from the
 # `ncu --set full` captures summarised under profiles/ (bytes, capture, trajectories in it)
 NCU_TRAFFIC = {
-    "lorenz_dop853": (848.322304e6 + 13.346549e9, "profiles/r1_dop853_v1_queue_8warps.txt", 524288),
-    "robertson_lsoda": (16.3008e6 + 280.787968e6, "profiles/r1_lsoda_v4_attempt_per_pass.txt", 131072),
+    "lorenz_dop853": (732.222976e6 + 6.947206e9, "profiles/r1_dop853_v3_fast_controller.txt", 262144),
+    "robertson_lsoda": (31.317504e6 + 605.663744e6, "profiles/r1_lsoda_v5_throughput_mode.txt", 262144),
     "brusselator_lsoda": (4.124928e6 + 150.701824e6, "profiles/r1_lsodaw_v1_fast_solves.txt", 4000),
 }
 
