@@ -54,6 +54,30 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
 void oracle_dop853_set_scipy_reject_rule(int on);
 void oracle_dop853_set_fast_ctrl(int on);
 
+/* solve_ivp (numbalsoda/driver_solve_ivp.py:86-218, src/dop853_solve_ivp.f90): see
+ * solve_ivp_oracle.c.  message: which of the reference's strings. */
+#define ORACLE_IVP_MSG_END 0      /* 'The solver successfully reached the end of the integration interval.' */
+#define ORACLE_IVP_MSG_EVENT 1    /* 'A termination event occurred.' */
+#define ORACLE_IVP_MSG_FAILED 2   /* 'Failed to complete integration.' */
+#define ORACLE_IVP_MSG_TEVAL 3    /* '"t_eval" does not always increase or decrease' */
+#define ORACLE_IVP_MSG_INIT 4     /* 'Integrator failed to initialize.' (unreachable from the driver) */
+#define ORACLE_IVP_MSG_BRENT 5    /* the reference prints 'brent failed' and stops the process */
+#define ORACLE_IVP_MSG_CAPACITY 6 /* not in the reference: more accepted steps than rows provided */
+typedef struct {
+    int success, message, nfev, nt_out, event_found, ind_event;
+    int idid, nstep, naccpt, nrejct;
+    int rows_needed; /* rows a complete result has (= accepted steps + 1 without t_eval) */
+    int pad_;
+    double t_event;
+} oracle_ivp_result;
+
+/* t_eval given (nt > 0): y_out[nt,neq], t_out unused.  Otherwise every accepted step is
+ * saved: t_out[cap], y_out[cap,neq]. */
+void oracle_solve_ivp(oracle_rhs_fn f, const double *t_span, int neq, const double *y0, int nt,
+                      const double *teval, int n_events, oracle_rhs_fn events, void *data,
+                      double first_step, double max_step, double rtol, double atol, int cap,
+                      double *t_out, double *y_out, double *y_event, oracle_ivp_result *res);
+
 /* Same contract as the reference's lsoda_wrapper (src/wrapper.cpp:10-57) plus an
  * optional statistics block. */
 void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,

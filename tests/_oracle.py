@@ -121,3 +121,40 @@ def solve_batch(solver, fptr, u0, t_eval, data, rtol, atol, mxstep=10000,
                            _p(te), _p(us), ct.c_double(rtol), ct.c_double(atol), int(mxstep),
                            int(exit_on_warning), _p(ok), _p(cnt), int(nthreads))
     return us, ok == 1, cnt
+
+
+class IvpResult(ct.Structure):
+    _fields_ = [(k, ct.c_int) for k in
+                "success message nfev nt_out event_found ind_event idid nstep naccpt nrejct "
+                "rows_needed pad_".split()] + [("t_event", ct.c_double)]
+
+
+IVP_MESSAGES = ["The solver successfully reached the end of the integration interval.",
+                "A termination event occurred.", "Failed to complete integration.",
+                '"t_eval" does not always increase or decrease', "Integrator failed to initialize.",
+                "brent failed", "output capacity exceeded"]
+
+
+def solve_ivp(fptr, t_span, y0, t_eval=None, n_events=0, events=0, data=None, first_step=0.0,
+              max_step=0.0, rtol=1e-3, atol=1e-6, cap=20000):
+    """oracle_solve_ivp: returns a dict with the fields of the reference's ODEResult
+    (numbalsoda/driver_solve_ivp.py:59-69) plus the private counters."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    ts = np.ascontiguousarray(t_span, dtype=np.float64)
+    te = np.ascontiguousarray([] if t_eval is None else t_eval, dtype=np.float64)
+    data = np.ascontiguousarray([0.0] if data is None else data)
+    n, nt = len(y0), len(te)
+    rows = nt if nt else cap
+    t_out = np.full(rows, np.nan)
+    y_out = np.full((rows, n), np.nan)
+    y_event = np.zeros(n)
+    res = IvpResult()
+    lib.oracle_solve_ivp(ct.c_void_p(fptr), _p(ts), n, _p(y0), nt, _p(te), int(n_events),
+                         ct.c_void_p(events), _p(data), ct.c_double(first_step),
+                         ct.c_double(max_step), ct.c_double(rtol), ct.c_double(atol), int(cap),
+                         _p(t_out), _p(y_out), _p(y_event), ct.byref(res))
+    k = res.nt_out
+    return dict(message=IVP_MESSAGES[res.message], nfev=res.nfev, success=bool(res.success),
+                t=(te[:k].copy() if nt else t_out[:k]), y=y_out[:k], event_found=bool(res.event_found),
+                ind_event=res.ind_event, t_event=res.t_event, y_event=y_event, idid=res.idid,
+                nstep=res.nstep, naccpt=res.naccpt, nrejct=res.nrejct, rows_needed=res.rows_needed)
