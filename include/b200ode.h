@@ -37,6 +37,8 @@ extern "C" {
 /* solver */
 #define B200ODE_DOP853 0 /* replaces dop853_wrapper, src/dop853_c_interface.f90:75 */
 #define B200ODE_LSODA 1  /* replaces lsoda_wrapper,  src/wrapper.cpp:10 */
+#define B200ODE_SOLVE_IVP 2 /* replaces dop853_solve_ivp_wrapper + dop853_solve_ivp_result,
+                               src/dop853_solve_ivp.f90:211-434 (b200ode_link_ivp) */
 
 /* kind of right-hand-side image passed to b200ode_link_rhs() */
 #define B200ODE_IMG_LTOIR 0   /* NVVM LTO-IR, e.g. numba.cuda.compile(..., output='ltoir') */
@@ -153,6 +155,85 @@ typedef struct b200ode_problem {
 int b200ode_solve(b200ode_rhs_t rhs, const b200ode_problem* problem, int device);
 /* device pointers on the current device; asynchronous on `stream` */
 int b200ode_solve_device(b200ode_rhs_t rhs, const b200ode_problem* problem, void* stream);
+
+/* ---- solve_ivp: the reference's third entry point,
+ *
+ *   void dop853_solve_ivp_wrapper(rhs, t_span, neq, y0, nt, t_eval, n_events, events_fcn,
+ *                                 data, first_step, max_step, rtol, atol, len_message,
+ *                                 nt_out, n_events_found, d_p)   src/dop853_solve_ivp.f90:211-215
+ *   void dop853_solve_ivp_result (d_p, neq, len_message, nt_out, message, success, nfev,
+ *                                 t, y, event_found, ind_event, t_event, y_event)   :398-401
+ *
+ * (ctypes prototypes: numbalsoda/driver_solve_ivp.py:19-56), for ensembles: DOP853 over
+ * t_span (forward or backward) with output at t_eval or at every accepted step, first_step /
+ * max_step, and terminal events located by Brent's method on the dense interpolant.  The
+ * reference's two-phase call (solve, then fetch the variable-length result through an opaque
+ * pointer) becomes one call with caller-owned arrays.
+ *
+ * The events function  void events(double t, double* y, double* out, void* data)
+ * (src/dop853_solve_ivp.f90:9-17) is handed over like the right-hand side: a device function
+ * named `b200ode_user_events` with the same signature as `b200ode_user_rhs`, writing
+ * n_events <= 8 values.  events_image = NULL with n_events = 0 links a handle without events. */
+#define B200ODE_IVP_NEVENTS_MAX 8
+int b200ode_link_ivp(int neq, const void* rhs_image, size_t rhs_size, int rhs_kind,
+                     int n_events, const void* events_image, size_t events_size,
+                     int events_kind, unsigned flags, b200ode_rhs_t* out);
+
+/* result[b*12 + k]: what the reference's ODEResult holds (driver_solve_ivp.py:59-69) and
+ * the solver's private counters */
+#define B200ODE_IVP_NRESULT 12
+#define B200ODE_IVP_SUCCESS 0     /* 1 / 0 */
+#define B200ODE_IVP_MESSAGE 1     /* b200ode_ivp_message() gives the reference's string */
+#define B200ODE_IVP_NFEV 2        /* right-hand-side evaluations (0 on failure, as the reference) */
+#define B200ODE_IVP_NT_OUT 3      /* rows of t / y that are valid */
+#define B200ODE_IVP_ROWS_NEEDED 4 /* rows a complete result has (no t_eval: accepted steps + 1) */
+#define B200ODE_IVP_EVENT_FOUND 5
+#define B200ODE_IVP_IND_EVENT 6   /* 0-based index of the event function that fired */
+#define B200ODE_IVP_IDID 7        /* dop853_module.f90:340-347; 2 = stopped by an event */
+#define B200ODE_IVP_NSTEP 8
+#define B200ODE_IVP_NACCPT 9
+#define B200ODE_IVP_NREJCT 10
+const char* b200ode_ivp_message(int code);
+
+/* Zero-initialise and set size = sizeof(b200ode_ivp_problem). */
+typedef struct b200ode_ivp_problem {
+    size_t size;
+    long long B;
+    int neq;
+    const double* t_span;     /* [B,2] (t_span_stride = 2) or one shared [2] (0) */
+    long long t_span_stride;
+    const double* y0;         /* [B,neq] (y0_stride = neq) or one shared [neq] (0) */
+    long long y0_stride;
+    const void* data;         /* as b200ode_dop853_batched */
+    long long data_stride;
+    int np;
+    int nt;                   /* 0: no t_eval -- every accepted step is an output row */
+    const double* teval;      /* [nt], shared by the ensemble; must not decrease (increase) for a
+                                 trajectory that integrates forward (backward) */
+    int n_events;             /* as given to b200ode_link_ivp */
+    double first_step;        /* 0: the solver chooses (hinit) */
+    double max_step;          /* 0: no limit */
+    double rtol, atol;
+    const double* rtol_b;     /* [B] or NULL */
+    const double* atol_b;
+    /* Output rows.  With t_eval: y_out[B,nt,neq], t_out unused.  Without: trajectory b owns
+     * `cap` rows, t_out[B,cap], y_out[B,cap,neq] -- or, with row_offset[B+1], the rows
+     * [row_offset[b], row_offset[b+1]) of t_out[row_offset[B]], y_out[row_offset[B],neq].
+     * A trajectory with more accepted steps than rows ends with success = 0, message
+     * "output capacity exceeded", its rows filled and ROWS_NEEDED = what it takes: a first
+     * pass with cap = 0 (t_out = y_out = NULL) sizes an exact second one. */
+    long long cap;
+    const long long* row_offset;
+    double* t_out;
+    double* y_out;
+    int* result;              /* [B,12] */
+    double* t_event;          /* [B]; 0 without an event */
+    double* y_event;          /* [B,neq]; 0 without an event */
+} b200ode_ivp_problem;
+/* host pointers; copies to / from `device` */
+int b200ode_solve_ivp(b200ode_rhs_t ivp, const b200ode_ivp_problem* problem, int device);
+/* device pointers on the current device; asynchronous on `stream` */
+int b200ode_solve_ivp_device(b200ode_rhs_t ivp, const b200ode_ivp_problem* problem, void* stream);
 
 /* Page-locked host memory for usol / success / counters: with it the device-to-host
  * copies of b200ode_*_batched run at full PCIe speed and overlap the kernels (with pageable

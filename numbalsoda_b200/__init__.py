@@ -1,9 +1,10 @@
-"""numbalsoda_b200: B200-native batched lsoda / dop853 behind numbalsoda's API
-(reference numbalsoda/__init__.py:1-2)."""
+"""numbalsoda_b200: B200-native batched lsoda / dop853 / solve_ivp behind numbalsoda's API
+(reference numbalsoda/__init__.py:1-3)."""
 from .driver import lsoda_sig, lsoda, address_as_void_pointer
 from .driver_dop853 import dop853
+from .driver_solve_ivp import solve_ivp, ODEResult, ODEResultBatch
 from .rhs import builtin, register, get_handle
 from ._lib import B200OdeError, pinned_empty
 
-__all__ = ["lsoda_sig", "lsoda", "dop853", "address_as_void_pointer", "builtin", "register",
+__all__ = ["lsoda_sig", "lsoda", "dop853", "solve_ivp", "ODEResult", "ODEResultBatch", "address_as_void_pointer", "builtin", "register",
            "get_handle", "B200OdeError", "pinned_empty"]

@@ -6,11 +6,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(HERE, "libb200ode.so")
 
-DOP853, LSODA = 0, 1
+DOP853, LSODA, SOLVE_IVP = 0, 1, 2
 IMG_LTOIR, IMG_PTX, IMG_FATBIN, IMG_BUILTIN = 0, 1, 2, 3
 STRICT_FP = 1
 EXACT_CTRL = 2
 NCOUNTERS = 8
+IVP_NRESULT = 12
+IVP_NEVENTS_MAX = 8
 
 
 class B200OdeError(RuntimeError):
@@ -28,13 +30,26 @@ class Problem(ct.Structure):
                 ("counters", ct.c_void_p)]
 
 
+class IvpProblem(ct.Structure):
+    """b200ode_ivp_problem (include/b200ode.h)."""
+    _fields_ = [("size", ct.c_size_t), ("B", ct.c_longlong), ("neq", ct.c_int),
+                ("t_span", ct.c_void_p), ("t_span_stride", ct.c_longlong), ("y0", ct.c_void_p),
+                ("y0_stride", ct.c_longlong), ("data", ct.c_void_p), ("data_stride", ct.c_longlong),
+                ("np", ct.c_int), ("nt", ct.c_int), ("teval", ct.c_void_p), ("n_events", ct.c_int),
+                ("first_step", ct.c_double), ("max_step", ct.c_double), ("rtol", ct.c_double),
+                ("atol", ct.c_double), ("rtol_b", ct.c_void_p), ("atol_b", ct.c_void_p),
+                ("cap", ct.c_longlong), ("row_offset", ct.c_void_p), ("t_out", ct.c_void_p),
+                ("y_out", ct.c_void_p), ("result", ct.c_void_p), ("t_event", ct.c_void_p),
+                ("y_event", ct.c_void_p)]
+
+
 def _load(rebuilt=False):
     if not os.path.exists(LIBPATH):
         from . import build as _build
         _build.build()
         rebuilt = True
     lib = ct.CDLL(LIBPATH)
-    if not hasattr(lib, "b200ode_host_alloc") and not rebuilt:
+    if not hasattr(lib, "b200ode_solve_ivp") and not rebuilt:
         # a library built from older sources: rebuild it once
         from . import build as _build
         _build.build(force=True)
@@ -53,6 +68,11 @@ def _load(rebuilt=False):
     lib.b200ode_kernel_info.argtypes = [vp, ct.POINTER(i * 8)]
     lib.b200ode_solve.argtypes = [vp, ct.POINTER(Problem), i]
     lib.b200ode_solve_device.argtypes = [vp, ct.POINTER(Problem), vp]
+    lib.b200ode_link_ivp.argtypes = [i, vp, sz, i, i, vp, sz, i, ct.c_uint, ct.POINTER(vp)]
+    lib.b200ode_solve_ivp.argtypes = [vp, ct.POINTER(IvpProblem), i]
+    lib.b200ode_solve_ivp_device.argtypes = [vp, ct.POINTER(IvpProblem), vp]
+    lib.b200ode_ivp_message.argtypes = [i]
+    lib.b200ode_ivp_message.restype = ct.c_char_p
     lib.b200ode_host_alloc.argtypes = [sz, ct.POINTER(vp)]
     lib.b200ode_host_free.argtypes = [vp]
     return lib

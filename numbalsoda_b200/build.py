@@ -28,11 +28,13 @@ NVCC_FLAGS = ["-O3", "-lineinfo", "-rdc=true", "-fatbin", "-std=c++17"]
 # threads that must fit one SM); chosen so that ptxas does not spill (checked by
 # tests/test_abi.py on the linked cubin).
 MINBLOCKS = {"dop853": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1},
-             "lsoda": {1: 3, 2: 3, 3: 3, 4: 2, 5: 4, 6: 3, 7: 2, 8: 2}}
+             "lsoda": {1: 3, 2: 3, 3: 3, 4: 2, 5: 4, 6: 3, 7: 2, 8: 2},
+             "ivp": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1}}
 # lsoda keeps (13 n + n^2) doubles per thread in shared memory (lsoda_kernel.cu):
 # blocks of 64 threads from n = 5 so that several blocks still fit the 227 KB of an SM
 THREADS = {"dop853": {n: 128 for n in range(1, 9)},
-           "lsoda": {1: 128, 2: 128, 3: 128, 4: 128, 5: 64, 6: 64, 7: 64, 8: 64}}
+           "lsoda": {1: 128, 2: 128, 3: 128, 4: 128, 5: 64, 6: 64, 7: 64, 8: 64},
+           "ivp": {n: 128 for n in range(1, 9)}}
 # DOP853 dense-output queue: records per warp (dop853_kernel.cu); 64 = single inlined
 # drain site; sized so that MINBLOCKS blocks fit the 227 KB of shared memory.
 QCAP = {1: 55, 2: 55, 3: 55, 4: 63, 5: 63, 6: 63, 7: 63, 8: 63}
@@ -50,8 +52,11 @@ SOLVERS = {
     # name: (source, sizes)
     "dop853": ("dop853_kernel.cu", list(range(1, 9))),
     "lsoda": ("lsoda_kernel.cu", list(range(1, 9))),
+    # solve_ivp: DOP853 with dense output after every step and terminal events
+    "ivp": ("solve_ivp_kernel.cu", list(range(1, 9))),
 }
 BUILTIN_RHS = ["lotka_volterra", "lorenz", "robertson", "brusselator1d"]
+BUILTIN_EVENTS = ["none", "lv_prey", "lorenz_z"]
 
 
 def _newer(target, deps):
@@ -96,6 +101,8 @@ def build(force=False, verbose=False):
                     extra += os.environ.get("B200ODE_LSODA_DEFS", "").split()
                 if name == "dop853":
                     extra += os.environ.get("B200ODE_DOP853_DEFS", "").split()
+                if name == "ivp":
+                    extra += os.environ.get("B200ODE_IVP_DEFS", "").split()
                 log = _run([NVCC] + ARCH + NVCC_FLAGS + extra + ["-DB200_NEQ=%d" % n, "-DB200_QCAP=%d" % qc,
                                                           "-DB200_MINBLOCKS=%d" % mb, "-DB200_DRAIN_NOINLINE=%d" % ni, "-DB200_THREADS=%d" % th,
                                                           "-o", out, srcp])
@@ -121,6 +128,13 @@ def build(force=False, verbose=False):
         if force or _newer(out, [srcp]):
             _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_RHS_%s" % r.upper(), "-o", out, srcp])
         images.append(("rhs_" + r, out))
+
+    srcp = os.path.join(CSRC, "events_builtin.cu")
+    for r in BUILTIN_EVENTS:
+        out = os.path.join(OBJ, "events_%s.fatbin" % r)
+        if force or _newer(out, [srcp]):
+            _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_EVENTS_%s" % r.upper(), "-o", out, srcp])
+        images.append(("events_" + r, out))
 
     # the handle's link flags as a link-time constant (link_flags.cu)
     srcp = os.path.join(CSRC, "link_flags.cu")

@@ -145,6 +145,7 @@ struct PerDevice {
 
 struct b200ode_rhs_s {
     int solver = 0, neq = 0;
+    int n_events = 0;  // solve_ivp handles
     unsigned flags = 0;
     std::vector<char> cubin;
     std::mutex mu;
@@ -163,54 +164,53 @@ static bool warp_kernel(int solver, int neq)
 }
 static const char* kernel_name(int solver, int neq)
 {
+    if (solver == B200ODE_SOLVE_IVP) return "b200ode_ivp_kernel";
     if (solver == B200ODE_DOP853)
         return warp_kernel(solver, neq) ? "b200ode_dop853w_kernel" : "b200ode_dop853_kernel";
     return warp_kernel(solver, neq) ? "b200ode_lsodaw_kernel" : "b200ode_lsoda_kernel";
 }
 
-extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t size, int kind,
-                                unsigned flags, b200ode_rhs_t* out)
+// One user image of a link: kind (B200ODE_IMG_*) -> what nvJitLink takes.
+struct UserImage {
+    const void* data = nullptr;
+    size_t size = 0;
+    nvJitLinkInputType type = NVJITLINK_INPUT_LTOIR;
+};
+static int resolve_image(const void* image, size_t size, int kind, const char* builtin_prefix,
+                         const char* what, UserImage* out)
 {
-    if (!out) return fail(B200ODE_EINVAL, "out is NULL");
-    *out = nullptr;
-    if (solver != B200ODE_DOP853 && solver != B200ODE_LSODA)
-        return fail(B200ODE_EINVAL, "unknown solver %d", solver);
-    if (neq < 1) return fail(B200ODE_EINVAL, "neq = %d", neq);
-    if (!image) return fail(B200ODE_EINVAL, "image is NULL");
-    char name[64];
-    if (warp_kernel(solver, neq)) {
-        if (neq > B200ODE_WARP_NMAX)
-            return fail(B200ODE_ENOSYS, "neq = %d exceeds %d", neq, B200ODE_WARP_NMAX);
-        snprintf(name, sizeof name, solver == B200ODE_DOP853 ? "dop853w" : "lsodaw");
-    } else {
-        snprintf(name, sizeof name, "%s_n%d", solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq);
-    }
-    const B200EmbeddedImage* solver_img = find_image(name);
-    if (!solver_img)
-        return fail(B200ODE_ENOSYS, "no %s kernel was built for neq = %d (image %s missing)",
-                    solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq, name);
-
-    const void* rhs_data = image;
-    size_t rhs_size = size;
-    nvJitLinkInputType rhs_type = NVJITLINK_INPUT_LTOIR;
+    if (!image) return fail(B200ODE_EINVAL, "%s image is NULL", what);
+    out->data = image;
+    out->size = size;
     switch (kind) {
-    case B200ODE_IMG_LTOIR: rhs_type = NVJITLINK_INPUT_LTOIR; break;
-    case B200ODE_IMG_PTX: rhs_type = NVJITLINK_INPUT_PTX; break;
-    case B200ODE_IMG_FATBIN: rhs_type = NVJITLINK_INPUT_FATBIN; break;
+    case B200ODE_IMG_LTOIR: out->type = NVJITLINK_INPUT_LTOIR; break;
+    case B200ODE_IMG_PTX: out->type = NVJITLINK_INPUT_PTX; break;
+    case B200ODE_IMG_FATBIN: out->type = NVJITLINK_INPUT_FATBIN; break;
     case B200ODE_IMG_BUILTIN: {
-        std::string n = std::string("rhs_") + static_cast<const char*>(image);
+        std::string n = std::string(builtin_prefix) + static_cast<const char*>(image);
         const B200EmbeddedImage* r = find_image(n);
-        if (!r) return fail(B200ODE_EINVAL, "unknown built-in right-hand side '%s'",
+        if (!r) return fail(B200ODE_EINVAL, "unknown built-in %s '%s'", what,
                             static_cast<const char*>(image));
-        rhs_data = r->begin;
-        rhs_size = (size_t)(r->end - r->begin);
-        rhs_type = NVJITLINK_INPUT_FATBIN;
+        out->data = r->begin;
+        out->size = (size_t)(r->end - r->begin);
+        out->type = NVJITLINK_INPUT_FATBIN;
         break;
     }
     default: return fail(B200ODE_EINVAL, "unknown image kind %d", kind);
     }
-    if (rhs_size == 0) return fail(B200ODE_EINVAL, "empty right-hand-side image");
+    if (out->size == 0) return fail(B200ODE_EINVAL, "empty %s image", what);
+    return 0;
+}
 
+// nvJitLink: solver image + right-hand side (+ events function) + link flags -> cubin.
+static int link_handle(int solver, int neq, const char* name, const UserImage& rhs,
+                       const UserImage* events, int n_events, unsigned flags, b200ode_rhs_t* out)
+{
+    const B200EmbeddedImage* solver_img = find_image(name);
+    if (!solver_img)
+        return fail(B200ODE_ENOSYS, "no %s kernel was built for neq = %d (image %s missing)",
+                    solver == B200ODE_DOP853 ? "dop853" : solver == B200ODE_LSODA ? "lsoda" : "solve_ivp",
+                    neq, name);
     std::vector<const char*> opts = {"-arch=sm_100a", "-lto", "-O3", "-lineinfo"};
     if (flags & B200ODE_STRICT_FP) opts.push_back("-fma=0");
     nvJitLinkHandle h;
@@ -229,8 +229,12 @@ extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t s
     r = nvJitLinkAddData(h, NVJITLINK_INPUT_FATBIN, solver_img->begin,
                          (size_t)(solver_img->end - solver_img->begin), name);
     if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(solver)", r);
-    r = nvJitLinkAddData(h, rhs_type, rhs_data, rhs_size, "b200ode_user_rhs");
+    r = nvJitLinkAddData(h, rhs.type, rhs.data, rhs.size, "b200ode_user_rhs");
     if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(rhs)", r);
+    if (events) {
+        r = nvJitLinkAddData(h, events->type, events->data, events->size, "b200ode_user_events");
+        if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(events)", r);
+    }
     {
         // the flags as a device-side link-time constant (link_flags.cu)
         char fname[32];
@@ -251,6 +255,7 @@ extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t s
     b200ode_rhs_s* H = new b200ode_rhs_s;
     H->solver = solver;
     H->neq = neq;
+    H->n_events = n_events;
     H->flags = flags;
     H->cubin.resize(n);
     r = nvJitLinkGetLinkedCubin(h, H->cubin.data());
@@ -261,6 +266,57 @@ extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t s
     nvJitLinkDestroy(&h);
     *out = H;
     return 0;
+}
+
+extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t size, int kind,
+                                unsigned flags, b200ode_rhs_t* out)
+{
+    if (!out) return fail(B200ODE_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (solver == B200ODE_SOLVE_IVP)
+        return b200ode_link_ivp(neq, image, size, kind, 0, nullptr, 0, 0, flags, out);
+    if (solver != B200ODE_DOP853 && solver != B200ODE_LSODA)
+        return fail(B200ODE_EINVAL, "unknown solver %d", solver);
+    if (neq < 1) return fail(B200ODE_EINVAL, "neq = %d", neq);
+    char name[64];
+    if (warp_kernel(solver, neq)) {
+        if (neq > B200ODE_WARP_NMAX)
+            return fail(B200ODE_ENOSYS, "neq = %d exceeds %d", neq, B200ODE_WARP_NMAX);
+        snprintf(name, sizeof name, solver == B200ODE_DOP853 ? "dop853w" : "lsodaw");
+    } else {
+        snprintf(name, sizeof name, "%s_n%d", solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq);
+    }
+    UserImage rhs;
+    int rc = resolve_image(image, size, kind, "rhs_", "right-hand side", &rhs);
+    if (rc) return rc;
+    return link_handle(solver, neq, name, rhs, nullptr, 0, flags, out);
+}
+
+extern "C" int b200ode_link_ivp(int neq, const void* rhs_image, size_t rhs_size, int rhs_kind,
+                                int n_events, const void* events_image, size_t events_size,
+                                int events_kind, unsigned flags, b200ode_rhs_t* out)
+{
+    if (!out) return fail(B200ODE_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (neq < 1) return fail(B200ODE_EINVAL, "neq = %d", neq);
+    if (neq > B200ODE_THREAD_NMAX)
+        return fail(B200ODE_ENOSYS, "solve_ivp: neq = %d exceeds %d", neq, B200ODE_THREAD_NMAX);
+    if (n_events < 0 || n_events > B200ODE_IVP_NEVMAX)
+        return fail(n_events < 0 ? B200ODE_EINVAL : B200ODE_ENOSYS,
+                    "solve_ivp: n_events = %d (at most %d)", n_events, B200ODE_IVP_NEVMAX);
+    if (n_events > 0 && !events_image)
+        return fail(B200ODE_EINVAL, "n_events = %d but the events image is NULL", n_events);
+    char name[64];
+    snprintf(name, sizeof name, "ivp_n%d", neq);
+    UserImage rhs, ev;
+    int rc = resolve_image(rhs_image, rhs_size, rhs_kind, "rhs_", "right-hand side", &rhs);
+    if (rc) return rc;
+    if (n_events > 0)
+        rc = resolve_image(events_image, events_size, events_kind, "events_", "events function", &ev);
+    else
+        rc = resolve_image("none", 4, B200ODE_IMG_BUILTIN, "events_", "events function", &ev);
+    if (rc) return rc;
+    return link_handle(B200ODE_SOLVE_IVP, neq, name, rhs, &ev, n_events, flags, out);
 }
 
 extern "C" void b200ode_rhs_free(b200ode_rhs_t H)
@@ -338,8 +394,10 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         } else {
             // ask the image for its build-time geometry (queue / storage sizes, threads)
             const bool dop = H->solver == B200ODE_DOP853;
+            const bool ivp = H->solver == B200ODE_SOLVE_IVP;
             CUfunction cfg;
-            CU(cuModuleGetFunction(&cfg, P.mod, dop ? "b200ode_dop853_config" : "b200ode_lsoda_config"));
+            CU(cuModuleGetFunction(&cfg, P.mod, ivp ? "b200ode_ivp_config"
+                                                    : dop ? "b200ode_dop853_config" : "b200ode_lsoda_config"));
             int* d_cfg = reinterpret_cast<int*>(P.next);  // scratch: 32 bytes of the slots
             void* cp[] = {&d_cfg};
             CU(cuLaunchKernel(cfg, 1, 1, 1, 1, 1, 1, 0, nullptr, cp, nullptr));
@@ -350,7 +408,11 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
             P.threads = cfgv[4];
             if (P.threads < 32 || P.threads > 1024 || P.threads % 32)
                 return fail(B200ODE_ECUDA, "solver image reports %d threads per block", P.threads);
-            if (dop) {
+            if (ivp) {
+                if (cfgv[0] != B200ODE_IVP_DOUBLES(H->neq) * P.threads || cfgv[1] != B200ODE_IVP_NEVMAX)
+                    return fail(B200ODE_ECUDA, "solve_ivp image reports an inconsistent geometry");
+                P.dyn_smem = cfgv[0] * (int)sizeof(double);
+            } else if (dop) {
                 if (cfgv[0] < 32 || cfgv[1] != B200ODE_DOP853_QFIELDS(H->neq))
                     return fail(B200ODE_ECUDA, "dop853 image reports an inconsistent queue geometry");
                 P.qcap = cfgv[0];
@@ -793,6 +855,281 @@ extern "C" int b200ode_solve_device(b200ode_rhs_t H, const b200ode_problem* p, v
                         p->mxstep, p->success, p->counters,
                         H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, stream, p->rtol_b,
                         p->atol_b);
+}
+
+// ---------------------------------------------------------------- solve_ivp
+static const char* const kIvpMessages[] = {
+    // the reference's strings, src/dop853_solve_ivp.f90:390, :364, :351, :300, :273
+    "The solver successfully reached the end of the integration interval.",
+    "A termination event occurred.",
+    "Failed to complete integration.",
+    "\"t_eval\" does not always increase or decrease",
+    "Integrator failed to initialize.",
+    "brent failed",              // the reference prints this and stops the process (:110-113)
+    "output capacity exceeded",  // not in the reference, whose result arrays grow
+};
+extern "C" const char* b200ode_ivp_message(int code)
+{
+    if (code < 0 || code >= (int)(sizeof kIvpMessages / sizeof kIvpMessages[0])) return "";
+    return kIvpMessages[code];
+}
+
+static int check_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p)
+{
+    if (!H) return fail(B200ODE_EINVAL, "handle is NULL");
+    if (!p) return fail(B200ODE_EINVAL, "problem is NULL");
+    if (p->size != sizeof(b200ode_ivp_problem))
+        return fail(B200ODE_EINVAL, "problem.size = %zu, expected sizeof(b200ode_ivp_problem) = %zu",
+                    p->size, sizeof(b200ode_ivp_problem));
+    if (H->solver != B200ODE_SOLVE_IVP)
+        return fail(B200ODE_EINVAL, "handle was not linked by b200ode_link_ivp");
+    if (p->neq != H->neq)
+        return fail(B200ODE_EINVAL, "neq = %d but the handle was linked for neq = %d", p->neq, H->neq);
+    if (p->n_events != H->n_events)
+        return fail(B200ODE_EINVAL, "n_events = %d but the handle was linked for %d", p->n_events,
+                    H->n_events);
+    if (p->B < 0 || p->nt < 0 || p->cap < 0)
+        return fail(B200ODE_EINVAL, "B = %lld, nt = %d, cap = %lld", p->B, p->nt, p->cap);
+    if (p->np > B200ODE_NPMAX)
+        return fail(B200ODE_EINVAL, "np = %d exceeds %d; pass np = -1 to hand the record's address "
+                                    "to the right-hand side instead", p->np, B200ODE_NPMAX);
+    if (p->t_span_stride != 0 && p->t_span_stride != 2)
+        return fail(B200ODE_EINVAL, "t_span_stride = %lld (0 or 2)", p->t_span_stride);
+    if (p->y0_stride != 0 && p->y0_stride < p->neq)
+        return fail(B200ODE_EINVAL, "y0_stride = %lld", p->y0_stride);
+    if (p->B == 0) return 0;
+    if (!p->t_span || !p->y0 || !p->result || !p->t_event || !p->y_event || (!p->data && p->np != 0) ||
+        (p->nt > 0 && (!p->teval || !p->y_out)))
+        return fail(B200ODE_EINVAL, "NULL array argument");
+    return 0;
+}
+
+static int launch_ivp(b200ode_rhs_t H, PerDevice* P, B200IvpLaunch args, CUstream stream)
+{
+    if (args.B == 0) return 0;
+    unsigned slot = H->slot.fetch_add(1) % kCounterSlots;
+    CUdeviceptr next = P->next + slot * sizeof(unsigned long long);
+    CU(cuMemsetD8Async(next, 0, sizeof(unsigned long long), stream));
+    args.next = reinterpret_cast<unsigned long long*>(next);
+    const long long want = (args.B + P->threads - 1) / P->threads;
+    const long long resident = (long long)P->sms * P->blocks_per_sm;
+    const int grid = (int)std::min(want, resident);
+    CUfunction fn = args.np >= 0 ? P->fn : P->fn_ptr;
+    void* params[] = {&args};
+    CU(cuLaunchKernel(fn, grid, 1, 1, P->threads, 1, 1, (unsigned)P->dyn_smem, stream, params, nullptr));
+    H->last_grid = grid;
+    H->launches++;
+    return 0;
+}
+
+static void fill_ivp_launch(B200IvpLaunch* a, const b200ode_ivp_problem* p)
+{
+    memset(a, 0, sizeof *a);
+    a->B = p->B;
+    a->t_span = p->t_span;
+    a->t_span_stride = p->t_span_stride;
+    a->y0 = p->y0;
+    a->y0_stride = p->y0_stride;
+    a->data = static_cast<const char*>(p->data);
+    a->data_stride = p->data_stride > 0 ? p->data_stride : 0;
+    a->np = p->np;
+    a->nt = p->nt;
+    a->t_eval = p->teval;
+    a->n_events = p->n_events;
+    a->cap = p->nt > 0 ? p->nt : p->cap;
+    a->row_offset = p->nt > 0 ? nullptr : p->row_offset;
+    a->first_step = p->first_step;
+    a->max_step = p->max_step;
+    a->rtol = p->rtol;
+    a->atol = p->atol;
+    a->rtol_b = p->rtol_b;
+    a->atol_b = p->atol_b;
+    a->t_out = p->t_out;
+    a->y_out = p->y_out;
+    a->result = p->result;
+    a->t_event = p->t_event;
+    a->y_event = p->y_event;
+}
+
+extern "C" int b200ode_solve_ivp_device(b200ode_rhs_t H, const b200ode_ivp_problem* p, void* stream)
+{
+    int rc = check_ivp(H, p);
+    if (rc) return rc;
+    PerDevice* P;
+    rc = device_state(H, -1, &P);
+    if (rc) return rc;
+    B200IvpLaunch a;
+    fill_ivp_launch(&a, p);
+    return launch_ivp(H, P, a, static_cast<CUstream>(stream));
+}
+
+// Host-buffer entry point: the ensemble is cut into chunks of trajectories whose rows fit a
+// device buffer; chunk c integrates on the kernel stream while the rows of chunk c-1 travel
+// back on the copy stream (two output buffers).
+extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, int device)
+{
+    int rc = check_ivp(H, p);
+    if (rc) return rc;
+    if (device < 0) return fail(B200ODE_EINVAL, "device = %d", device);
+    const long long B = p->B;
+    if (B == 0) return 0;
+    const int n = p->neq, nt = p->nt;
+    const bool ragged = nt == 0 && p->row_offset != nullptr;
+    if (ragged)
+        for (long long b = 0; b < B; b++)
+            if (p->row_offset[b + 1] < p->row_offset[b] || p->row_offset[b + 1] - p->row_offset[b] > 0x7fffffffLL)
+                return fail(B200ODE_EINVAL, "row_offset must not decrease (trajectory %lld)", b);
+    auto rows_upto = [&](long long b) -> long long {  // rows owned by trajectories [0, b)
+        return nt > 0 ? b * nt : ragged ? p->row_offset[b] - p->row_offset[0] : b * p->cap;
+    };
+    if (rows_upto(B) > 0 && (!p->y_out || (nt == 0 && !p->t_out)))
+        return fail(B200ODE_EINVAL, "NULL output array");
+    PerDevice* P;
+    rc = device_state(H, device, &P);
+    if (rc) return rc;
+
+    // chunks: at most ~1 GiB of rows (and what the device has free), at least one trajectory
+    size_t free_b = 0, total_b = 0;
+    CU(cuMemGetInfo_v2(&free_b, &total_b));
+    const size_t row_bytes = sizeof(double) * (size_t)(n + (nt == 0 ? 1 : 0));
+    const size_t budget = std::min<size_t>((size_t)1 << 30, std::max<size_t>(free_b / 8, (size_t)64 << 20));
+    const size_t fixed = sizeof(int) * B200ODE_IVP_NRESULT + sizeof(double) * (size_t)(1 + n);
+    std::vector<long long> cut = {0};
+    {
+        long long b0 = 0;
+        while (b0 < B) {
+            long long b1 = b0 + 1;
+            // grow the chunk while it fits the budget (binary search on the prefix sums)
+            long long lo = b0 + 1, hi = B;
+            while (lo < hi) {
+                const long long mid = lo + (hi - lo + 1) / 2;
+                const size_t bytes = (size_t)(rows_upto(mid) - rows_upto(b0)) * row_bytes + (size_t)(mid - b0) * fixed;
+                if (bytes <= budget) lo = mid;
+                else hi = mid - 1;
+            }
+            b1 = std::max(b1, lo);
+            // a few chunks even when everything fits, so that copies overlap kernels
+            const long long resident = (long long)P->sms * P->blocks_per_sm * P->threads;
+            long long want = std::max<long long>(4 * resident, (B + 7) / 8);
+            if (const char* e = getenv("B200ODE_IVP_CHUNK"))  // tests: force many small chunks
+                want = std::max<long long>(1, atoll(e));
+            b1 = std::min(b1, b0 + want);
+            cut.push_back(b1);
+            b0 = b1;
+        }
+    }
+    const long long nchunks = (long long)cut.size() - 1;
+    long long max_rows = 0, max_traj = 0;
+    for (long long c = 0; c < nchunks; c++) {
+        max_rows = std::max(max_rows, rows_upto(cut[c + 1]) - rows_upto(cut[c]));
+        max_traj = std::max(max_traj, cut[c + 1] - cut[c]);
+    }
+    const int nbuf = (int)std::min<long long>(nchunks, 2);
+
+    const size_t rec = p->data_stride != 0 ? (size_t)(p->data_stride > 0 ? p->data_stride : -p->data_stride)
+                                           : (size_t)(p->np > 0 ? p->np * 8 : 0);
+    const size_t data_bytes = p->data ? (p->data_stride > 0 ? (size_t)p->data_stride * (size_t)B : rec) : 0;
+    const size_t ts_bytes = sizeof(double) * 2 * (size_t)(p->t_span_stride ? B : 1);
+    const size_t y0_bytes = sizeof(double) * n * (size_t)(p->y0_stride ? B : 1);
+    const size_t tol_bytes = sizeof(double) * (size_t)B;
+    const size_t off_bytes = ragged ? sizeof(long long) * (size_t)(max_traj + 1) : 0;
+    const size_t in_bytes = align256(sizeof(double) * std::max(nt, 1)) + align256(ts_bytes) + align256(y0_bytes) +
+                            align256(data_bytes) + (p->rtol_b ? align256(tol_bytes) : 0) +
+                            (p->atol_b ? align256(tol_bytes) : 0);
+    const size_t out_bytes = align256(sizeof(double) * (size_t)max_rows * n) +
+                             (nt == 0 ? align256(sizeof(double) * (size_t)max_rows) : 0) +
+                             align256(sizeof(int) * B200ODE_IVP_NRESULT * (size_t)max_traj) +
+                             align256(sizeof(double) * (size_t)max_traj) +
+                             align256(sizeof(double) * n * (size_t)max_traj) + align256(off_bytes);
+    Scratch mem;
+    if ((rc = mem.acquire(device, in_bytes + out_bytes * nbuf + 8192))) return rc;
+    const CUdeviceptr d_te = mem.take(sizeof(double) * std::max(nt, 1));
+    const CUdeviceptr d_ts = mem.take(ts_bytes);
+    const CUdeviceptr d_y0 = mem.take(y0_bytes);
+    const CUdeviceptr d_data = mem.take(data_bytes);
+    const CUdeviceptr d_rtol = p->rtol_b ? mem.take(tol_bytes) : 0;
+    const CUdeviceptr d_atol = p->atol_b ? mem.take(tol_bytes) : 0;
+    CUdeviceptr d_y[2], d_t[2] = {0, 0}, d_res[2], d_tev[2], d_yev[2], d_off[2] = {0, 0};
+    for (int i = 0; i < nbuf; i++) {
+        d_y[i] = mem.take(sizeof(double) * (size_t)max_rows * n);
+        if (nt == 0) d_t[i] = mem.take(sizeof(double) * (size_t)max_rows);
+        d_res[i] = mem.take(sizeof(int) * B200ODE_IVP_NRESULT * (size_t)max_traj);
+        d_tev[i] = mem.take(sizeof(double) * (size_t)max_traj);
+        d_yev[i] = mem.take(sizeof(double) * n * (size_t)max_traj);
+        if (ragged) d_off[i] = mem.take(off_bytes);
+    }
+    Stream sk, sc;
+    if ((rc = sk.create()) || (rc = sc.create())) return rc;
+    Event ev_kernel[2], ev_copied[2];
+    for (int i = 0; i < nbuf; i++)
+        if ((rc = ev_kernel[i].create()) || (rc = ev_copied[i].create())) return rc;
+
+    if (nt > 0) CU(cuMemcpyHtoDAsync_v2(d_te, p->teval, sizeof(double) * nt, sk.s));
+    CU(cuMemcpyHtoDAsync_v2(d_ts, p->t_span, ts_bytes, sk.s));
+    if (p->y0_stride == 0 || p->y0_stride == n) {
+        CU(cuMemcpyHtoDAsync_v2(d_y0, p->y0, y0_bytes, sk.s));
+    } else {
+        for (long long b = 0; b < B; b++)
+            CU(cuMemcpyHtoDAsync_v2(d_y0 + sizeof(double) * n * (size_t)b, p->y0 + b * p->y0_stride,
+                                    sizeof(double) * n, sk.s));
+    }
+    if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data, p->data, data_bytes, sk.s));
+    if (p->rtol_b) CU(cuMemcpyHtoDAsync_v2(d_rtol, p->rtol_b, tol_bytes, sk.s));
+    if (p->atol_b) CU(cuMemcpyHtoDAsync_v2(d_atol, p->atol_b, tol_bytes, sk.s));
+
+    // ragged offsets of a chunk, relative to its first row (kept alive until the end)
+    std::vector<std::vector<long long>> rel(ragged ? (size_t)nchunks : 0);
+    auto copy_back = [&](long long c) -> int {
+        const int i = (int)(c % nbuf);
+        const long long b0 = cut[c], nb = cut[c + 1] - b0;
+        const long long r0 = rows_upto(b0), nr = rows_upto(cut[c + 1]) - r0;
+        CU(cuStreamWaitEvent(sc.s, ev_kernel[i].e, 0));
+        if (nr > 0) {
+            CU(cuMemcpyDtoHAsync_v2(p->y_out + (size_t)r0 * n, d_y[i], sizeof(double) * (size_t)nr * n, sc.s));
+            if (nt == 0) CU(cuMemcpyDtoHAsync_v2(p->t_out + r0, d_t[i], sizeof(double) * (size_t)nr, sc.s));
+        }
+        CU(cuMemcpyDtoHAsync_v2(p->result + b0 * B200ODE_IVP_NRESULT, d_res[i],
+                                sizeof(int) * B200ODE_IVP_NRESULT * (size_t)nb, sc.s));
+        CU(cuMemcpyDtoHAsync_v2(p->t_event + b0, d_tev[i], sizeof(double) * (size_t)nb, sc.s));
+        CU(cuMemcpyDtoHAsync_v2(p->y_event + b0 * n, d_yev[i], sizeof(double) * n * (size_t)nb, sc.s));
+        CU(cuEventRecord(ev_copied[i].e, sc.s));
+        return 0;
+    };
+    for (long long c = 0; c < nchunks; c++) {
+        const int i = (int)(c % nbuf);
+        const long long b0 = cut[c], nb = cut[c + 1] - b0;
+        if (c >= nbuf) CU(cuStreamWaitEvent(sk.s, ev_copied[i].e, 0));  // buffer i is free again
+        B200IvpLaunch a;
+        fill_ivp_launch(&a, p);
+        a.B = nb;
+        a.t_span = reinterpret_cast<const double*>(d_ts) + (p->t_span_stride ? 2 * (size_t)b0 : 0);
+        a.y0 = reinterpret_cast<const double*>(d_y0) + (p->y0_stride ? (size_t)b0 * n : 0);
+        a.y0_stride = p->y0_stride ? n : 0;
+        a.data = reinterpret_cast<const char*>(d_data) + (p->data_stride > 0 ? (size_t)b0 * p->data_stride : 0);
+        a.t_eval = reinterpret_cast<const double*>(d_te);
+        a.rtol_b = p->rtol_b ? reinterpret_cast<const double*>(d_rtol) + b0 : nullptr;
+        a.atol_b = p->atol_b ? reinterpret_cast<const double*>(d_atol) + b0 : nullptr;
+        a.row_offset = nullptr;
+        if (ragged) {
+            std::vector<long long>& r = rel[(size_t)c];
+            r.resize((size_t)nb + 1);
+            for (long long k = 0; k <= nb; k++) r[(size_t)k] = p->row_offset[b0 + k] - p->row_offset[b0];
+            CU(cuMemcpyHtoDAsync_v2(d_off[i], r.data(), sizeof(long long) * (size_t)(nb + 1), sk.s));
+            a.row_offset = reinterpret_cast<const long long*>(d_off[i]);
+        }
+        a.t_out = reinterpret_cast<double*>(d_t[i]);
+        a.y_out = reinterpret_cast<double*>(d_y[i]);
+        a.result = reinterpret_cast<int*>(d_res[i]);
+        a.t_event = reinterpret_cast<double*>(d_tev[i]);
+        a.y_event = reinterpret_cast<double*>(d_yev[i]);
+        if ((rc = launch_ivp(H, P, a, sk.s))) return rc;
+        CU(cuEventRecord(ev_kernel[i].e, sk.s));
+        if (c >= 1 && (rc = copy_back(c - 1))) return rc;
+    }
+    if ((rc = copy_back(nchunks - 1))) return rc;
+    CU(cuStreamSynchronize(sc.s));
+    CU(cuStreamSynchronize(sk.s));
+    return 0;
 }
 
 // ---------------------------------------------------------------- pinned host memory

@@ -52,4 +52,43 @@ typedef struct B200OdeLaunch {
                                  shared memory and every block keeps its own copy of t_eval there */
 } B200OdeLaunch;
 
+/* ---- solve_ivp (solve_ivp_core.cuh, solve_ivp_kernel.cu) */
+#define B200ODE_IVP_NEVMAX 8   /* event functions per problem (values kept in registers) */
+#define B200ODE_IVP_NRESULT 12 /* ints per trajectory in the result array (include/b200ode.h) */
+/* per thread: 8 n dense-output coefficients + the previous event values */
+#define B200ODE_IVP_DOUBLES(n) (8 * (n) + B200ODE_IVP_NEVMAX)
+/* message codes = which of the reference's strings (dop853_solve_ivp.f90:273,:300,:351,:364,:390) */
+#define B200ODE_IVP_MSG_END 0
+#define B200ODE_IVP_MSG_EVENT 1
+#define B200ODE_IVP_MSG_FAILED 2
+#define B200ODE_IVP_MSG_TEVAL 3
+#define B200ODE_IVP_MSG_INIT 4
+#define B200ODE_IVP_MSG_BRENT 5
+#define B200ODE_IVP_MSG_CAPACITY 6
+
+typedef struct B200IvpLaunch {
+    long long B;
+    const double* t_span;    /* [B,2] (t_span_stride = 2) or [2] shared (0) */
+    long long t_span_stride; /* in doubles */
+    const double* y0;        /* [B,n] (y0_stride = n) or [n] shared (0) */
+    long long y0_stride;
+    const char* data;        /* as B200OdeLaunch */
+    long long data_stride;
+    int np;
+    int nt;                  /* 0: no t_eval, every accepted step is a row */
+    const double* t_eval;    /* [nt] */
+    int n_events;
+    long long cap;           /* without t_eval: rows per trajectory of t_out / y_out ... */
+    const long long* row_offset; /* ... or, if not null, [B+1] ragged row offsets */
+    double first_step, max_step, rtol, atol;
+    const double* rtol_b;    /* [B] or null */
+    const double* atol_b;
+    double* t_out;           /* [B,cap] or [row_offset[B]], written without t_eval only */
+    double* y_out;           /* [B,nt,n], [B,cap,n] or [row_offset[B],n] */
+    int* result;             /* [B,12] */
+    double* t_event;         /* [B] */
+    double* y_event;         /* [B,n] */
+    unsigned long long* next;
+} B200IvpLaunch;
+
 #endif

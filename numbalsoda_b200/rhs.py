@@ -138,15 +138,16 @@ def without_carray(pyfunc):
     return env[fdef.name]
 
 
-def compile_ltoir(pyfunc):
-    """numba.cuda: Python rhs(t, u, du, p) -> LTO-IR of `b200ode_user_rhs`."""
+def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs"):
+    """numba.cuda: Python rhs(t, u, du, p) -> LTO-IR of `b200ode_user_rhs` (or, for
+    solve_ivp's events(t, y, out, p), of `b200ode_user_events`)."""
     from numba import cuda, types
     sig = (types.double, types.CPointer(types.double), types.CPointer(types.double),
            types.CPointer(types.double))
 
     def build(f):
         code, _ = cuda.compile(f, sig, device=True, abi="c",
-                               abi_info={"abi_name": "b200ode_user_rhs"}, output="ltoir", cc=(9, 0))
+                               abi_info={"abi_name": abi_name}, output="ltoir", cc=(9, 0))
         return bytes(code)
 
     try:
@@ -194,5 +195,52 @@ def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False):
                                            ct.byref(out))
         _lib.check(rc)
         h = RhsHandle(out, solver, neq, flags, origin)
+        _handles[k] = h
+        return h
+
+
+def _origin(f, what):
+    """-> (cache key, Builtin or Python function) of a right-hand side / events function."""
+    if isinstance(f, Builtin):
+        return ("builtin", f.name), f
+    if isinstance(f, int):
+        f = _pyfunc_from_address(f)
+    elif hasattr(f, "_pyfunc") and hasattr(f, "address"):
+        f = f._pyfunc
+    if not callable(f):
+        raise TypeError("%s must be a cfunc address, a cfunc, a Python function or builtin(name); "
+                        "got %r" % (what, f))
+    return ("py", f), f
+
+
+def get_ivp_handle(rhs, neq, n_events=0, events=None, strict=False):
+    """solve_ivp: link the right-hand side and the events function (reference
+    numbalsoda/driver_solve_ivp.py:86-88: `funcptr`, `n_events`, `event_fcn`) with the
+    solve_ivp kernel, once per combination."""
+    flags = _lib.STRICT_FP if strict else 0
+    if isinstance(rhs, RhsHandle):
+        return rhs
+    n_events = int(n_events)
+    if n_events > 0 and (events is None or (isinstance(events, int) and events == 0)):
+        raise ValueError("n_events = %d but no event function was given" % n_events)
+    rkey, rorig = _origin(rhs, "right-hand side")
+    ekey, eorig = _origin(events, "event_fcn") if n_events > 0 else (None, None)
+    k = (rkey, ekey, n_events, _lib.SOLVE_IVP, neq, flags)
+    with _lock:
+        h = _handles.get(k)
+        if h is not None:
+            return h
+
+        def image(orig, abi_name):
+            if isinstance(orig, Builtin):
+                name = orig.name.encode()
+                return name, len(name), _lib.IMG_BUILTIN
+            img = compile_ltoir(orig, abi_name)
+            return img, len(img), _lib.IMG_LTOIR
+        ri, rn, rk = image(rorig, "b200ode_user_rhs")
+        ei, en, ek = image(eorig, "b200ode_user_events") if n_events > 0 else (None, 0, 0)
+        out = ct.c_void_p()
+        _lib.check(_lib.lib.b200ode_link_ivp(neq, ri, rn, rk, n_events, ei, en, ek, flags, ct.byref(out)))
+        h = RhsHandle(out, _lib.SOLVE_IVP, neq, flags, (rorig, eorig))
         _handles[k] = h
         return h

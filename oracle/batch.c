@@ -91,3 +91,68 @@ int oracle_solve_batch(int solver, oracle_rhs_fn f, long B, int neq, const doubl
         pthread_join(th[i], 0);
     return nthreads;
 }
+
+/* ---- solve_ivp ensembles: t_eval given (y_out[B,nt,neq]) or `cap` rows per trajectory
+ * (t_out[B,cap], y_out[B,cap,neq]); res[B], y_event[B,neq]. */
+typedef struct {
+    oracle_rhs_fn f, events;
+    long B;
+    int neq, nt, n_events, cap;
+    const double *t_span;
+    long t_span_stride;
+    const double *y0;
+    long y0_stride;
+    const void *data;
+    long data_stride;
+    const double *teval;
+    double first_step, max_step, rtol, atol;
+    double *t_out, *y_out, *y_event;
+    oracle_ivp_result *res;
+    atomic_long next;
+} ivp_job_t;
+
+static void *ivp_worker(void *arg)
+{
+    ivp_job_t *j = (ivp_job_t *)arg;
+    const long rows = j->nt > 0 ? j->nt : j->cap;
+    for (;;) {
+        long b0 = atomic_fetch_add(&j->next, 8), b1 = b0 + 8;
+        if (b0 >= j->B)
+            break;
+        if (b1 > j->B)
+            b1 = j->B;
+        for (long b = b0; b < b1; b++)
+            oracle_solve_ivp(j->f, j->t_span + b * j->t_span_stride, j->neq, j->y0 + b * j->y0_stride,
+                             j->nt, j->teval, j->n_events, j->events,
+                             (void *)((const char *)j->data + b * j->data_stride), j->first_step,
+                             j->max_step, j->rtol, j->atol, j->cap,
+                             j->t_out ? j->t_out + (size_t)b * rows : 0,
+                             j->y_out + (size_t)b * rows * j->neq, j->y_event + (size_t)b * j->neq,
+                             &j->res[b]);
+    }
+    return 0;
+}
+
+int oracle_solve_ivp_batch(oracle_rhs_fn f, oracle_rhs_fn events, long B, int neq, const double *t_span,
+                           long t_span_stride, const double *y0, long y0_stride, const void *data,
+                           long data_stride, int nt, const double *teval, int n_events,
+                           double first_step, double max_step, double rtol, double atol, int cap,
+                           double *t_out, double *y_out, double *y_event, oracle_ivp_result *res,
+                           int nthreads)
+{
+    ivp_job_t j = {f, events, B, neq, nt, n_events, cap, t_span, t_span_stride, y0, y0_stride, data,
+                   data_stride, teval, first_step, max_step, rtol, atol, t_out, y_out, y_event, res, 0};
+    pthread_t th[256];
+    if (nthreads <= 0)
+        nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (nthreads > 256)
+        nthreads = 256;
+    if (nthreads < 1)
+        nthreads = 1;
+    for (int i = 1; i < nthreads; i++)
+        pthread_create(&th[i], 0, ivp_worker, &j);
+    ivp_worker(&j);
+    for (int i = 1; i < nthreads; i++)
+        pthread_join(th[i], 0);
+    return nthreads;
+}

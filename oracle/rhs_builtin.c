@@ -62,8 +62,28 @@ void oracle_rhs_brusselator1d(double t, double *y, double *dy, void *pv)
     }
 }
 
+/* Events functions of solve_ivp (numbalsoda_b200/csrc/events_builtin.cu):
+ *   lv_prey   /root/reference/solve_ivp.ipynb cell 9: prey population u[0] crosses 1
+ *   lorenz_z  z crosses the level in the 4th parameter */
+void oracle_events_lv_prey(double t, double *u, double *out, void *pv)
+{
+    (void)t, (void)pv;
+    out[0] = u[0] - 1;
+}
+
+void oracle_events_lorenz_z(double t, double *u, double *out, void *pv)
+{
+    const double *p = (const double *)pv;
+    (void)t;
+    out[0] = u[2] - p[3];
+}
+
 oracle_rhs_fn oracle_builtin_rhs(const char *name)
 {
+    if (!strcmp(name, "events_lv_prey"))
+        return oracle_events_lv_prey;
+    if (!strcmp(name, "events_lorenz_z"))
+        return oracle_events_lorenz_z;
     if (!strcmp(name, "lotka_volterra"))
         return oracle_rhs_lotka_volterra;
     if (!strcmp(name, "lorenz"))

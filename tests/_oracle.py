@@ -158,3 +158,34 @@ def solve_ivp(fptr, t_span, y0, t_eval=None, n_events=0, events=0, data=None, fi
                 t=(te[:k].copy() if nt else t_out[:k]), y=y_out[:k], event_found=bool(res.event_found),
                 ind_event=res.ind_event, t_event=res.t_event, y_event=y_event, idid=res.idid,
                 nstep=res.nstep, naccpt=res.naccpt, nrejct=res.nrejct, rows_needed=res.rows_needed)
+
+
+def solve_ivp_batch(fptr, t_span, y0, t_eval=None, n_events=0, events=0, data=None, first_step=0.0,
+                    max_step=0.0, rtol=1e-3, atol=1e-6, cap=0, nthreads=0):
+    """oracle_solve_ivp_batch over host threads.  t_span [2] or [B,2], y0 [n] or [B,n], data [p] or
+    [B,p] -> dict of arrays: result[B] (IvpResult records), y[B,rows,n], t[B,rows] (no t_eval),
+    y_event[B,n]."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    ts = np.ascontiguousarray(t_span, dtype=np.float64)
+    te = np.ascontiguousarray([] if t_eval is None else t_eval, dtype=np.float64)
+    data = np.ascontiguousarray([0.0] if data is None else data, dtype=np.float64)
+    B = max([a.shape[0] for a in (y0, ts, data) if a.ndim == 2] or [1])
+    n, nt = y0.shape[-1], len(te)
+    rows = nt if nt else cap
+    t_out = np.full((B, rows), np.nan)
+    y_out = np.full((B, rows, n), np.nan)
+    y_event = np.zeros((B, n))
+    res = (IvpResult * B)()
+    lib.oracle_solve_ivp_batch.restype = ct.c_int
+    lib.oracle_solve_ivp_batch(ct.c_void_p(fptr), ct.c_void_p(events), ct.c_long(B), n, _p(ts),
+                               ct.c_long(2 if ts.ndim == 2 else 0), _p(y0),
+                               ct.c_long(n if y0.ndim == 2 else 0), _p(data),
+                               ct.c_long(data.shape[-1] * 8 if data.ndim == 2 else 0), nt, _p(te),
+                               int(n_events), ct.c_double(first_step), ct.c_double(max_step),
+                               ct.c_double(rtol), ct.c_double(atol), int(cap), _p(t_out), _p(y_out),
+                               _p(y_event), res, int(nthreads))
+    rec = np.frombuffer(res, dtype=np.dtype([(k, np.int32) for k in
+                                             "success message nfev nt_out event_found ind_event idid "
+                                             "nstep naccpt nrejct rows_needed pad_".split()] +
+                                            [("t_event", np.float64)])).copy()
+    return dict(result=rec, y=y_out, t=t_out, y_event=y_event)
