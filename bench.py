@@ -49,14 +49,24 @@ WORKLOADS = {
                               t_eval=(0.0, 10.0, 100), rtol=1e-6, atol=1e-8, mxstep=10000,
                               batch=100000, config="BASELINE.json configs[3] (SURVEY 8d C4): "
                               "1-D Brusselator on 32 cells, warp per trajectory"),
+    # the reference's third entry point on the C2 sweep, with the terminal
+    # event z = 50 (45 % of the trajectories stop in the first transient, the others run to
+    # t = 100: the persistent work queue is what keeps the lanes busy)
+    "lorenz_solve_ivp": dict(solver="solve_ivp", rhs="lorenz", n=3, p=4, u0=[1.0, 0.0, 0.0],
+                             t_eval=(0.0, 100.0, 1001), rtol=1e-8, atol=1e-8, mxstep=100000,
+                             events="lorenz_z", level=50.0, batch=1 << 20,
+                             config="SURVEY 8f rank 2: solve_ivp (DOP853, dense output every step, "
+                                    "terminal event by Brent) on the sweep of BASELINE.json configs[1]"),
 }
 
 
 MIXED = ["lorenz_dop853", "robertson_lsoda"]  # BASELINE.json configs[4]
 
 
-def sweep(name, B, seed):
+def sweep(name, B, seed, level=None):
     import _problems as pr
+    if level is not None:  # solve_ivp: the event level as a 4th parameter
+        return np.ascontiguousarray(np.column_stack([pr.lorenz_sweep(B, seed), np.full(B, level)]))
     if name == "lorenz":
         return pr.lorenz_sweep(B, seed)
     if name == "brusselator1d":
@@ -96,6 +106,18 @@ def lsoda_flops(cnt, n, f_rhs, nt):
     per_fe = f_rhs + 2 * n * n + 8 * n + 10
     per_je = (2 * n * n + 4 * n) + (2 * n * n + n) + n + (2.0 / 3.0) * n ** 3 + 0.5 * n * n
     fl = nst * per_step + nfe * per_fe + nje * per_je + rows * (n * (3 * nq + 1) + 2)
+    return float(fl.sum())
+
+
+def ivp_flops(res, n, f_rhs, f_ev):
+    """solve_ivp = dp86co with iout = 2: every accepted step prepares dense output (the "event
+    step" term of SURVEY.md 8(d)) and evaluates the events function; per output row 14n + 3.
+    res = [B,12] (include/b200ode.h)."""
+    nstep = res[:, 8].astype(np.float64)
+    naccpt = res[:, 9].astype(np.float64)
+    rows = res[:, 3].astype(np.float64)
+    fl = nstep * (157 * n + 37 + 11 * f_rhs) + naccpt * (f_rhs + 153 * n + 6 + 3 * f_rhs + f_ev) + \
+        rows * (14 * n + 3) + (2 * f_rhs + 12 * n)
     return float(fl.sum())
 
 
@@ -220,18 +242,22 @@ def cpu_arm(wl, budget_s, seed=0):
                     os.close(fd)
             return time.perf_counter() - t0
         t0 = time.perf_counter()
-        orc.solve_batch(wl["solver"], f, u0, te, P, wl["rtol"], wl["atol"], wl["mxstep"])
+        if wl["solver"] == "solve_ivp":
+            orc.solve_ivp_batch(f, [te[0], te[-1]], u0, te, 1, orc.builtin_rhs("events_" + wl["events"]),
+                                P, rtol=wl["rtol"], atol=wl["atol"])
+        else:
+            orc.solve_batch(wl["solver"], f, u0, te, P, wl["rtol"], wl["atol"], wl["mxstep"])
         return time.perf_counter() - t0
 
-    probe = sweep(wl["rhs"], 4 * cores, seed)
+    probe = sweep(wl["rhs"], 4 * cores, seed, wl.get("level"))
     t = run(probe)
     per = max(t / len(probe), 1e-7)
     B = int(min(wl["batch"], max(8 * cores, budget_s / per)))
-    P = sweep(wl["rhs"], B, seed)
+    P = sweep(wl["rhs"], B, seed, wl.get("level"))
     t = run(P)
     kind = "reference" if use_ref else "port"
     what = ("oracle/_ref (unmodified reference LSODA.cpp + wrapper.cpp, g++ -O3)" if use_ref else
-            "oracle port (C restatement; the reference's DOP853 is Fortran, no compiler here)")
+            "oracle port (C restatement; the reference's DOP853 / solve_ivp are Fortran, no compiler here)")
     sample = "%d trajectories of the same sweep (seed %d), %s, %d threads" % (B, seed, what, cores)
     return B / t, cores, kind, sample, t
 
@@ -353,9 +379,14 @@ def bench_one(a, workload, ranks, rank, world, local):
     dev = torch.device("cuda", local)
 
     B, n, nt = wl["batch"], wl["n"], wl["t_eval"][2]
-    solver = _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
-    h = nb.get_handle(nb.builtin(wl["rhs"]), solver, n, strict=a.strict, exact_ctrl=a.exact_ctrl)
-    Ph = sweep(wl["rhs"], B, seed=rank)  # every rank integrates its own shard of the sweep
+    ivp = wl["solver"] == "solve_ivp"
+    solver = _lib.SOLVE_IVP if ivp else _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
+    if ivp:
+        from numbalsoda_b200 import rhs as _rhs
+        h = _rhs.get_ivp_handle(nb.builtin(wl["rhs"]), n, 1, nb.builtin(wl["events"]), strict=a.strict)
+    else:
+        h = nb.get_handle(nb.builtin(wl["rhs"]), solver, n, strict=a.strict, exact_ctrl=a.exact_ctrl)
+    Ph = sweep(wl["rhs"], B, rank, wl.get("level"))  # every rank integrates its own shard of the sweep
     teh = np.linspace(*wl["t_eval"][:2], nt)
     P = torch.tensor(Ph, device=dev)
     u0 = torch.tensor(initial_state(wl), dtype=torch.float64, device=dev)
@@ -365,8 +396,23 @@ def bench_one(a, workload, ranks, rank, world, local):
     cnt = torch.zeros((B, 8), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    if ivp:
+        span = torch.tensor([teh[0], teh[-1]], dtype=torch.float64, device=dev)
+        res = torch.zeros((B, _lib.IVP_NRESULT), dtype=torch.int32, device=dev)
+        t_event = torch.zeros(B, dtype=torch.float64, device=dev)
+        y_event = torch.zeros((B, n), dtype=torch.float64, device=dev)
+        pb = _lib.IvpProblem()
+        pb.size = ct.sizeof(_lib.IvpProblem)
+        pb.B, pb.neq, pb.nt, pb.np, pb.n_events = B, n, nt, wl["p"], 1
+        pb.t_span, pb.t_span_stride, pb.y0, pb.y0_stride = span.data_ptr(), 0, u0.data_ptr(), 0
+        pb.data, pb.data_stride, pb.teval = P.data_ptr(), wl["p"] * 8, te.data_ptr()
+        pb.rtol, pb.atol, pb.y_out = wl["rtol"], wl["atol"], usol.data_ptr()
+        pb.result, pb.t_event, pb.y_event = res.data_ptr(), t_event.data_ptr(), y_event.data_ptr()
 
     def step():
+        if ivp:
+            _lib.check(_lib.lib.b200ode_solve_ivp_device(h.ptr, ct.byref(pb), ct.c_void_p(stream.cuda_stream)))
+            return
         args = [h.ptr, B, n, u0.data_ptr(), 0, P.data_ptr(), wl["p"] * 8, wl["p"], nt,
                 te.data_ptr(), usol.data_ptr(), wl["rtol"], wl["atol"], wl["mxstep"],
                 ok.data_ptr(), cnt.data_ptr()]
@@ -406,7 +452,7 @@ def bench_one(a, workload, ranks, rank, world, local):
     ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     dev_s = sum(ms) / 1e3
     dev_s_max = ranks.max(dev_s)  # every multi-GPU time is the slowest rank's
-    n_ok = int(ranks.sum(int((ok == 1).sum().item())))
+    n_ok = int(ranks.sum(int(((res[:, 0] if ivp else ok) == 1).sum().item())))
     value = world * B * a.steps / dev_s_max
 
     # ---- end to end: the call a user makes -- numbalsoda_b200.lsoda / dop853 with host
@@ -426,7 +472,15 @@ def bench_one(a, workload, ranks, rank, world, local):
         api = nb.dop853 if solver == _lib.DOP853 else nb.lsoda
         rhs = nb.builtin(wl["rhs"])
 
+        def e2e_step_ivp():
+            sol = nb.solve_ivp(rhs, np.array([teh[0], teh[-1]]), u0h, teh, n_events=1,
+                               event_fcn=nb.builtin(wl["events"]), data=Pe, rtol=wl["rtol"],
+                               atol=wl["atol"], strict=a.strict, device=local, out=out)
+            return int(sol.success.sum())
+
         def e2e_step():
+            if ivp:
+                return e2e_step_ivp()
             us, okh = api(rhs, u0h, teh, Pe, wl["rtol"], wl["atol"], wl["mxstep"],
                           strict=a.strict, exact_ctrl=a.exact_ctrl, device=local, out=out)
             return int(okh.sum())  # the host reads the step's result
@@ -442,28 +496,39 @@ def bench_one(a, workload, ranks, rank, world, local):
         te2e = ranks.max(time.perf_counter() - t0)
         e2e = {"value": world * Be * ke / te2e, "unit": "traj/s",
                "h2d_bytes_per_step": int(Pe.nbytes + teh.nbytes + u0h.nbytes),
-               "d2h_bytes_per_step": int(Be * nt * n * 8 + Be * 4),
+               "d2h_bytes_per_step": int(Be * nt * n * 8 + Be * (4 if not ivp else 48 + 8 + 8 * n)),
                "trajectories_per_gpu": Be,
                "steps": ke, "ms_per_step": 1e3 * te2e / ke, "success_fraction": n_ok_e2e / Be,
-               "api": "numbalsoda_b200.%s(rhs, u0, t_eval, data[B,p], rtol, atol, out=pinned) "
+               "api": ("numbalsoda_b200.solve_ivp(rhs, t_span, y0, t_eval, n_events=1, event_fcn, "
+                       "data[B,p], rtol, atol, out=pinned) -> ODEResultBatch on the host") if ivp else
+                      "numbalsoda_b200.%s(rhs, u0, t_eval, data[B,p], rtol, atol, out=pinned) "
                       "-> (usol[B,nt,n], success[B]) on the host" % wl["solver"]}
         del out
 
     if rank != 0:
         return None
 
-    cnt_h = cnt.cpu().numpy()
-    flops = (dop853_flops if wl["solver"] == "dop853" else lsoda_flops)(cnt_h, n, F_RHS[wl["rhs"]], nt)
+    if ivp:
+        res_h = res.cpu().numpy()
+        flops = ivp_flops(res_h, n, F_RHS[wl["rhs"]], 1)
+        cnt_h = res_h[:, 8:9]  # nstep
+        rows_h = float(res_h[:, 3].mean())
+    else:
+        cnt_h = cnt.cpu().numpy()
+        flops = (dop853_flops if wl["solver"] == "dop853" else lsoda_flops)(cnt_h, n, F_RHS[wl["rhs"]], nt)
     per_launch_s = dev_s / a.steps
     achieved_tf = flops / per_launch_s / 1e12
     peaks = measured_peaks()
     out_bytes = B * (nt * n * 8 + (n + wl["p"]) * 8 + 4)
+    if ivp:  # rows actually written (an event trims the rest), the result record, the event
+        out_bytes = int(B * (rows_h * n * 8 + wl["p"] * 8 + 48 + 8 + 8 * n))
     tr = NCU_TRAFFIC.get(workload)
     roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf if peak_tf else None,
             "traffic": (tr[0] / tr[2] * B) if tr else None,
             "traffic_source": ("ncu dram bytes per trajectory x B, %s" % tr[1]) if tr else None,
-            "kernel": "b200ode_%s_kernel" % (wl["solver"] + ("w" if wl["n"] > 8 else "")),
+            "kernel": "b200ode_ivp_kernel" if ivp else
+                      "b200ode_%s_kernel" % (wl["solver"] + ("w" if wl["n"] > 8 else "")),
             "flops_per_launch": flops, "flops_per_trajectory": flops / B,
             "flop_count": "algorithmic, SURVEY.md 8(d) formulas x per-trajectory counters",
             "peak_source": peak_src,
@@ -476,7 +541,8 @@ def bench_one(a, workload, ranks, rank, world, local):
     line = {"metric": "trajectories/s", "value": value, "unit": "traj/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s_max / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": cfg, "mode": "strict" if a.strict else ("FMA, exact controller" if a.exact_ctrl else "fast (FMA, fast controller)"),
+            "data": "synthetic", "config": cfg,
+            "mode": "strict" if a.strict else ("FMA, exact controller" if (a.exact_ctrl or ivp) else "fast (FMA, fast controller)"),
             "success_fraction": n_ok / (B * world), "wall_s_timed_region": t_wall,
             "mean_steps_per_trajectory": float(cnt_h[:, 0].mean()),
             "roofline": roof, "clocks": clocks, "gpu_launches": launches,
@@ -487,6 +553,9 @@ def bench_one(a, workload, ranks, rank, world, local):
         v, cores, kind, sample, secs = cpu_arm(wl, 12.0)
         line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": kind,
                                 "sample": sample, "seconds": secs}
+    if ivp:
+        line["event_fraction"] = float(res_h[:, 5].mean())
+        line["mean_rows_per_trajectory"] = rows_h
     del usol, cnt, ok, flush
     torch.cuda.empty_cache()
     return line

@@ -144,7 +144,7 @@ def _run(handle, devices, B, n, ts, y0, dbuf, batched_data, rec, nps, te, n_even
 
 def solve_ivp(funcptr, t_span, y0, t_eval=np.array([], np.double), method="DOP853", n_events=0,
               event_fcn=0, data=0, first_step=0.0, max_step=0.0, rtol=1.0e-3, atol=1.0e-6, *,
-              strict=False, device=None, max_rows=None):
+              strict=False, device=None, max_rows=None, out=None):
     """Solve initial value problems with the DOP853 solve_ivp kernel on the GPU.
 
     Arguments as the reference's solve_ivp (driver_solve_ivp.py:86-127).  funcptr / event_fcn:
@@ -152,7 +152,9 @@ def solve_ivp(funcptr, t_span, y0, t_eval=np.array([], np.double), method="DOP85
     numbalsoda_b200.builtin(name).  data: a float64 array [p] or [B,p] or a record array (the
     reference takes a raw address, which cannot be followed from the device), 0 / None = none.
     Keyword-only: strict (FMA contraction off: bit-for-bit the CPU arithmetic), device (index,
-    list or "all"), max_rows (see the module docstring), rtol / atol may have shape [B]."""
+    list or "all"), max_rows (see the module docstring), out (with t_eval: a preallocated
+    C-contiguous float64 buffer of B*nt*n elements for the rows, e.g. from
+    numbalsoda_b200.pinned_empty, to reuse across calls); rtol / atol may have shape [B]."""
     t_span = _as_f64(t_span, "t_span")
     y0 = _as_f64(y0, "y0")
     if t_span.shape[-1:] != (2,) or t_span.ndim not in (1, 2):
@@ -203,7 +205,13 @@ def solve_ivp(funcptr, t_span, y0, t_eval=np.array([], np.double), method="DOP85
               float(first_step), float(max_step), float(rtol), float(atol), rtol_b, atol_b)
     row_offset = t_out = None
     if te is not None:
-        y_out = np.empty((B, te.shape[0], n))
+        if out is not None:
+            if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != B * te.shape[0] * n:
+                raise ValueError("out must be a C-contiguous float64 array of %d elements"
+                                 % (B * te.shape[0] * n))
+            y_out = out.reshape(B, te.shape[0], n)
+        else:
+            y_out = np.empty((B, te.shape[0], n))
         _run(*common, 0, None, None, y_out, result, t_event, y_event)
     elif max_rows is not None:
         cap = int(max_rows)

@@ -122,7 +122,7 @@ def test_lorenz_event_sweep_strict_bitwise(mode):
     B = 1500
     ts, y0, data = _lorenz_ensemble(B)
     te = np.linspace(0.0, 6.0, 61) if mode == "t_eval" else None
-    cap = 400 if mode == "max_rows" else 4000
+    cap = 40 if mode == "max_rows" else 4000
     got = nb.solve_ivp(nb.builtin("lorenz"), ts, y0, te, n_events=1, event_fcn=nb.builtin("lorenz_z"),
                        data=data, rtol=1e-7, atol=1e-9, strict=True,
                        max_rows=cap if mode == "max_rows" else None)
