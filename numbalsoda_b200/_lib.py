@@ -4,7 +4,9 @@ import ctypes as ct
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libb200ode.so")
+# B200ODE_LIB: load another build of the library (tools/sweep_ivp.sh times kernel variants
+# built ahead with different launch bounds)
+LIBPATH = os.environ.get("B200ODE_LIB") or os.path.join(HERE, "libb200ode.so")
 
 DOP853, LSODA, SOLVE_IVP = 0, 1, 2
 IMG_LTOIR, IMG_PTX, IMG_FATBIN, IMG_BUILTIN = 0, 1, 2, 3
