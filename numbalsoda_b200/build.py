@@ -122,6 +122,12 @@ def build(force=False, verbose=False):
     if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
         _run([NVCC] + ARCH + NVCC_FLAGS + ["-o", out, srcp])
     images.append(("dop853w", out))
+    # solve_ivp, one warp per trajectory
+    srcp = os.path.join(CSRC, "solve_ivp_warp_kernel.cu")
+    out = os.path.join(OBJ, "ivpw.fatbin")
+    if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
+        _run([NVCC] + ARCH + NVCC_FLAGS + ["-o", out, srcp])
+    images.append(("ivpw", out))
     srcp = os.path.join(CSRC, "rhs_builtin.cu")
     for r in BUILTIN_RHS:
         out = os.path.join(OBJ, "rhs_%s.fatbin" % r)

@@ -164,7 +164,8 @@ static bool warp_kernel(int solver, int neq)
 }
 static const char* kernel_name(int solver, int neq)
 {
-    if (solver == B200ODE_SOLVE_IVP) return "b200ode_ivp_kernel";
+    if (solver == B200ODE_SOLVE_IVP)
+        return warp_kernel(solver, neq) ? "b200ode_ivpw_kernel" : "b200ode_ivp_kernel";
     if (solver == B200ODE_DOP853)
         return warp_kernel(solver, neq) ? "b200ode_dop853w_kernel" : "b200ode_dop853_kernel";
     return warp_kernel(solver, neq) ? "b200ode_lsodaw_kernel" : "b200ode_lsoda_kernel";
@@ -299,15 +300,16 @@ extern "C" int b200ode_link_ivp(int neq, const void* rhs_image, size_t rhs_size,
     if (!out) return fail(B200ODE_EINVAL, "out is NULL");
     *out = nullptr;
     if (neq < 1) return fail(B200ODE_EINVAL, "neq = %d", neq);
-    if (neq > B200ODE_THREAD_NMAX)
-        return fail(B200ODE_ENOSYS, "solve_ivp: neq = %d exceeds %d", neq, B200ODE_THREAD_NMAX);
+    if (neq > B200ODE_WARP_NMAX)
+        return fail(B200ODE_ENOSYS, "solve_ivp: neq = %d exceeds %d", neq, B200ODE_WARP_NMAX);
     if (n_events < 0 || n_events > B200ODE_IVP_NEVMAX)
         return fail(n_events < 0 ? B200ODE_EINVAL : B200ODE_ENOSYS,
                     "solve_ivp: n_events = %d (at most %d)", n_events, B200ODE_IVP_NEVMAX);
     if (n_events > 0 && !events_image)
         return fail(B200ODE_EINVAL, "n_events = %d but the events image is NULL", n_events);
     char name[64];
-    snprintf(name, sizeof name, "ivp_n%d", neq);
+    if (warp_kernel(B200ODE_SOLVE_IVP, neq)) snprintf(name, sizeof name, "ivpw");
+    else snprintf(name, sizeof name, "ivp_n%d", neq);
     UserImage rhs, ev;
     int rc = resolve_image(rhs_image, rhs_size, rhs_kind, "rhs_", "right-hand side", &rhs);
     if (rc) return rc;
@@ -380,7 +382,10 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
         CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
         CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
-        if (warp && H->solver == B200ODE_DOP853) {
+        if (warp && H->solver == B200ODE_SOLVE_IVP) {
+            P.threads = 32;
+            P.dyn_smem = B200ODE_IVPW_DOUBLES(H->neq) * (int)sizeof(double);
+        } else if (warp && H->solver == B200ODE_DOP853) {
             P.threads = 32;
             P.dyn_smem = B200ODE_DOP853W_DOUBLES(H->neq) * (int)sizeof(double);
         } else if (warp) {
@@ -911,11 +916,13 @@ static int launch_ivp(b200ode_rhs_t H, PerDevice* P, B200IvpLaunch args, CUstrea
     CUdeviceptr next = P->next + slot * sizeof(unsigned long long);
     CU(cuMemsetD8Async(next, 0, sizeof(unsigned long long), stream));
     args.next = reinterpret_cast<unsigned long long*>(next);
-    const long long want = (args.B + P->threads - 1) / P->threads;
+    const bool warp = warp_kernel(H->solver, H->neq);
+    const long long want = warp ? args.B : (args.B + P->threads - 1) / P->threads;
     const long long resident = (long long)P->sms * P->blocks_per_sm;
     const int grid = (int)std::min(want, resident);
-    CUfunction fn = args.np >= 0 ? P->fn : P->fn_ptr;
-    void* params[] = {&args};
+    CUfunction fn = (args.np >= 0 && !warp) ? P->fn : P->fn_ptr;
+    int neq = H->neq;
+    void* params[] = {&args, &neq};  // (the thread kernels take the first only)
     CU(cuLaunchKernel(fn, grid, 1, 1, P->threads, 1, 1, (unsigned)P->dyn_smem, stream, params, nullptr));
     H->last_grid = grid;
     H->launches++;
@@ -1009,7 +1016,8 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
             }
             b1 = std::max(b1, lo);
             // a few chunks even when everything fits, so that copies overlap kernels
-            const long long resident = (long long)P->sms * P->blocks_per_sm * P->threads;
+            const long long resident = (long long)P->sms * P->blocks_per_sm *
+                                       (warp_kernel(H->solver, H->neq) ? 1 : P->threads);
             long long want = std::max<long long>(4 * resident, (B + 7) / 8);
             if (const char* e = getenv("B200ODE_IVP_CHUNK"))  // tests: force many small chunks
                 want = std::max<long long>(1, atoll(e));

@@ -57,6 +57,9 @@ typedef struct B200OdeLaunch {
 #define B200ODE_IVP_NRESULT 12 /* ints per trajectory in the result array (include/b200ode.h) */
 /* per thread: 8 n dense-output coefficients + the previous event values */
 #define B200ODE_IVP_DOUBLES(n) (8 * (n) + B200ODE_IVP_NEVMAX)
+/* warp per trajectory (solve_ivp_warp.cuh): 12 stage vectors, 8 n coefficients, 2 n norm terms,
+ * one interpolated state, three event vectors */
+#define B200ODE_IVPW_DOUBLES(n) (23 * (n) + 3 * B200ODE_IVP_NEVMAX)
 /* message codes = which of the reference's strings (dop853_solve_ivp.f90:273,:300,:351,:364,:390) */
 #define B200ODE_IVP_MSG_END 0
 #define B200ODE_IVP_MSG_EVENT 1

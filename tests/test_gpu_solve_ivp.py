@@ -294,3 +294,62 @@ def test_full_size_properties():
     for j, bb in enumerate(idx):
         k = min(rr["nt_out"][j], np.searchsorted(te, ts[bb, 1], side="right"))
         assert np.array_equal(a.y[bb, :k], ref["y"][j, :k])
+
+
+def ev_brus(t, u, out, p):
+    out[0] = u[5] - 1.0
+    out[1] = u[40] - 3.0
+
+
+@pytest.mark.parametrize("mode", ["t_eval", "two_pass"])
+def test_warp_kernel_n64_strict_bitwise(mode):
+    """Systems of more than 8 equations run one trajectory per warp (solve_ivp_warp.cuh): the
+    n = 64 Brusselator with two events, numba-compiled right-hand side and events function."""
+    import numba
+    nb = _nb()
+    B = 40
+    P = pr.brusselator_sweep(B)
+    y0 = pr.brusselator_u0()
+    rhs = numba.cfunc(nb.lsoda_sig)(pr.brusselator_rhs)
+    ev = numba.cfunc(nb.lsoda_sig)(ev_brus)
+    te = np.linspace(0.0, 2.0, 21) if mode == "t_eval" else None
+    got = nb.solve_ivp(rhs.address, np.array([0.0, 2.0]), y0, te, n_events=2, event_fcn=ev.address,
+                       data=P, rtol=1e-6, atol=1e-8, strict=True)
+    ref = orc.solve_ivp_batch(rhs.address, [0.0, 2.0], y0, te, 2, ev.address, P, rtol=1e-6, atol=1e-8,
+                              cap=6000)
+    rr = ref["result"]
+    assert set(rr["ind_event"][rr["event_found"] == 1]) == {0, 1}
+    for k, f in (("message_code", "message"), ("nfev", "nfev"), ("nt_out", "nt_out"),
+                 ("ind_event", "ind_event"), ("idid", "idid"), ("nstep", "nstep"), ("naccpt", "naccpt"),
+                 ("nrejct", "nrejct"), ("rows_needed", "rows_needed")):
+        assert np.array_equal(getattr(got, k), rr[f]), k
+    assert np.array_equal(got.t_event, rr["t_event"]) and np.array_equal(got.y_event, ref["y_event"])
+    for b in range(B):
+        k = rr["nt_out"][b]
+        r = got[b]
+        assert len(r.t) == k
+        if te is not None and rr["idid"][b] < 0:
+            continue  # a failed trajectory's rows beyond the failure are uninitialised
+        assert np.array_equal(r.y, ref["y"][b, :k]), b
+        if te is None:
+            assert np.array_equal(r.t, ref["t"][b, :k]), b
+
+
+def test_warp_kernel_n12_fast_mode_and_failures():
+    nb = _nb()
+    B = 64
+    rng = np.random.default_rng(2)
+    P = np.column_stack([rng.uniform(0.5, 2.0, B), np.full(B, 12.0)])
+    y0 = np.ones(12)
+    te = np.linspace(0.0, 1.0, 11)
+    import numba
+    cf = numba.cfunc(nb.lsoda_sig)(pr.chain_rhs)
+    got = nb.solve_ivp(cf.address, np.array([0.0, 1.0]), y0, te, data=P, rtol=1e-7, atol=1e-9)
+    ref = orc.solve_ivp_batch(cf.address, [0.0, 1.0], y0, te, data=P, rtol=1e-7, atol=1e-9)
+    assert got.success.all() and (ref["result"]["success"] == 1).all()
+    assert (np.abs(got.y - ref["y"]) / (np.abs(ref["y"]) + 1.0)).max() <= 10 * 1e-7
+    # decreasing t_eval against an increasing span: the reference's message
+    bad = nb.solve_ivp(cf.address, np.array([0.0, 1.0]), y0, te[::-1].copy(), data=P[:3])
+    assert not bad.success.any() and "does not always increase" in bad[0].message
+    with pytest.raises(nb.B200OdeError, match="exceeds 128"):
+        nb.solve_ivp(cf.address, np.array([0.0, 1.0]), np.ones(129), te, data=P[:3])

@@ -1,6 +1,6 @@
-"""The thread-per-trajectory solve_ivp core (numbalsoda_b200/csrc/solve_ivp_core.cuh: DOP853
-with dense output after every step, terminal events by Brent's method) compiled as host C++
-against the CPU oracle (oracle/solve_ivp_oracle.c, pinned by the reference's notebook outputs):
+"""The solve_ivp cores -- thread per trajectory (numbalsoda_b200/csrc/solve_ivp_core.cuh, n <= 8) and
+warp per trajectory (solve_ivp_warp.cuh, one emulated lane): DOP853 with dense output after every
+step, terminal events by Brent's method -- compiled as host C++ against the CPU oracle (oracle/solve_ivp_oracle.c, pinned by the reference's notebook outputs):
 every field of the reference's ODEResult bit for bit."""
 import ctypes as ct
 import os
@@ -16,9 +16,9 @@ from numba import cfunc, types  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "solve_ivp_core_host.cpp")
 HDRS = [os.path.join(ROOT, "numbalsoda_b200", "csrc", f)
-        for f in ("solve_ivp_core.cuh", "b200ode_launch.h", "dop853_tableau.cuh", "b200ode_pow.cuh")]
+        for f in ("solve_ivp_core.cuh", "solve_ivp_warp.cuh", "b200ode_warp.cuh", "b200ode_launch.h",
+                  "dop853_tableau.cuh", "b200ode_pow.cuh")]
 NRESULT = 12
 
 
@@ -34,14 +34,27 @@ class IvpLaunch(ct.Structure):  # B200IvpLaunch, numbalsoda_b200/csrc/b200ode_la
                 ("next", ct.c_void_p)]
 
 
-@pytest.fixture(scope="module")
-def lib():
+def _compile(stem):
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
-    so = os.path.join(HERE, "_build", "libsolve_ivp_core_host.so")
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in [SRC] + HDRS):
+    src = os.path.join(HERE, stem + ".cpp")
+    so = os.path.join(HERE, "_build", "lib%s.so" % stem)
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in [src] + HDRS):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared",
-                               "-Wno-unknown-pragmas", "-o", so, SRC])
+                               "-Wno-unknown-pragmas", "-o", so, src])
     return ct.CDLL(so)
+
+
+class _Core:
+    def __init__(self, fn):
+        self.solve_ivp_core_host = fn
+
+
+@pytest.fixture(scope="module", params=["thread", "warp"])
+def lib(request):
+    """Both cores behind one entry-point name (same B200IvpLaunch contract)."""
+    if request.param == "thread":
+        return _Core(_compile("solve_ivp_core_host").solve_ivp_core_host)
+    return _Core(_compile("solve_ivp_warp_host").solve_ivp_warp_host)
 
 
 def run(lib, f, t_span, y0, t_eval=None, n_events=0, events=0, data=None, first_step=0.0,
@@ -186,3 +199,60 @@ def test_stiffness_abort_and_step_limit(lib):
         got = run(lib, stiff.address, span, y0, data=np.array([lam]), rtol=1e-3, cap=200000)[0]
         assert ref["idid"] == -4 and not ref["success"] and ref["nfev"] == 0
         same(got, ref)
+
+
+def test_ragged_rows(lib):
+    """row_offset[B+1]: exactly sized rows after a counting pass with cap = 0."""
+    rng = np.random.default_rng(8)
+    B = 12
+    data = np.column_stack([rng.uniform(9, 11, B), rng.uniform(20, 36, B), rng.uniform(2, 3.33, B)])
+    ts = np.column_stack([np.zeros(B), rng.uniform(0.3, 3.0, B)])
+    y0 = np.array([1.0, 0.0, 0.0])
+    need = np.array([orc.solve_ivp(lorenz.address, ts[b], y0, data=data[b], rtol=1e-7)["rows_needed"]
+                     for b in range(B)])
+    off = np.zeros(B + 1, np.int64)
+    np.cumsum(need, out=off[1:])
+    R, n = int(off[-1]), 3
+    t_out, y_out = np.full(R, np.nan), np.full((R, n), np.nan)
+    res = np.zeros((B, NRESULT), np.int32)
+    t_event, y_event = np.zeros(B), np.zeros((B, n))
+    p = lambda a: a.ctypes.data  # noqa: E731
+    L = IvpLaunch(B=B, t_span=p(ts), t_span_stride=2, y0=p(y0), y0_stride=0, data=p(data), data_stride=24,
+                  np=-1, nt=0, t_eval=None, n_events=0, cap=0, row_offset=p(off), first_step=0.0,
+                  max_step=0.0, rtol=1e-7, atol=1e-6, rtol_b=None, atol_b=None, t_out=p(t_out),
+                  y_out=p(y_out), result=p(res), t_event=p(t_event), y_event=p(y_event), next=None)
+    assert lib.solve_ivp_core_host(ct.c_void_p(lorenz.address), None, n, ct.byref(L)) == 0
+    assert np.array_equal(res[:, 3], need) and res[:, 0].all() and not np.isnan(y_out).any()
+    for b in range(B):
+        ref = orc.solve_ivp(lorenz.address, ts[b], y0, data=data[b], rtol=1e-7)
+        assert np.array_equal(t_out[off[b]:off[b + 1]], ref["t"])
+        assert np.array_equal(y_out[off[b]:off[b + 1]], ref["y"])
+
+
+def test_brusselator_n64_with_event():
+    """The warp core at a size the thread core does not cover."""
+    warp = _compile("solve_ivp_warp_host").solve_ivp_warp_host
+    import _problems as pr
+    f = orc.builtin_rhs("brusselator1d")
+    y0 = pr.brusselator_u0()
+    P = pr.brusselator_sweep(3)
+
+    @cfunc(SIG)
+    def ev(t, u, out, p):
+        out[0] = u[5] - 1.0    # crossed downwards by the third parameter set
+        out[1] = u[40] - 3.0   # crossed downwards by the first
+
+    seen = set()
+    for te in (None, np.linspace(0.0, 2.0, 21)):
+        for b in range(3):
+            ref = orc.solve_ivp(f, [0.0, 2.0], y0, te, 2, ev.address, P[b], rtol=1e-6, atol=1e-8, cap=5000)
+            got = run(_Core(warp), f, [0.0, 2.0], y0, te, 2, ev.address, P[b], rtol=1e-6, atol=1e-8,
+                      cap=5000)[0]
+            same(got, ref)
+            seen.add((ref["idid"], ref["ind_event"] if ref["event_found"] else -1))
+    assert seen == {(2, 0), (2, 1)}, seen  # both events were exercised
+    # ... and the stiffness abort (idid = -4: iprint = 0, module :642-650) without events
+    ref = orc.solve_ivp(f, [0.0, 2.0], y0, None, data=P[1], rtol=1e-6, atol=1e-8, cap=5000)
+    got = run(_Core(warp), f, [0.0, 2.0], y0, None, data=P[1], rtol=1e-6, atol=1e-8, cap=5000)[0]
+    same(got, ref)
+    assert ref["idid"] == -4 and not ref["success"] and ref["nstep"] > 1000
