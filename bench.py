@@ -383,7 +383,8 @@ def bench_one(a, workload, ranks, rank, world, local):
     solver = _lib.SOLVE_IVP if ivp else _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
     if ivp:
         from numbalsoda_b200 import rhs as _rhs
-        h = _rhs.get_ivp_handle(nb.builtin(wl["rhs"]), n, 1, nb.builtin(wl["events"]), strict=a.strict)
+        h = _rhs.get_ivp_handle(nb.builtin(wl["rhs"]), n, 1, nb.builtin(wl["events"]), strict=a.strict,
+                                exact_ctrl=a.exact_ctrl)
     else:
         h = nb.get_handle(nb.builtin(wl["rhs"]), solver, n, strict=a.strict, exact_ctrl=a.exact_ctrl)
     Ph = sweep(wl["rhs"], B, rank, wl.get("level"))  # every rank integrates its own shard of the sweep
@@ -475,7 +476,8 @@ def bench_one(a, workload, ranks, rank, world, local):
         def e2e_step_ivp():
             sol = nb.solve_ivp(rhs, np.array([teh[0], teh[-1]]), u0h, teh, n_events=1,
                                event_fcn=nb.builtin(wl["events"]), data=Pe, rtol=wl["rtol"],
-                               atol=wl["atol"], strict=a.strict, device=local, out=out)
+                               atol=wl["atol"], strict=a.strict, exact_ctrl=a.exact_ctrl, device=local,
+                               out=out)
             return int(sol.success.sum())
 
         def e2e_step():
@@ -542,7 +544,7 @@ def bench_one(a, workload, ranks, rank, world, local):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s_max / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg,
-            "mode": "strict" if a.strict else ("FMA, exact controller" if (a.exact_ctrl or ivp) else "fast (FMA, fast controller)"),
+            "mode": "strict" if a.strict else ("FMA, exact controller" if a.exact_ctrl else "fast (FMA, fast controller)"),
             "success_fraction": n_ok / (B * world), "wall_s_timed_region": t_wall,
             "mean_steps_per_trajectory": float(cnt_h[:, 0].mean()),
             "roofline": roof, "clocks": clocks, "gpu_launches": launches,

@@ -29,15 +29,24 @@
 
 #include "b200ode_launch.h"
 #include "b200ode_pow.cuh"
+#include "b200ode_fastmath.cuh"
 #include "dop853_tableau.cuh"
 
 #if defined(__CUDACC__)
 #define IVP_FN __device__ __forceinline__
 #define IVP_SLOW __device__ __noinline__
+// throughput mode (handle linked without B200ODE_STRICT_FP / B200ODE_EXACT_CTRL): the error
+// norm and the step-size controller through reciprocals and a single-precision power, as in
+// dop853_kernel.cu (b200ode_fastmath.cuh); a link-time constant
+#define IVP_FAST_CTRL() B200ODE_FAST_CTRL()
 #else
 #include <cmath>
 #define IVP_FN static inline
 #define IVP_SLOW static
+#ifndef IVP_HOST_FAST
+#define IVP_HOST_FAST 0  // tests: the throughput mode's arithmetic with libm stand-ins
+#endif
+#define IVP_FAST_CTRL() (IVP_HOST_FAST != 0)
 #endif
 
 #define IVP_UROUND 2.220446049250313e-16  // epsilon(1.0d0), dop853_constants.f90:11
@@ -85,7 +94,7 @@ struct IvpShared {
 template <int N>
 IVP_FN void ivp_contd8(const IvpShared& sh, double xold, double hout, double x, double* out)
 {
-    const double s = (x - xold) / hout;
+    const double s = IVP_FAST_CTRL() ? b200_div(x - xold, hout) : (x - xold) / hout;
     const double s1 = 1.0 - s;
     IVP_FOR_N {
         const double conpar = IVP_CONT(4, i) + s * (IVP_CONT(5, i) + s1 * (IVP_CONT(6, i) + s * IVP_CONT(7, i)));
@@ -408,28 +417,50 @@ IVP_FN bool ivp_step(IvpLane<N>& S, const B200IvpLaunch& L, long long b, const I
         k5[i] = y[i] + h * k4[i];
     }
     // error estimation, module :591-616
-    double err = 0.0, err2 = 0.0;
-    IVP_FOR_N {
-        const double sk = S.atol + S.rtol * ivp_max(fabs(y[i]), fabs(k5[i]));
-        double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
-        double qq = erri / sk;
-        err2 = err2 + qq * qq;
-        erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] + DP_ER9 * k9[i] +
-               DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
-        qq = erri / sk;
-        err = err + qq * qq;
+    double err = 0.0, err2 = 0.0, fac11 = 0.0, ifac = 0.0, hnew;
+    if (IVP_FAST_CTRL()) {
+        // the same quantities through reciprocals; err holds the *square* of the reference's
+        // err (the test err <= 1 is unchanged by that), ifac = safe / err**(1/8)
+        IVP_FOR_N {
+            const double isk = b200_rcp(S.atol + S.rtol * ivp_max(fabs(y[i]), fabs(k5[i])));
+            double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
+            double qq = erri * isk;
+            err2 = err2 + qq * qq;
+            erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] + DP_ER9 * k9[i] +
+                   DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
+            qq = erri * isk;
+            err = err + qq * qq;
+        }
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = (h * h) * (err * err) * b200_rcp((double)N * deno);
+        ifac = IVP_SAFE * b200_inv_root16(err);
+        // fac = max(facc2, min(facc1, fac11/safe)); hnew = h/fac   (module :620-623)
+        hnew = h * ivp_min(IVP_FAC2, ivp_max(IVP_FAC1, ifac));
+    } else {
+        IVP_FOR_N {
+            const double sk = S.atol + S.rtol * ivp_max(fabs(y[i]), fabs(k5[i]));
+            double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
+            double qq = erri / sk;
+            err2 = err2 + qq * qq;
+            erri = DP_ER1 * k1[i] + DP_ER6 * k6[i] + DP_ER7 * k7[i] + DP_ER8 * k8[i] + DP_ER9 * k9[i] +
+                   DP_ER10 * k10[i] + DP_ER11 * k2[i] + DP_ER12 * k3[i];
+            qq = erri / sk;
+            err = err + qq * qq;
+        }
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
+        // step size controller, module :618-623 (facold**beta = 1: beta = 0)
+        fac11 = b200ode_pow_eighth(err);
+        double fac = fac11 / 1.0;
+        fac = ivp_max(facc2, ivp_min(facc1, fac / IVP_SAFE));
+        hnew = h / fac;
     }
-    double deno = err + 0.01 * err2;
-    if (deno <= 0.0) deno = 1.0;
-    err = fabs(h) * err * sqrt(1.0 / ((double)N * deno));
-    // step size controller, module :618-623 (facold**beta = 1: beta = 0)
-    const double fac11 = b200ode_pow_eighth(err);
-    double fac = fac11 / 1.0;
-    fac = ivp_max(facc2, ivp_min(facc1, fac / IVP_SAFE));
-    double hnew = h / fac;
     if (!(err <= 1.0)) {
         // ---- rejected, module :724-728
-        hnew = h / ivp_min(facc1, fac11 / IVP_SAFE);
+        if (IVP_FAST_CTRL()) hnew = h * ivp_max(IVP_FAC1, ifac);
+        else hnew = h / ivp_min(facc1, fac11 / IVP_SAFE);
         if (S.naccpt >= 1) S.nrejct++;
         S.flags = (S.flags & IVP_FORWARD) | IVP_REJECT;  // and last = .false.
         S.h = hnew;

@@ -144,14 +144,16 @@ def _run(handle, devices, B, n, ts, y0, dbuf, batched_data, rec, nps, te, n_even
 
 def solve_ivp(funcptr, t_span, y0, t_eval=np.array([], np.double), method="DOP853", n_events=0,
               event_fcn=0, data=0, first_step=0.0, max_step=0.0, rtol=1.0e-3, atol=1.0e-6, *,
-              strict=False, device=None, max_rows=None, out=None):
+              strict=False, exact_ctrl=False, device=None, max_rows=None, out=None):
     """Solve initial value problems with the DOP853 solve_ivp kernel on the GPU.
 
     Arguments as the reference's solve_ivp (driver_solve_ivp.py:86-127).  funcptr / event_fcn:
     address of a numba @cfunc(lsoda_sig), the cfunc, the Python function `f(t, y, out, p)` or
     numbalsoda_b200.builtin(name).  data: a float64 array [p] or [B,p] or a record array (the
     reference takes a raw address, which cannot be followed from the device), 0 / None = none.
-    Keyword-only: strict (FMA contraction off: bit-for-bit the CPU arithmetic), device (index,
+    Keyword-only: strict (FMA contraction off: bit-for-bit the CPU arithmetic), exact_ctrl (FMA
+    contraction on, but the reference's controller arithmetic -- IEEE divisions, libm-exact pow --
+    instead of the default mode's reciprocals and single-precision err**(1/8)), device (index,
     list or "all"), max_rows (see the module docstring), out (with t_eval: a preallocated
     C-contiguous float64 buffer of B*nt*n elements for the rows, e.g. from
     numbalsoda_b200.pinned_empty, to reuse across calls); rtol / atol may have shape [B]."""
@@ -187,7 +189,7 @@ def solve_ivp(funcptr, t_span, y0, t_eval=np.array([], np.double), method="DOP85
     batched = bool(sizes)
     B = sizes[0] if sizes else 1
     n_events = int(n_events)
-    handle = _rhs.get_ivp_handle(funcptr, n, n_events, event_fcn, strict=strict)
+    handle = _rhs.get_ivp_handle(funcptr, n, n_events, event_fcn, strict=strict, exact_ctrl=exact_ctrl)
     rtol_b = atol_b = None
     if np.ndim(rtol) > 0:
         rtol_b, rtol = np.ascontiguousarray(rtol, dtype=np.float64), 0.0

@@ -213,11 +213,11 @@ def _origin(f, what):
     return ("py", f), f
 
 
-def get_ivp_handle(rhs, neq, n_events=0, events=None, strict=False):
+def get_ivp_handle(rhs, neq, n_events=0, events=None, strict=False, exact_ctrl=False):
     """solve_ivp: link the right-hand side and the events function (reference
     numbalsoda/driver_solve_ivp.py:86-88: `funcptr`, `n_events`, `event_fcn`) with the
     solve_ivp kernel, once per combination."""
-    flags = _lib.STRICT_FP if strict else 0
+    flags = _lib.STRICT_FP if strict else (_lib.EXACT_CTRL if exact_ctrl else 0)
     if isinstance(rhs, RhsHandle):
         return rhs
     n_events = int(n_events)

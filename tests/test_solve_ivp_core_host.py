@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 HDRS = [os.path.join(ROOT, "numbalsoda_b200", "csrc", f)
         for f in ("solve_ivp_core.cuh", "solve_ivp_warp.cuh", "b200ode_warp.cuh", "b200ode_launch.h",
-                  "dop853_tableau.cuh", "b200ode_pow.cuh")]
+                  "dop853_tableau.cuh", "b200ode_pow.cuh", "b200ode_fastmath.cuh")]
 NRESULT = 12
 
 
@@ -34,13 +34,15 @@ class IvpLaunch(ct.Structure):  # B200IvpLaunch, numbalsoda_b200/csrc/b200ode_la
                 ("next", ct.c_void_p)]
 
 
-def _compile(stem):
+def _compile(stem, fast=False):
+    """fast: the throughput link mode's arithmetic (b200ode_fastmath.cuh) with libm stand-ins."""
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
     src = os.path.join(HERE, stem + ".cpp")
-    so = os.path.join(HERE, "_build", "lib%s.so" % stem)
+    so = os.path.join(HERE, "_build", "lib%s%s.so" % (stem, "_fast" if fast else ""))
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in [src] + HDRS):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared",
-                               "-Wno-unknown-pragmas", "-o", so, src])
+                               "-Wno-unknown-pragmas"] + (["-DIVP_HOST_FAST=1"] if fast else []) +
+                              ["-o", so, src])
     return ct.CDLL(so)
 
 
@@ -256,3 +258,32 @@ def test_brusselator_n64_with_event():
     got = run(_Core(warp), f, [0.0, 2.0], y0, None, data=P[1], rtol=1e-6, atol=1e-8, cap=5000)[0]
     same(got, ref)
     assert ref["idid"] == -4 and not ref["success"] and ref["nstep"] > 1000
+
+
+def test_throughput_mode_emulation():
+    """The default link mode's controller (reciprocals, single-precision err**(-1/16)) emulated on
+    the host: same event decisions as the oracle, event times to the Brent tolerance, states
+    within 10 rtol (north_star's bound), step counts within a few."""
+    fast = _Core(_compile("solve_ivp_core_host", fast=True).solve_ivp_core_host)
+    rng = np.random.default_rng(11)
+    B = 200
+    data = np.column_stack([rng.uniform(9, 11, B), rng.uniform(20, 36, B), rng.uniform(2, 3.33, B)])
+    y0 = np.column_stack([rng.uniform(0.5, 1.5, B), rng.uniform(-0.5, 0.5, B), rng.uniform(0, 1, B)])
+    ts = np.column_stack([np.zeros(B), rng.uniform(0.3, 2.0, B)])
+    te = np.linspace(0.0, 2.0, 21)
+    rtol = 1e-8
+    got = run(fast, lorenz.address, ts, y0, te, 1, ev_lorenz.address, data, rtol=rtol, atol=rtol)
+    worst = 0.0
+    for b in range(B):
+        ref = orc.solve_ivp(lorenz.address, ts[b], y0[b], te, 1, ev_lorenz.address, data[b], rtol=rtol,
+                            atol=rtol)
+        g = got[b]
+        assert (g["success"], g["event_found"], g["message"]) == (ref["success"], ref["event_found"],
+                                                                  ref["message"])
+        assert len(g["t"]) == len(ref["t"]) and abs(g["nstep"] - ref["nstep"]) <= 3
+        if ref["event_found"]:
+            assert abs(g["t_event"] - ref["t_event"]) < 5e-8
+        k = min(len(ref["t"]), np.searchsorted(te, ts[b, 1], side="right"))
+        if k:
+            worst = max(worst, (np.abs(g["y"][:k] - ref["y"][:k]) / (np.abs(ref["y"][:k]) + 1.0)).max())
+    assert 0.0 < worst <= 10 * rtol, worst

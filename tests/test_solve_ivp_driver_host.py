@@ -29,7 +29,7 @@ def drv(lib, monkeypatch):  # noqa: F811
         def __init__(self, f, ev, n, ne):
             self.f, self.ev, self.n, self.ne, self.ptr = f, ev, n, ne, self
 
-    def get_ivp_handle(rhs, neq, n_events=0, events=None, strict=False):
+    def get_ivp_handle(rhs, neq, n_events=0, events=None, strict=False, exact_ctrl=False):
         if n_events > 0 and (events is None or (isinstance(events, int) and events == 0)):
             raise ValueError("n_events = %d but no event function was given" % n_events)
         return FakeHandle(rhs, events if n_events else 0, neq, n_events)
