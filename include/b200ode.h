@@ -218,7 +218,8 @@ typedef struct b200ode_ivp_problem {
     const double* atol_b;
     /* Output rows.  With t_eval: y_out[B,nt,neq], t_out unused.  Without: trajectory b owns
      * `cap` rows, t_out[B,cap], y_out[B,cap,neq] -- or, with row_offset[B+1], the rows
-     * [row_offset[b], row_offset[b+1]) of t_out[row_offset[B]], y_out[row_offset[B],neq].
+     * [row_offset[b], row_offset[b+1]) of t_out[row_offset[B]], y_out[row_offset[B],neq]
+     * (row_offset[0] need not be 0: a shard passes a slice of the offsets and the same arrays).
      * A trajectory with more accepted steps than rows ends with success = 0, message
      * "output capacity exceeded", its rows filled and ROWS_NEEDED = what it takes: a first
      * pass with cap = 0 (t_out = y_out = NULL) sizes an exact second one. */

@@ -986,10 +986,12 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
         for (long long b = 0; b < B; b++)
             if (p->row_offset[b + 1] < p->row_offset[b] || p->row_offset[b + 1] - p->row_offset[b] > 0x7fffffffLL)
                 return fail(B200ODE_EINVAL, "row_offset must not decrease (trajectory %lld)", b);
-    auto rows_upto = [&](long long b) -> long long {  // rows owned by trajectories [0, b)
-        return nt > 0 ? b * nt : ragged ? p->row_offset[b] - p->row_offset[0] : b * p->cap;
+    // first row of trajectory b in t_out / y_out (ragged: row_offset is used as given, so a
+    // shard of a larger problem passes a slice of the offsets and the unshifted arrays)
+    auto rows_upto = [&](long long b) -> long long {
+        return nt > 0 ? b * nt : ragged ? p->row_offset[b] : b * p->cap;
     };
-    if (rows_upto(B) > 0 && (!p->y_out || (nt == 0 && !p->t_out)))
+    if (rows_upto(B) > rows_upto(0) && (!p->y_out || (nt == 0 && !p->t_out)))
         return fail(B200ODE_EINVAL, "NULL output array");
     PerDevice* P;
     rc = device_state(H, device, &P);

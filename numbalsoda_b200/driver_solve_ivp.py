@@ -93,7 +93,8 @@ def _run(handle, devices, B, n, ts, y0, dbuf, batched_data, rec, nps, te, n_even
     nt = 0 if te is None else te.shape[0]
 
     def rows_before(b):
-        return b * nt if nt else (int(row_offset[b]) if row_offset is not None else b * cap)
+        # (ragged rows are addressed through row_offset itself: the arrays are not shifted)
+        return b * nt if nt else (0 if row_offset is not None else b * cap)
 
     def run(dev, b0, b1):
         if b1 <= b0:

@@ -77,3 +77,80 @@ def test_example_matches_oracle(built):
         assert [int(x) for x in row[2:5]] == [st.nst, st.nfe, st.nje]
         got = np.array([float(x) for x in row[6:9]])
         assert (got == us[-1]).all(), (b, got, us[-1])
+
+
+# ---------------------------------------------------------------- solve_ivp from C
+@pytest.fixture(scope="module")
+def built_ivp(tmp_path_factory):
+    d = tmp_path_factory.mktemp("c_example_ivp")
+    src = os.path.join(EX, "lorenz_events.cu")
+    rhs, ev, exe = str(d / "lorenz_rhs.fatbin"), str(d / "lorenz_events.fatbin"), str(d / "lorenz_events")
+    for macro, out in (("LORENZ_RHS", rhs), ("LORENZ_EVENTS", ev)):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=lto_100a", "-rdc=true",
+                               "-fatbin", "-D" + macro, "-o", out, src])
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-o", exe, os.path.join(EX, "lorenz_events.c"), "-L", LIBDIR, "-lb200ode",
+                           "-lm"])
+    return rhs, ev, exe
+
+
+def test_ivp_fatbins_link_without_a_gpu(built_ivp):
+    from numbalsoda_b200 import _lib
+    rhs, ev = (open(f, "rb").read() for f in built_ivp[:2])
+    for flags in (0, _lib.STRICT_FP):
+        h = ct.c_void_p()
+        rc = _lib.lib.b200ode_link_ivp(3, rhs, len(rhs), _lib.IMG_FATBIN, 2, ev, len(ev), _lib.IMG_FATBIN,
+                                       flags, ct.byref(h))
+        assert rc == 0 and h.value, _lib.lib.b200ode_last_error()
+        _lib.lib.b200ode_rhs_free(h)
+    # argument errors of the link call
+    h = ct.c_void_p()
+    assert _lib.lib.b200ode_link_ivp(3, rhs, len(rhs), _lib.IMG_FATBIN, 9, ev, len(ev), _lib.IMG_FATBIN,
+                                     0, ct.byref(h)) == -5  # more than 8 events
+    assert _lib.lib.b200ode_link_ivp(3, rhs, len(rhs), _lib.IMG_FATBIN, 1, None, 0, 0, 0,
+                                     ct.byref(h)) == -1
+    assert _lib.lib.b200ode_link_ivp(129, rhs, len(rhs), _lib.IMG_FATBIN, 0, None, 0, 0, 0,
+                                     ct.byref(h)) == -5
+
+
+def test_ivp_example_fails_loudly_without_a_device(built_ivp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    r = _run(built_ivp[2], built_ivp[0], built_ivp[1], "4")
+    assert r.returncode == 1 and "not available" in r.stderr
+
+
+@pytest.mark.gpu
+def test_ivp_example_matches_oracle(built_ivp):
+    from numba import cfunc, types
+    sig = types.void(types.double, types.CPointer(types.double), types.CPointer(types.double),
+                     types.CPointer(types.double))
+
+    @cfunc(sig)
+    def events(t, u, out, p):
+        out[0] = u[2] - p[3]
+        out[1] = u[0]
+
+    B = 129
+    r = _run(built_ivp[2], built_ivp[0], built_ivp[1], str(B), "strict")
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.strip().splitlines()]
+    assert len(rows) == B
+    f = orc.builtin_rhs("lorenz")
+    seen = set()
+    for b in (0, 1, 31, 64, 100, 127, 128):
+        s = b / (B - 1)
+        data = np.array([9.0 + 2.0 * s, 20.0 + 16.0 * s, 2.0 + 1.33 * s, 25.0 + 30.0 * (1.0 - s)])
+        ref = orc.solve_ivp(f, [0.0, 5.0], [1.0, 0.0, 0.0], None, 2, events.address, data, rtol=1e-8,
+                            atol=1e-8)
+        row = rows[b]
+        assert int(row[0]) == b
+        assert [int(x) for x in row[1:7]] == [int(ref["success"]), orc.IVP_MESSAGES.index(ref["message"]),
+                                              ref["nfev"], len(ref["t"]), int(ref["event_found"]),
+                                              ref["ind_event"]]
+        got = np.array([float(x) for x in row[7:]])
+        want = np.concatenate([[ref["t_event"]], ref["y_event"], [ref["t"][-1]], ref["y"][-1]])
+        assert (got == want).all(), (b, got, want)
+        seen.add((ref["event_found"], ref["ind_event"]))
+    assert len(seen) >= 2

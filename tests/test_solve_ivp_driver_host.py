@@ -132,3 +132,29 @@ def test_argument_errors(drv):
         drv.solve_ivp(f, np.zeros((3, 2)), np.zeros((4, 2)), data=ONE)
     with pytest.raises(TypeError, match="float64"):
         drv.solve_ivp(f, SPAN, np.array([5, 1]), data=ONE)
+
+
+@pytest.mark.parametrize("mode", ["t_eval", "two_pass", "max_rows"])
+def test_sharding_over_devices(drv, mode):
+    """device=[...] shards the ensemble by trajectory, one host thread per device, no exchange
+    (SURVEY.md 8e); the ragged rows of a shard are addressed through its slice of row_offset."""
+    rng = np.random.default_rng(4)
+    B = 23
+    data = np.column_stack([rng.uniform(9, 11, B), rng.uniform(20, 36, B), rng.uniform(2, 3.33, B),
+                            rng.uniform(30, 45, B)])
+    ts = np.column_stack([np.zeros(B), rng.uniform(0.3, 3.0, B)])
+    y0 = np.array([1.0, 0.0, 0.0])
+    f, ev = orc.builtin_rhs("lorenz"), orc.builtin_rhs("events_lorenz_z")
+    kw = dict(n_events=1, event_fcn=ev, data=data, rtol=1e-7, atol=1e-9)
+    if mode == "t_eval":
+        kw["t_eval"] = np.linspace(0.0, 3.0, 16)
+    if mode == "max_rows":
+        kw["max_rows"] = 300
+    one = drv.solve_ivp(f, ts, y0, **kw)
+    three = drv.solve_ivp(f, ts, y0, device=[0, 0, 0], **kw)
+    assert np.array_equal(one._r, three._r) and np.array_equal(one.t_event, three.t_event)
+    assert np.array_equal(one.y_event, three.y_event)
+    for k, (a, b) in enumerate(zip(one, three)):
+        # (t_eval rows beyond a trajectory's span are uninitialised memory)
+        m = np.searchsorted(kw["t_eval"], ts[k, 1], side="right") if mode == "t_eval" else len(a.t)
+        assert np.array_equal(a.t, b.t) and np.array_equal(a.y[:m], b.y[:m])
