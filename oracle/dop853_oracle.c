@@ -17,7 +17,11 @@
  *   - the reference's own known-answer test (tests/test_numbalsoda.py:22-31),
  *   - Hairer's original Fortran DOP853 as shipped inside scipy
  *     (scipy.integrate.ode('dop853')) with the reference's controller constants,
- * by tests/test_oracle_dop853.py.
+ * by tests/test_oracle_dop853.py, and
+ *   - the event times the reference itself printed in solve_ivp.ipynb, through
+ *     solve_ivp_oracle.c (an independent restatement of the same dp86co that takes the same
+ *     steps and produces the same rows bit for bit, rejected steps included):
+ *     tests/test_oracle_solve_ivp.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this file's shared object.

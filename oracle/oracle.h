@@ -78,6 +78,8 @@ void oracle_solve_ivp(oracle_rhs_fn f, const double *t_span, int neq, const doub
                       double first_step, double max_step, double rtol, double atol, int cap,
                       double *t_out, double *y_out, double *y_event, oracle_ivp_result *res);
 
+void oracle_ivp_set_scipy_reject_rule(int on); /* test-only, see solve_ivp_oracle.c */
+
 /* ensemble of independent oracle_solve_ivp calls over host threads (batch.c) */
 int oracle_solve_ivp_batch(oracle_rhs_fn f, oracle_rhs_fn events, long B, int neq, const double *t_span,
                            long t_span_stride, const double *y0, long y0_stride, const void *data,

@@ -28,6 +28,12 @@
 
 #define UROUND 2.220446049250313e-16 /* epsilon(1.0d0) */
 
+/* test-only: scipy's (Hairer's original) rejection rule hnew = h/facc1 instead of the
+ * reference's h/min(facc1, fac11/safe) (dop853_module.f90:725) -- used to show that the event
+ * times the reference printed distinguish the two (tests/test_oracle_solve_ivp.py) */
+static int g_ivp_scipy_reject_rule = 0;
+void oracle_ivp_set_scipy_reject_rule(int on) { g_ivp_scipy_reject_rule = on; }
+
 static inline double dmax(double a, double b) { return (b > a || isnan(a)) ? b : a; }
 static inline double dmin(double a, double b) { return (b < a || isnan(a)) ? b : a; }
 static inline double dsign(double a, double b) { return signbit(b) ? -fabs(a) : fabs(a); }
@@ -492,7 +498,7 @@ void oracle_solve_ivp(oracle_rhs_fn f, const double *t_span, int neq, const doub
                 hnew = posneg * dmin(fabs(hnew), fabs(h));
             reject = 0;
         } else {
-            hnew = h / dmin(facc1, fac11 / safe);
+            hnew = g_ivp_scipy_reject_rule ? h / facc1 : h / dmin(facc1, fac11 / safe);
             reject = 1;
             if (naccpt >= 1)
                 nrejct++;

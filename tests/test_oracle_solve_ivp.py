@@ -137,3 +137,47 @@ def test_edge_cases():
     # capacity (ours): more accepted steps than rows
     r = orc.solve_ivp(lv.address, SPAN, U0, rtol=1e-8, atol=1e-8, cap=10)
     assert not r["success"] and r["message"] == "output capacity exceeded" and r["rows_needed"] > 10
+
+
+def _sweep_event_times():
+    got, rej = [], []
+    for i in range(10):
+        a1 = 0.1 * np.ones(6)
+        a2 = 0.05 * np.ones(3)
+        a1[:] = 0.1 - i * 0.01
+        a2[:] = 0.1 + i * 0.01
+        S = np.array([np.sum(a1), np.sum(a2)])
+        r = orc.solve_ivp(lv_sums.address, SPAN, U0, TE, 1, ev_u0_is_1.address, data=S, rtol=1e-6)
+        got.append(r["t_event"])
+        rej.append(r["nstep"] - r["naccpt"])
+    return np.array(got), np.array(rej)
+
+
+def test_notebook_outputs_pin_the_step_controller_and_its_rejection_rule():
+    """Every one of the notebook's runs rejects steps (1-4 of its 6-10 attempts), so the event
+    times the reference printed depend on dp86co's controller *including* the one line scipy's
+    dop853 cannot cover: hnew = h/min(facc1, fac11/safe) after a rejection (module :725).  With
+    Hairer's original rule (h/facc1) the oracle misses the printed values by five orders of
+    magnitude more than with the reference's."""
+    got, rej = _sweep_event_times()
+    assert (rej >= 1).all()
+    assert np.abs(got - NOTEBOOK_CELL_27).max() < 1e-13
+    orc.lib.oracle_ivp_set_scipy_reject_rule(1)
+    try:
+        alt, _ = _sweep_event_times()
+    finally:
+        orc.lib.oracle_ivp_set_scipy_reject_rule(0)
+    assert np.abs(alt - NOTEBOOK_CELL_27).max() > 1e-9
+    assert (np.abs(alt - NOTEBOOK_CELL_27) > 1e-11).sum() >= 8
+
+
+def test_the_dop853_oracle_inherits_the_pin():
+    """dop853_oracle.c and solve_ivp_oracle.c restate dp86co independently (iout = 3 / iout = 2).
+    On the notebook's problem -- rejected steps included -- they take the same steps and produce
+    the same rows bit for bit, so what pins the one pins the other."""
+    for data, rtol in ((np.array([0.6, 0.3]), 1e-6), (np.array([0.1, 1.0]), 1e-6), (np.array([1.0, 1.0]), 1e-9)):
+        ref, ok, st = orc.dop853(lv_sums.address, U0, TE, data, rtol, 1e-6)
+        r = orc.solve_ivp(lv_sums.address, SPAN, U0, TE, data=data, rtol=rtol, atol=1e-6)
+        assert ok and r["success"] and st.nstep - st.naccpt >= 1
+        assert (r["nstep"], r["naccpt"], r["nrejct"]) == (st.nstep, st.naccpt, st.nrejct)
+        assert np.array_equal(r["y"], ref)
