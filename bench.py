@@ -127,6 +127,7 @@ NCU_TRAFFIC = {
     "lorenz_dop853": (732.222976e6 + 6.947206e9, "profiles/r1_dop853_v3_fast_controller.txt", 262144),
     "robertson_lsoda": (31.317504e6 + 605.663744e6, "profiles/r1_lsoda_v5_throughput_mode.txt", 262144),
     "brusselator_lsoda": (4.124928e6 + 150.701824e6, "profiles/r1_lsodaw_v1_fast_solves.txt", 4000),
+    "lorenz_solve_ivp": (342.943232e6 + 3.808480e9, "profiles/r1_ivp_v1_fast_controller.txt", 262144),
 }
 
 F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6, "brusselator1d": 608}

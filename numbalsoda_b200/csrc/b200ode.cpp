@@ -997,11 +997,13 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
     rc = device_state(H, device, &P);
     if (rc) return rc;
 
-    // chunks: at most ~1 GiB of rows (and what the device has free), at least one trajectory
+    // chunks: at most ~4 GiB of rows (and an eighth of what the device has free), at least one trajectory
     size_t free_b = 0, total_b = 0;
     CU(cuMemGetInfo_v2(&free_b, &total_b));
     const size_t row_bytes = sizeof(double) * (size_t)(n + (nt == 0 ? 1 : 0));
-    const size_t budget = std::min<size_t>((size_t)1 << 30, std::max<size_t>(free_b / 8, (size_t)64 << 20));
+    // (4 GiB: without t_eval a trajectory owns hundreds of rows, and a chunk should still hold
+    // a few trajectories per resident lane)
+    const size_t budget = std::min<size_t>((size_t)4 << 30, std::max<size_t>(free_b / 8, (size_t)64 << 20));
     const size_t fixed = sizeof(int) * B200ODE_IVP_NRESULT + sizeof(double) * (size_t)(1 + n);
     std::vector<long long> cut = {0};
     {
