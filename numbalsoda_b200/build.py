@@ -180,7 +180,8 @@ def build(force=False, verbose=False):
                                      os.path.join(os.path.dirname(HERE), "include", "b200ode.h")]
     if force or _newer(LIB, deps):
         cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-s", "-Wl,--gc-sections",
-               "-Wall", "-Wextra", "-I" + os.path.join(CUDA, "include"),
+               "-Wall", "-Wextra"] + os.environ.get("B200ODE_EXTRA_DEFS", "").split() + [
+               "-I" + os.path.join(CUDA, "include"),
                "-o", LIB, os.path.join(CSRC, "b200ode.cpp"), asm,
                "-Wl,--exclude-libs,ALL", "-L" + os.path.join(CUDA, "lib64"),
                "-l:libnvJitLink_static.a", "-l:libnvptxcompiler_static.a", "-ldl", "-lpthread", "-lrt"]

@@ -20,7 +20,11 @@
 #define B200ODE_DOP853W_DOUBLES(n) (22 * (n)) /* dop853_warp.cuh: shared memory of one trajectory */
 #define B200ODE_THREAD_NMAX 8
 #define B200ODE_WARP_NMAX 128
-#define B200ODE_LSODAW_JCOLS 8 /* Jacobian columns evaluated concurrently */
+#ifndef B200ODE_LSODAW_JCOLS
+#define B200ODE_LSODAW_JCOLS 16 /* Jacobian columns evaluated concurrently (<= 32): measured at
+                                   n = 64 -- 8: 77.0 k traj/s, 16: 80.1 k (still 4 warps per SM),
+                                   32: 61.5 k (3 warps per SM); profiles/r1_lsodaw_jcols_sweep.log */
+#endif
 #define B200ODE_LSODAW_MATRIX(n) ((n) * ((n) + 1)) /* the transposed, padded iteration matrix */
 #define B200ODE_LSODAW_DOUBLES(n) \
     (18 * (n) + B200ODE_LSODAW_MATRIX(n) + B200ODE_LSODAW_JCOLS * ((n) + 1) + (n) + 1)
