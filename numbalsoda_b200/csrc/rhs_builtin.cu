@@ -11,6 +11,10 @@ extern "C" __device__ long long b200ode_user_rhs(double t, double* u, double* du
 #if defined(B200_RHS_LOTKA_VOLTERRA)
     du[0] = u[0] - u[0] * u[1];
     du[1] = u[0] * u[1] - u[1] * p[0];
+#elif defined(B200_RHS_LOTKA_VOLTERRA2)
+    // /root/reference/solve_ivp.ipynb cell 21 with the two sums in p[0], p[1]
+    du[0] = u[0] - u[0] * u[1] * p[0];
+    du[1] = u[0] * u[1] - u[1] * p[1];
 #elif defined(B200_RHS_LORENZ)
     const double sigma = p[0], rho = p[1], beta = p[2];
     const double x = u[0], y = u[1], z = u[2];

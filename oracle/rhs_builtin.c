@@ -21,6 +21,15 @@ void oracle_rhs_lotka_volterra(double t, double *u, double *du, void *pv)
     du[1] = u[0] * u[1] - u[1] * p[0];
 }
 
+/* /root/reference/solve_ivp.ipynb cell 21 with np.sum(p.arr1), np.sum(p.arr2) in p[0], p[1] */
+void oracle_rhs_lotka_volterra2(double t, double *u, double *du, void *pv)
+{
+    const double *p = (const double *)pv;
+    (void)t;
+    du[0] = u[0] - u[0] * u[1] * p[0];
+    du[1] = u[0] * u[1] - u[1] * p[1];
+}
+
 void oracle_rhs_lorenz(double t, double *u, double *du, void *pv)
 {
     const double *p = (const double *)pv;
@@ -86,6 +95,8 @@ oracle_rhs_fn oracle_builtin_rhs(const char *name)
         return oracle_events_lorenz_z;
     if (!strcmp(name, "lotka_volterra"))
         return oracle_rhs_lotka_volterra;
+    if (!strcmp(name, "lotka_volterra2"))
+        return oracle_rhs_lotka_volterra2;
     if (!strcmp(name, "lorenz"))
         return oracle_rhs_lorenz;
     if (!strcmp(name, "robertson"))

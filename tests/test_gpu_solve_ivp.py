@@ -353,3 +353,16 @@ def test_warp_kernel_n12_fast_mode_and_failures():
     assert not bad.success.any() and "does not always increase" in bad[0].message
     with pytest.raises(nb.B200OdeError, match="exceeds 128"):
         nb.solve_ivp(cf.address, np.array([0.0, 1.0]), np.ones(129), te, data=P[:3])
+
+
+def test_golden_vectors_strict_bitwise():
+    """The committed fixtures (tests/golden/solve_ivp_oracle.npz: the cases of the reference's
+    solve_ivp.ipynb and tests, with the event times the reference printed) through the C ABI."""
+    import _ivp_golden as gold
+    nb = _nb()
+    for name, (rhs, span, y0, te, ne, ev, data, kw, printed) in gold.CASES.items():
+        r = nb.solve_ivp(nb.builtin(rhs), span, y0, te, n_events=ne,
+                         event_fcn=nb.builtin(ev) if ev else 0, data=data, strict=True, **kw)
+        f = dict(success=r.success, message=orc.IVP_MESSAGES.index(r.message), nfev=r.nfev,
+                 nt_out=len(r.t), event_found=r.event_found, ind_event=r.ind_event, **r.counters)
+        gold.check(name, f, r.t, r.y, r.t_event, r.y_event)

@@ -181,3 +181,18 @@ def test_the_dop853_oracle_inherits_the_pin():
         assert ok and r["success"] and st.nstep - st.naccpt >= 1
         assert (r["nstep"], r["naccpt"], r["nrejct"]) == (st.nstep, st.naccpt, st.nrejct)
         assert np.array_equal(r["y"], ref)
+
+
+def test_golden_vectors():
+    """The committed fixtures (tests/golden/solve_ivp_oracle.npz) are what the oracle produces --
+    and carry the event times the reference printed."""
+    import _ivp_golden as gold
+    assert len(gold.CASES) == 15
+    for name, (rhs, span, y0, te, ne, ev, data, kw, printed) in gold.CASES.items():
+        r = orc.solve_ivp(orc.builtin_rhs(rhs), span, y0, te, ne,
+                          orc.builtin_rhs("events_" + ev) if ev else 0, data, cap=4000, **kw)
+        f = dict(success=r["success"], message=orc.IVP_MESSAGES.index(r["message"]), nfev=r["nfev"],
+                 nt_out=len(r["t"]), rows_needed=r["rows_needed"], event_found=r["event_found"],
+                 ind_event=r["ind_event"], idid=r["idid"], nstep=r["nstep"], naccpt=r["naccpt"],
+                 nrejct=r["nrejct"])
+        gold.check(name, f, r["t"], r["y"], r["t_event"], r["y_event"])

@@ -287,3 +287,13 @@ def test_throughput_mode_emulation():
         if k:
             worst = max(worst, (np.abs(g["y"][:k] - ref["y"][:k]) / (np.abs(ref["y"][:k]) + 1.0)).max())
     assert 0.0 < worst <= 10 * rtol, worst
+
+
+def test_golden_vectors(lib):
+    """Both host-compiled cores against the committed fixtures."""
+    import _ivp_golden as gold
+    for name, (rhs, span, y0, te, ne, ev, data, kw, printed) in gold.CASES.items():
+        r = run(lib, orc.builtin_rhs(rhs), span, y0, te, ne, orc.builtin_rhs("events_" + ev) if ev else 0,
+                data, cap=4000, **kw)[0]
+        f = dict(r, message=orc.IVP_MESSAGES.index(r["message"]), nt_out=len(r["t"]))
+        gold.check(name, f, r["t"], r["y"], r["t_event"], r["y_event"])
