@@ -236,6 +236,16 @@ int b200ode_solve_ivp(b200ode_rhs_t ivp, const b200ode_ivp_problem* problem, int
 /* device pointers on the current device; asynchronous on `stream` */
 int b200ode_solve_ivp_device(b200ode_rhs_t ivp, const b200ode_ivp_problem* problem, void* stream);
 
+/* b200ode_solve_ivp with positional arguments, for callers that cannot build the structure
+ * (numba nopython code calls C through ctypes function objects: numbalsoda_b200/njit_api.py). */
+int b200ode_solve_ivp_args(b200ode_rhs_t ivp, long long B, int neq, const double* t_span,
+                           long long t_span_stride, const double* y0, long long y0_stride,
+                           const void* data, long long data_stride, int np, int nt,
+                           const double* teval, int n_events, double first_step, double max_step,
+                           double rtol, double atol, long long cap, const long long* row_offset,
+                           double* t_out, double* y_out, int* result, double* t_event,
+                           double* y_event, int device);
+
 /* Page-locked host memory for usol / success / counters: with it the device-to-host
  * copies of b200ode_*_batched run at full PCIe speed and overlap the kernels (with pageable
  * memory the driver stages them).  The reference's driver allocates usol with np.empty

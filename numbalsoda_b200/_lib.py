@@ -51,7 +51,7 @@ def _load(rebuilt=False):
         _build.build()
         rebuilt = True
     lib = ct.CDLL(LIBPATH)
-    if not hasattr(lib, "b200ode_solve_ivp") and not rebuilt:
+    if not hasattr(lib, "b200ode_solve_ivp_args") and not rebuilt:
         # a library built from older sources: rebuild it once
         from . import build as _build
         _build.build(force=True)

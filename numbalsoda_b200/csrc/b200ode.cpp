@@ -1144,6 +1144,28 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
     return 0;
 }
 
+extern "C" int b200ode_solve_ivp_args(b200ode_rhs_t H, long long B, int neq, const double* t_span,
+                                      long long t_span_stride, const double* y0, long long y0_stride,
+                                      const void* data, long long data_stride, int np, int nt,
+                                      const double* teval, int n_events, double first_step,
+                                      double max_step, double rtol, double atol, long long cap,
+                                      const long long* row_offset, double* t_out, double* y_out,
+                                      int* result, double* t_event, double* y_event, int device)
+{
+    b200ode_ivp_problem p;
+    memset(&p, 0, sizeof p);
+    p.size = sizeof p;
+    p.B = B, p.neq = neq;
+    p.t_span = t_span, p.t_span_stride = t_span_stride;
+    p.y0 = y0, p.y0_stride = y0_stride;
+    p.data = data, p.data_stride = data_stride, p.np = np;
+    p.nt = nt, p.teval = teval, p.n_events = n_events;
+    p.first_step = first_step, p.max_step = max_step, p.rtol = rtol, p.atol = atol;
+    p.cap = cap, p.row_offset = row_offset, p.t_out = t_out, p.y_out = y_out;
+    p.result = result, p.t_event = t_event, p.y_event = y_event;
+    return b200ode_solve_ivp(H, &p, device);
+}
+
 // ---------------------------------------------------------------- pinned host memory
 extern "C" int b200ode_host_alloc(size_t bytes, void** ptr)
 {

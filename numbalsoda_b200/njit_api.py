@@ -38,6 +38,11 @@ _dop853_c = _lib.lib.b200ode_dop853_batched
 _dop853_c.argtypes = [_vp, _ll, _i, _vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _d, _d, _i, _vp, _vp, _i]
 _dop853_c.restype = _i
 
+_ivp_c = _lib.lib.b200ode_solve_ivp_args
+_ivp_c.argtypes = [_vp, _ll, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _vp, _i, _d, _d, _d, _d, _ll, _vp,
+                   _vp, _vp, _vp, _vp, _vp, _i]
+_ivp_c.restype = _i
+
 _keep = []  # handles linked here live as long as the process (their address is all @njit code has)
 
 
@@ -47,6 +52,13 @@ def link(rhs, solver, neq, strict=False, exact_ctrl=False):
     address as an int, the stand-in for the reference's `funcptr` inside @njit code."""
     sid = {"lsoda": _lib.LSODA, "dop853": _lib.DOP853}[solver]
     h = _rhs.get_handle(rhs, sid, neq, strict=strict, exact_ctrl=exact_ctrl)
+    _keep.append(h)
+    return int(h.ptr.value)
+
+
+def link_ivp(rhs, neq, n_events=0, event_fcn=None, strict=False, exact_ctrl=False):
+    """solve_ivp: link the right-hand side and the events function; returns the handle's address."""
+    h = _rhs.get_ivp_handle(rhs, neq, n_events, event_fcn, strict=strict, exact_ctrl=exact_ctrl)
     _keep.append(h)
     return int(h.ptr.value)
 
@@ -84,3 +96,48 @@ def dop853_batched(handle, u0, t_eval, data, rtol=1.0e-3, atol=1.0e-6, mxstep=10
     if rc != 0:
         success[:] = 0
     return usol, success == 1
+
+
+@nb.njit
+def solve_ivp_batched(handle, t_span, y0, t_eval, data, n_events=0, first_step=0.0, max_step=0.0,
+                      rtol=1.0e-3, atol=1.0e-6, device=0):
+    """Batched numbalsoda.solve_ivp (driver_solve_ivp.py:86-218) from nopython code.
+    t_span [B,2], y0 [B,n], data [B,p] float64; t_eval [nt] or empty (every accepted step is a
+    row: two passes, the first counts).  Returns (t[R], y[R,n], row_offset[B+1], result[B,12],
+    t_event[B], y_event[B,n]): the rows of trajectory b are row_offset[b] : row_offset[b] +
+    result[b, 3]; result columns as in include/b200ode.h (success, message, nfev, nt_out, ...).
+    A failure of the library itself (no device, bad arguments) leaves result[:, 0] = 0."""
+    B, neq = y0.shape
+    nt = len(t_eval)
+    result = np.zeros((B, 12), np.int32)
+    t_event = np.zeros(B)
+    y_event = np.zeros((B, neq))
+    row_offset = np.zeros(B + 1, np.int64)
+    p = data.shape[1]
+    if nt > 0:
+        for b in range(B):
+            row_offset[b + 1] = (b + 1) * nt
+        t = np.empty(B * nt)
+        for b in range(B):
+            t[b * nt:(b + 1) * nt] = t_eval
+        y = np.empty((B * nt, neq))
+        rc = _ivp_c(handle, B, neq, t_span.ctypes.data, 2, y0.ctypes.data, neq, data.ctypes.data, p * 8, p,
+                    nt, t_eval.ctypes.data, n_events, first_step, max_step, rtol, atol, 0, 0, 0,
+                    y.ctypes.data, result.ctypes.data, t_event.ctypes.data, y_event.ctypes.data, device)
+    else:
+        rc = _ivp_c(handle, B, neq, t_span.ctypes.data, 2, y0.ctypes.data, neq, data.ctypes.data, p * 8, p,
+                    0, 0, n_events, first_step, max_step, rtol, atol, 0, 0, 0, 0, result.ctypes.data,
+                    t_event.ctypes.data, y_event.ctypes.data, device)
+        for b in range(B):
+            row_offset[b + 1] = row_offset[b] + result[b, 4]
+        R = row_offset[B]
+        t = np.empty(R)
+        y = np.empty((R, neq))
+        if rc == 0:
+            rc = _ivp_c(handle, B, neq, t_span.ctypes.data, 2, y0.ctypes.data, neq, data.ctypes.data, p * 8,
+                        p, 0, 0, n_events, first_step, max_step, rtol, atol, 0, row_offset.ctypes.data,
+                        t.ctypes.data, y.ctypes.data, result.ctypes.data, t_event.ctypes.data,
+                        y_event.ctypes.data, device)
+    if rc != 0:
+        result[:, 0] = 0
+    return t, y, row_offset, result, t_event, y_event

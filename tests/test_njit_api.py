@@ -59,3 +59,61 @@ def test_njit_calls_match_the_oracle():
     rb, okb, _ = orc.solve_batch("lsoda", orc.builtin_rhs("robertson"), u0, te_l, P_l, 1e-8, 1e-8)
     assert ok_a.all() and ok_b.all() and oka.all() and okb.all()
     assert np.array_equal(a, ra) and np.array_equal(b, rb)
+
+
+@nb.njit
+def ivp_twice(h, ts, y0, te, empty, P):
+    a = _ivp(h, ts, y0, te, P, 1, 0.0, 0.0, 1e-7, 1e-9)
+    b = _ivp(h, ts, y0, empty, P, 1, 0.0, 0.0, 1e-7, 1e-9)
+    return a, b
+
+
+def _ivp_inputs(B):
+    rng = np.random.default_rng(3)
+    P = np.column_stack([rng.uniform(9, 11, B), rng.uniform(20, 36, B), rng.uniform(2, 3.33, B),
+                         rng.uniform(30, 45, B)])
+    y0 = np.column_stack([rng.uniform(0.5, 1.5, B), rng.uniform(-0.5, 0.5, B), rng.uniform(0, 1, B)])
+    ts = np.column_stack([np.zeros(B), rng.uniform(0.3, 3.0, B)])
+    return ts, y0, np.linspace(0.0, 3.0, 31), np.empty(0), P
+
+
+def test_solve_ivp_compiles_and_fails_loudly_without_a_device():
+    import torch
+    import numbalsoda_b200 as b2
+    from numbalsoda_b200 import njit_api
+    global _ivp
+    _ivp = njit_api.solve_ivp_batched
+    h = njit_api.link_ivp(b2.builtin("lorenz"), 3, 1, b2.builtin("lorenz_z"), strict=True)
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    (t, y, off, res, tev, yev), (t2, y2, off2, res2, _, _) = ivp_twice(h, *_ivp_inputs(4))
+    assert y.shape == (4 * 31, 3) and off.tolist() == [0, 31, 62, 93, 124] and not res[:, 0].any()
+    assert y2.shape == (0, 3) and not res2[:, 0].any()
+    assert "no CPU fallback" in njit_api.last_status()
+
+
+@pytest.mark.gpu
+def test_solve_ivp_njit_matches_the_oracle():
+    import numbalsoda_b200 as b2
+    from numbalsoda_b200 import njit_api
+    global _ivp
+    _ivp = njit_api.solve_ivp_batched
+    h = njit_api.link_ivp(b2.builtin("lorenz"), 3, 1, b2.builtin("lorenz_z"), strict=True)
+    B = 200
+    ts, y0, te, empty, P = _ivp_inputs(B)
+    (t, y, off, res, tev, yev), (t2, y2, off2, res2, tev2, yev2) = ivp_twice(h, ts, y0, te, empty, P)
+    f, ev = orc.builtin_rhs("lorenz"), orc.builtin_rhs("events_lorenz_z")
+    ra = orc.solve_ivp_batch(f, ts, y0, te, 1, ev, P, rtol=1e-7, atol=1e-9)
+    rb = orc.solve_ivp_batch(f, ts, y0, None, 1, ev, P, rtol=1e-7, atol=1e-9, cap=2000)
+    for r, rr, tv, yv in ((res, ra, tev, yev), (res2, rb, tev2, yev2)):
+        g = rr["result"]
+        assert np.array_equal(r[:, 0], g["success"]) and np.array_equal(r[:, 3], g["nt_out"])
+        assert np.array_equal(r[:, 8], g["nstep"]) and np.array_equal(tv, g["t_event"])
+        assert np.array_equal(yv, rr["y_event"])
+    assert 0 < res[:, 5].sum() < B
+    for b in range(B):
+        k = min(res[b, 3], np.searchsorted(te, ts[b, 1], side="right"))
+        assert np.array_equal(y[off[b]:off[b] + k], ra["y"][b, :k])
+        k2 = res2[b, 3]
+        assert np.array_equal(t2[off2[b]:off2[b] + k2], rb["t"][b, :k2])
+        assert np.array_equal(y2[off2[b]:off2[b] + k2], rb["y"][b, :k2])
