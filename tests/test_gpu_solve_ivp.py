@@ -366,3 +366,50 @@ def test_golden_vectors_strict_bitwise():
         f = dict(success=r.success, message=orc.IVP_MESSAGES.index(r.message), nfev=r.nfev,
                  nt_out=len(r.t), event_found=r.event_found, ind_event=r.ind_event, **r.counters)
         gold.check(name, f, r.t, r.y, r.t_event, r.y_event)
+
+
+def ev_chain(t, u, out, p):
+    out[0] = u[0] - 0.4
+    out[1] = u[1] - 2.0  # never
+
+
+def stiff1(t, u, du, p):
+    du[0] = -p[0] * (u[0] - 1.0) + p[1]
+
+
+def ev1(t, u, out, p):
+    out[0] = u[0] - 0.5
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 33])
+def test_every_system_size_strict_bitwise(n):
+    """One thread-kernel image per n <= 8, the warp kernel above: each against the oracle."""
+    import numba
+    nb = _nb()
+    B = 37
+    rng = np.random.default_rng(n)
+    if n == 1:
+        rhs, ev, ne = numba.cfunc(nb.lsoda_sig)(stiff1), numba.cfunc(nb.lsoda_sig)(ev1), 1
+        data = np.column_stack([rng.uniform(0.5, 3.0, B), rng.uniform(-0.2, 0.2, B)])
+        y0 = np.zeros(1)
+    else:
+        rhs, ev, ne = numba.cfunc(nb.lsoda_sig)(pr.chain_rhs), numba.cfunc(nb.lsoda_sig)(ev_chain), 2
+        data = np.column_stack([rng.uniform(0.8, 2.5, B), np.full(B, float(n))])
+        y0 = np.linspace(1.0, 1.5, n)
+    for te in (None, np.linspace(0.0, 3.0, 13)):
+        got = nb.solve_ivp(rhs.address, np.array([0.0, 3.0]), y0, te, n_events=ne, event_fcn=ev.address,
+                           data=data, rtol=1e-7, atol=1e-10, strict=True)
+        ref = orc.solve_ivp_batch(rhs.address, [0.0, 3.0], y0, te, ne, ev.address, data, rtol=1e-7,
+                                  atol=1e-10, cap=3000)
+        rr = ref["result"]
+        assert rr["event_found"].any() and (rr["success"] == 1).all()
+        for k, f in (("nfev", "nfev"), ("nt_out", "nt_out"), ("ind_event", "ind_event"), ("idid", "idid"),
+                     ("nstep", "nstep"), ("naccpt", "naccpt"), ("nrejct", "nrejct")):
+            assert np.array_equal(getattr(got, k), rr[f]), (n, k)
+        assert np.array_equal(got.t_event, rr["t_event"]) and np.array_equal(got.y_event, ref["y_event"])
+        for b in range(B):
+            k = rr["nt_out"][b]
+            r = got[b]
+            assert np.array_equal(r.y, ref["y"][b, :k]), (n, b)
+            if te is None:
+                assert np.array_equal(r.t, ref["t"][b, :k]), (n, b)

@@ -297,3 +297,33 @@ def test_golden_vectors(lib):
                 data, cap=4000, **kw)[0]
         f = dict(r, message=orc.IVP_MESSAGES.index(r["message"]), nt_out=len(r["t"]))
         gold.check(name, f, r["t"], r["y"], r["t_event"], r["y_event"])
+
+
+@cfunc(SIG)
+def chain(t, u, du, p):  # _problems.chain_rhs: a nonlinear reaction chain of any size n = int(p[1])
+    n = int(p[1])
+    k = p[0]
+    du[0] = -k * u[0] + 0.5 * u[1] * u[1]
+    for i in range(1, n - 1):
+        du[i] = k * (u[i - 1] - u[i]) / (1.0 + i) + 0.1 * u[i + 1] - 0.1 * u[i] * u[i]
+    du[n - 1] = k * (u[n - 2] - u[n - 1]) / n
+
+
+@cfunc(SIG)
+def ev_chain(t, u, out, p):
+    out[0] = u[0] - 0.4
+    out[1] = u[1] - 2.0  # never
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])
+def test_every_thread_kernel_size(lib, n):
+    """One image per system size n <= 8 on the device: every instantiation of the core."""
+    y0 = np.linspace(1.0, 1.5, n)
+    data = np.array([1.7, float(n)])
+    for te in (None, np.linspace(0.0, 3.0, 13)):
+        ref = orc.solve_ivp(chain.address, [0.0, 3.0], y0, te, 2, ev_chain.address, data, rtol=1e-7,
+                            atol=1e-10)
+        got = run(lib, chain.address, [0.0, 3.0], y0, te, 2, ev_chain.address, data, rtol=1e-7,
+                  atol=1e-10)[0]
+        same(got, ref)
+        assert ref["event_found"] and ref["ind_event"] == 0 and ref["naccpt"] > 3
