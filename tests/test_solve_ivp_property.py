@@ -4,7 +4,6 @@ field, and the results have the properties the domain offers -- rows are the req
 times (or strictly monotone solver steps ending at the end of the span or at the event), an event
 state lies on its level to the Brent tolerance, and integrating back from the end point returns
 to the start."""
-import ctypes as ct
 
 import numpy as np
 import pytest
