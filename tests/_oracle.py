@@ -24,7 +24,10 @@ class Dop853Stats(ct.Structure):
 
 
 def _build():
-    if not os.path.exists(os.path.join(ODIR, "liboracle.so")):
+    so = os.path.join(ODIR, "liboracle.so")
+    srcs = [os.path.join(ODIR, f) for f in os.listdir(ODIR) if f.endswith((".c", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
+        # (make compares the same time stamps: a library older than its sources is rebuilt)
         subprocess.check_call(["make", "-C", ODIR, ])
     if os.path.exists(REFSRC) and not os.path.exists(os.path.join(ODIR, "_ref", "libref_probe.so")):
         subprocess.check_call(["make", "-C", ODIR, "ref", ])
