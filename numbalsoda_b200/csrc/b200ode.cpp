@@ -63,7 +63,7 @@ extern "C" int b200ode_version(void) { return B200ODE_VERSION; }
 // ---------------------------------------------------------------- CUDA driver (dlopen)
 #define DRV_FUNCS(X)                                                                        \
     X(cuInit) X(cuDeviceGet) X(cuDeviceGetCount) X(cuDeviceGetAttribute)                    \
-    X(cuDevicePrimaryCtxRetain) X(cuCtxSetCurrent) X(cuCtxGetCurrent) X(cuCtxGetDevice)     \
+    X(cuDevicePrimaryCtxRetain) X(cuDevicePrimaryCtxRelease_v2) X(cuCtxSetCurrent) X(cuCtxGetCurrent) X(cuCtxGetDevice)     \
     X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuFuncGetAttribute) X(cuFuncSetAttribute)      \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuLaunchKernel) X(cuMemAlloc_v2)       \
     X(cuMemFree_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)      \
@@ -321,16 +321,31 @@ extern "C" int b200ode_link_ivp(int neq, const void* rhs_image, size_t rhs_size,
     return link_handle(B200ODE_SOLVE_IVP, neq, name, rhs, &ev, n_events, flags, out);
 }
 
+// Frees what init_device_state() created (the device's context must be current).
+static void release_device_state(PerDevice& P)
+{
+    if (P.next) g_drv.cuMemFree_v2(P.next);
+    if (P.wm_scratch) g_drv.cuMemFree_v2(P.wm_scratch);
+    for (int i = 0; i < PerDevice::kScratchSets; i++)
+        if (P.wm_done[i]) g_drv.cuEventDestroy_v2(P.wm_done[i]);
+    if (P.mod) g_drv.cuModuleUnload(P.mod);
+    P.next = 0, P.wm_scratch = 0, P.mod = nullptr, P.fn = P.fn_ptr = nullptr;
+}
+
 extern "C" void b200ode_rhs_free(b200ode_rhs_t H)
 {
     if (!H) return;
     if (g_drv.ok) {
+        CUcontext prev = nullptr;
+        g_drv.cuCtxGetCurrent(&prev);
         for (auto& kv : H->dev) {
+            if (!kv.second.ctx) continue;
             g_drv.cuCtxSetCurrent(kv.second.ctx);
-            if (kv.second.next) g_drv.cuMemFree_v2(kv.second.next);
-            if (kv.second.wm_scratch) g_drv.cuMemFree_v2(kv.second.wm_scratch);
-            if (kv.second.mod) g_drv.cuModuleUnload(kv.second.mod);
+            release_device_state(kv.second);
+            CUdevice dev;
+            if (g_drv.cuDeviceGet(&dev, kv.first) == CUDA_SUCCESS) g_drv.cuDevicePrimaryCtxRelease_v2(dev);
         }
+        g_drv.cuCtxSetCurrent(prev);
     }
     delete H;
 }
@@ -343,8 +358,97 @@ extern "C" int b200ode_rhs_cubin(b200ode_rhs_t H, const void** cubin, size_t* si
     return 0;
 }
 
-// Make `device`'s primary context current on this thread (shared with the CUDA
-// runtime and torch) and load the module there once.
+// Loads the handle's cubin into the current context and fills `P` (module, functions, launch
+// geometry, work-queue heads).  On failure the caller releases whatever was created.
+static int init_device_state(b200ode_rhs_t H, int device, PerDevice& P)
+{
+    CUdevice dev;
+    CU(cuDeviceGet(&dev, device));
+    CU(cuModuleLoadData(&P.mod, H->cubin.data()));
+    const bool warp = warp_kernel(H->solver, H->neq);
+    CU(cuModuleGetFunction(&P.fn, P.mod, kernel_name(H->solver, H->neq)));
+    if (warp)
+        P.fn_ptr = P.fn;  // the warp kernel always hands the data record over by address
+    else
+        CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
+                               (std::string(kernel_name(H->solver, H->neq)) + "_ptr").c_str()));
+    CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
+    CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
+    CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
+    CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
+    if (warp && H->solver == B200ODE_SOLVE_IVP) {
+        P.threads = 32;
+        P.dyn_smem = B200ODE_IVPW_DOUBLES(H->neq) * (int)sizeof(double);
+    } else if (warp && H->solver == B200ODE_DOP853) {
+        P.threads = 32;
+        P.dyn_smem = B200ODE_DOP853W_DOUBLES(H->neq) * (int)sizeof(double);
+    } else if (warp) {
+        P.threads = 32;
+        P.dyn_smem = B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double);
+        // B200ODE_WM=global: iteration matrices in global memory (more warps per SM;
+        // measured slower at n = 64: 50 k vs 64 k traj/s, the LU then waits on L2)
+        const char* wm = getenv("B200ODE_WM");
+        if (wm && !strcmp(wm, "global"))
+            P.dyn_smem -= B200ODE_LSODAW_MATRIX(H->neq) * (int)sizeof(double);
+    } else {
+        // ask the image for its build-time geometry (queue / storage sizes, threads)
+        const bool dop = H->solver == B200ODE_DOP853;
+        const bool ivp = H->solver == B200ODE_SOLVE_IVP;
+        CUfunction cfg;
+        CU(cuModuleGetFunction(&cfg, P.mod, ivp ? "b200ode_ivp_config"
+                                                : dop ? "b200ode_dop853_config" : "b200ode_lsoda_config"));
+        int* d_cfg = reinterpret_cast<int*>(P.next);  // scratch: 32 bytes of the slots
+        void* cp[] = {&d_cfg};
+        CU(cuLaunchKernel(cfg, 1, 1, 1, 1, 1, 1, 0, nullptr, cp, nullptr));
+        int cfgv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CU(cuMemcpyDtoH_v2(cfgv, P.next, sizeof cfgv));
+        if (cfgv[3] != H->neq)
+            return fail(B200ODE_ECUDA, "solver image was built for neq = %d", cfgv[3]);
+        P.threads = cfgv[4];
+        if (P.threads < 32 || P.threads > 1024 || P.threads % 32)
+            return fail(B200ODE_ECUDA, "solver image reports %d threads per block", P.threads);
+        if (ivp) {
+            if (cfgv[0] != B200ODE_IVP_DOUBLES(H->neq) * P.threads || cfgv[1] != B200ODE_IVP_NEVMAX)
+                return fail(B200ODE_ECUDA, "solve_ivp image reports an inconsistent geometry");
+            P.dyn_smem = cfgv[0] * (int)sizeof(double);
+        } else if (dop) {
+            if (cfgv[0] < 32 || cfgv[1] != B200ODE_DOP853_QFIELDS(H->neq))
+                return fail(B200ODE_ECUDA, "dop853 image reports an inconsistent queue geometry");
+            P.qcap = cfgv[0];
+            P.dyn_smem = cfgv[5] * (int)sizeof(double);
+        } else {
+            P.dyn_smem = cfgv[0] * (int)sizeof(double);
+        }
+    }
+    P.max_dyn_smem = P.dyn_smem;
+    if (!warp && H->solver == B200ODE_DOP853) {
+        // room for a per-block copy of t_eval (launch(): te_shared)
+        int optin = 0;
+        CU(cuDeviceGetAttribute(&optin, CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN, dev));
+        P.max_dyn_smem = std::max(P.dyn_smem, optin - P.smem);
+    }
+    if (P.max_dyn_smem > 48 * 1024) {
+        CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
+        if (P.fn_ptr != P.fn)
+            CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
+    }
+    CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
+    CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+    if (P.blocks_per_sm < 1) P.blocks_per_sm = 1;
+    if (warp && H->solver == B200ODE_LSODA &&
+        P.dyn_smem < B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double)) {
+        P.wm_set_bytes = (size_t)P.sms * P.blocks_per_sm * B200ODE_LSODAW_MATRIX(H->neq) * sizeof(double);
+        CU(cuMemAlloc_v2(&P.wm_scratch, P.wm_set_bytes * PerDevice::kScratchSets));
+        for (int i = 0; i < PerDevice::kScratchSets; i++)
+            CU(cuEventCreate(&P.wm_done[i], CU_EVENT_DISABLE_TIMING));
+    }
+    return 0;
+}
+
+// Make `device`'s primary context current on this thread (shared with the CUDA runtime and
+// torch) and load the module there once.  The per-device state is built in a local object
+// and committed to the handle only when every step succeeded: a failed initialisation
+// leaves nothing half-made behind, and the next call tries again.
 static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
 {
     if (!driver())
@@ -362,96 +466,49 @@ static int device_state(b200ode_rhs_t H, int device, PerDevice** out)
         }
     }
     std::lock_guard<std::mutex> lk(H->mu);
-    PerDevice& P = H->dev[device];
-    if (!P.ctx) {
-        CU(cuDeviceGet(&dev, device));
-        CU(cuDevicePrimaryCtxRetain(&P.ctx, dev));
+    auto it = H->dev.find(device);
+    if (it != H->dev.end()) {
+        CU(cuCtxSetCurrent(it->second.ctx));
+        *out = &it->second;
+        return 0;
     }
-    CU(cuCtxSetCurrent(P.ctx));
-    if (!P.mod) {
-        CU(cuDeviceGet(&dev, device));
-        CU(cuModuleLoadData(&P.mod, H->cubin.data()));
-        const bool warp = warp_kernel(H->solver, H->neq);
-        CU(cuModuleGetFunction(&P.fn, P.mod, kernel_name(H->solver, H->neq)));
-        if (warp)
-            P.fn_ptr = P.fn;  // the warp kernel always hands the data record over by address
-        else
-            CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
-                                   (std::string(kernel_name(H->solver, H->neq)) + "_ptr").c_str()));
-        CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
-        CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
-        CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
-        CU(cuFuncGetAttribute(&P.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, P.fn));
-        if (warp && H->solver == B200ODE_SOLVE_IVP) {
-            P.threads = 32;
-            P.dyn_smem = B200ODE_IVPW_DOUBLES(H->neq) * (int)sizeof(double);
-        } else if (warp && H->solver == B200ODE_DOP853) {
-            P.threads = 32;
-            P.dyn_smem = B200ODE_DOP853W_DOUBLES(H->neq) * (int)sizeof(double);
-        } else if (warp) {
-            P.threads = 32;
-            P.dyn_smem = B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double);
-            // B200ODE_WM=global: iteration matrices in global memory (more warps per SM;
-            // measured slower at n = 64: 50 k vs 64 k traj/s, the LU then waits on L2)
-            const char* wm = getenv("B200ODE_WM");
-            if (wm && !strcmp(wm, "global"))
-                P.dyn_smem -= B200ODE_LSODAW_MATRIX(H->neq) * (int)sizeof(double);
-        } else {
-            // ask the image for its build-time geometry (queue / storage sizes, threads)
-            const bool dop = H->solver == B200ODE_DOP853;
-            const bool ivp = H->solver == B200ODE_SOLVE_IVP;
-            CUfunction cfg;
-            CU(cuModuleGetFunction(&cfg, P.mod, ivp ? "b200ode_ivp_config"
-                                                    : dop ? "b200ode_dop853_config" : "b200ode_lsoda_config"));
-            int* d_cfg = reinterpret_cast<int*>(P.next);  // scratch: 32 bytes of the slots
-            void* cp[] = {&d_cfg};
-            CU(cuLaunchKernel(cfg, 1, 1, 1, 1, 1, 1, 0, nullptr, cp, nullptr));
-            int cfgv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            CU(cuMemcpyDtoH_v2(cfgv, P.next, sizeof cfgv));
-            if (cfgv[3] != H->neq)
-                return fail(B200ODE_ECUDA, "solver image was built for neq = %d", cfgv[3]);
-            P.threads = cfgv[4];
-            if (P.threads < 32 || P.threads > 1024 || P.threads % 32)
-                return fail(B200ODE_ECUDA, "solver image reports %d threads per block", P.threads);
-            if (ivp) {
-                if (cfgv[0] != B200ODE_IVP_DOUBLES(H->neq) * P.threads || cfgv[1] != B200ODE_IVP_NEVMAX)
-                    return fail(B200ODE_ECUDA, "solve_ivp image reports an inconsistent geometry");
-                P.dyn_smem = cfgv[0] * (int)sizeof(double);
-            } else if (dop) {
-                if (cfgv[0] < 32 || cfgv[1] != B200ODE_DOP853_QFIELDS(H->neq))
-                    return fail(B200ODE_ECUDA, "dop853 image reports an inconsistent queue geometry");
-                P.qcap = cfgv[0];
-                P.dyn_smem = cfgv[5] * (int)sizeof(double);
-            } else {
-                P.dyn_smem = cfgv[0] * (int)sizeof(double);
-            }
-        }
-        P.max_dyn_smem = P.dyn_smem;
-        if (!warp && H->solver == B200ODE_DOP853) {
-            // room for a per-block copy of t_eval (launch(): te_shared)
-            int optin = 0;
-            CU(cuDeviceGetAttribute(&optin, CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN, dev));
-            P.max_dyn_smem = std::max(P.dyn_smem, optin - P.smem);
-        }
-        if (P.max_dyn_smem > 48 * 1024) {
-            CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
-            if (P.fn_ptr != P.fn)
-                CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
-        }
-        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
-        CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
-        if (P.blocks_per_sm < 1) P.blocks_per_sm = 1;
-        if (warp && H->solver == B200ODE_LSODA &&
-            P.dyn_smem < B200ODE_LSODAW_DOUBLES(H->neq) * (int)sizeof(double)) {
-            P.wm_set_bytes = (size_t)P.sms * P.blocks_per_sm * B200ODE_LSODAW_MATRIX(H->neq) * sizeof(double);
-            CU(cuMemAlloc_v2(&P.wm_scratch, P.wm_set_bytes * PerDevice::kScratchSets));
-            for (int i = 0; i < PerDevice::kScratchSets; i++)
-                CU(cuEventCreate(&P.wm_done[i], CU_EVENT_DISABLE_TIMING));
-        }
+    PerDevice P;
+    CU(cuDeviceGet(&dev, device));
+    CU(cuDevicePrimaryCtxRetain(&P.ctx, dev));
+    int rc = 0;
+    {
+        CUresult r = g_drv.cuCtxSetCurrent(P.ctx);
+        rc = r == CUDA_SUCCESS ? init_device_state(H, device, P) : cu_fail(r, "cuCtxSetCurrent");
     }
-    *out = &P;
+    if (rc) {
+        const std::string msg = g_err;  // (the clean-up must not overwrite the message)
+        release_device_state(P);
+        g_drv.cuDevicePrimaryCtxRelease_v2(dev);
+        g_err = msg;
+        return rc;
+    }
+    PerDevice& Q = H->dev[device];
+    Q = P;
+    *out = &Q;
     return 0;
 }
+
+// Host-path calls name their device explicitly and make its context current for the duration
+// of the call only: the caller's current context (torch's, the CUDA runtime's) is put back.
+namespace {
+struct CtxRestore {
+    CUcontext prev = nullptr;
+    bool armed = false;
+    CtxRestore()
+    {
+        if (g_drv.ok && g_drv.cuCtxGetCurrent(&prev) == CUDA_SUCCESS) armed = true;
+    }
+    ~CtxRestore()
+    {
+        if (armed) g_drv.cuCtxSetCurrent(prev);
+    }
+};
+}  // namespace
 
 static int check_args(b200ode_rhs_t H, int solver, long long B, int neq, const void* u0,
                       const void* data, int np, int nt, const void* teval, const void* usol,
@@ -526,6 +583,7 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
 {
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
+    if (u0_stride != 0 && u0_stride < neq) return fail(B200ODE_EINVAL, "u0_stride = %lld", u0_stride);
     PerDevice* P;
     rc = device_state(H, -1, &P);
     if (rc) return rc;
@@ -535,7 +593,9 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
     a.u0 = u0;
     a.u0_stride = u0_stride;
     a.data = static_cast<const char*>(data);
-    a.data_stride = data_stride;
+    // data_stride < 0: one record of -data_stride bytes shared by all (include/b200ode.h);
+    // the kernels address record b at data + b * stride, so shared means stride 0
+    a.data_stride = data_stride > 0 ? data_stride : 0;
     a.np = np;
     a.nt = nt;
     a.t_eval = teval;
@@ -642,11 +702,44 @@ struct Scratch {
         used += (bytes + 255) & ~(size_t)255;
         return p;
     }
+    // work that uses the block could not be waited for: never hand it out again (it stays
+    // marked busy -- leaked on purpose, freeing it could fault the work still running)
+    bool poisoned = false;
     ~Scratch()
     {
-        if (!pooled) return;
+        if (!pooled || poisoned) return;
         std::lock_guard<std::mutex> lk(g_pool.mu);
         g_pool.blocks[device][index].busy = false;
+    }
+};
+
+// Waits for the streams of a host-path call on every way out of it.  Once the first copy or
+// kernel is enqueued, an early error return must not release the pooled device block (the
+// next call would reuse it under running kernels) nor give the caller's host buffers back
+// while asynchronous copies may still write into them.
+struct StreamDrain {
+    Scratch* mem;
+    CUstream s[3] = {nullptr, nullptr, nullptr};
+    explicit StreamDrain(Scratch* m) : mem(m) {}
+    int wait()
+    {
+        int rc = 0;
+        for (CUstream q : s)
+            if (q) {
+                CUresult r = g_drv.cuStreamSynchronize(q);
+                if (r != CUDA_SUCCESS) {
+                    if (mem) mem->poisoned = true;
+                    if (!rc) rc = cu_fail(r, "cuStreamSynchronize");
+                }
+            }
+        s[0] = s[1] = s[2] = nullptr;
+        return rc;
+    }
+    ~StreamDrain()
+    {
+        const std::string msg = g_err;  // keep the error that caused the early return
+        wait();
+        if (!msg.empty()) g_err = msg;
     }
 };
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -672,6 +765,7 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
     if (device < 0) return fail(B200ODE_EINVAL, "device = %d", device);
+    if (u0_stride != 0 && u0_stride < neq) return fail(B200ODE_EINVAL, "u0_stride = %lld", u0_stride);
     if (B == 0) return 0;
     // dop853: nmax <= 0 is rejected before any work (dop853_module.f90:243-246)
     if (solver == B200ODE_DOP853 && mxstep <= 0) {
@@ -684,6 +778,7 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     }
     const bool trace = getenv("B200ODE_TRACE") != nullptr;
     const double t0 = now_ms();
+    CtxRestore restore_ctx;
     PerDevice* P;
     rc = device_state(H, device, &P);
     if (rc) return rc;
@@ -695,8 +790,11 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
                                         : (size_t)(np > 0 ? np * 8 : 0);
     const size_t data_bytes = data ? (data_stride > 0 ? (size_t)data_stride * (size_t)B : rec) : 0;
     const size_t tol_bytes = sizeof(double) * (size_t)B;
+    // u0 rows wider than neq travel as the padded block they are (one copy; the kernels take
+    // the stride), not as B small copies
+    const size_t u0_doubles = u0_stride ? (size_t)(B - 1) * (size_t)u0_stride + (size_t)neq : (size_t)neq;
     const size_t in_bytes = align256(sizeof(double) * nt) +
-                            align256(sizeof(double) * neq * (size_t)(u0_stride ? B : 1)) +
+                            align256(sizeof(double) * u0_doubles) +
                             align256(data_bytes) + (rtol_b ? align256(tol_bytes) : 0) +
                             (atol_b ? align256(tol_bytes) : 0);
     // chunk size: at least 4 trajectories per resident lane (a persistent grid needs a few
@@ -717,7 +815,7 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
                              (counters ? align256(sizeof(int) * B200ODE_NCOUNTERS * (size_t)chunk) : 0);
     if ((rc = mem.acquire(device, in_bytes + out_bytes * nbuf + 4096))) return rc;
     const CUdeviceptr d_te = mem.take(sizeof(double) * nt);
-    const CUdeviceptr d_u0 = mem.take(sizeof(double) * neq * (size_t)(u0_stride ? B : 1));
+    const CUdeviceptr d_u0 = mem.take(sizeof(double) * u0_doubles);
     const CUdeviceptr d_data = mem.take(data_bytes);
     const CUdeviceptr d_rtol = rtol_b ? mem.take(tol_bytes) : 0;
     const CUdeviceptr d_atol = atol_b ? mem.take(tol_bytes) : 0;
@@ -734,20 +832,11 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     for (int i = 0; i < nbuf; i++)
         if ((rc = ev_kernel[i].create()) || (rc = ev_copied[i].create())) return rc;
     const double t1 = now_ms();
+    StreamDrain drain(&mem);  // from here on every return waits for the streams first
+    drain.s[0] = sk[0].s, drain.s[1] = sk[1].s, drain.s[2] = sc.s;
 
     CU(cuMemcpyHtoDAsync_v2(d_te, teval, sizeof(double) * nt, sk[0].s));
-    if (u0_stride) {
-        // gather rows if the caller's stride is wider than neq
-        if (u0_stride == neq) {
-            CU(cuMemcpyHtoDAsync_v2(d_u0, u0, sizeof(double) * neq * (size_t)B, sk[0].s));
-        } else {
-            for (long long b = 0; b < B; b++)
-                CU(cuMemcpyHtoDAsync_v2(d_u0 + sizeof(double) * neq * (size_t)b, u0 + b * u0_stride,
-                                        sizeof(double) * neq, sk[0].s));
-        }
-    } else {
-        CU(cuMemcpyHtoDAsync_v2(d_u0, u0, sizeof(double) * neq, sk[0].s));
-    }
+    CU(cuMemcpyHtoDAsync_v2(d_u0, u0, sizeof(double) * u0_doubles, sk[0].s));
     if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data, data, data_bytes, sk[0].s));
     if (rtol_b) CU(cuMemcpyHtoDAsync_v2(d_rtol, rtol_b, tol_bytes, sk[0].s));
     if (atol_b) CU(cuMemcpyHtoDAsync_v2(d_atol, atol_b, tol_bytes, sk[0].s));
@@ -774,8 +863,8 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
         B200OdeLaunch a;
         memset(&a, 0, sizeof a);
         a.B = nb;
-        a.u0 = reinterpret_cast<const double*>(d_u0) + (u0_stride ? (size_t)b0 * neq : 0);
-        a.u0_stride = u0_stride ? neq : 0;
+        a.u0 = reinterpret_cast<const double*>(d_u0) + (size_t)b0 * (size_t)u0_stride;
+        a.u0_stride = u0_stride;
         a.data = reinterpret_cast<const char*>(d_data) + (data_stride > 0 ? (size_t)b0 * data_stride : 0);
         a.data_stride = data_stride > 0 ? data_stride : 0;
         a.np = np;
@@ -798,9 +887,7 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     }
     if ((rc = copy_back(nchunks - 1))) return rc;
     const double t2 = now_ms();
-    CU(cuStreamSynchronize(sc.s));
-    CU(cuStreamSynchronize(sk[0].s));
-    CU(cuStreamSynchronize(sk[1].s));
+    if ((rc = drain.wait())) return rc;
     if (trace)
         fprintf(stderr, "[b200ode] B=%lld chunk=%lld x%lld buffers=%d scratch=%.1f MB | setup %.2f ms, "
                         "enqueue %.2f ms, drain %.2f ms\n", B, chunk, nchunks, nbuf,
@@ -993,6 +1080,7 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
     };
     if (rows_upto(B) > rows_upto(0) && (!p->y_out || (nt == 0 && !p->t_out)))
         return fail(B200ODE_EINVAL, "NULL output array");
+    CtxRestore restore_ctx;
     PerDevice* P;
     rc = device_state(H, device, &P);
     if (rc) return rc;
@@ -1042,7 +1130,9 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
                                            : (size_t)(p->np > 0 ? p->np * 8 : 0);
     const size_t data_bytes = p->data ? (p->data_stride > 0 ? (size_t)p->data_stride * (size_t)B : rec) : 0;
     const size_t ts_bytes = sizeof(double) * 2 * (size_t)(p->t_span_stride ? B : 1);
-    const size_t y0_bytes = sizeof(double) * n * (size_t)(p->y0_stride ? B : 1);
+    // (rows wider than neq travel as the padded block they are: one copy, the kernel takes the stride)
+    const size_t y0_bytes = sizeof(double) * (p->y0_stride ? (size_t)(B - 1) * (size_t)p->y0_stride + (size_t)n
+                                                           : (size_t)n);
     const size_t tol_bytes = sizeof(double) * (size_t)B;
     const size_t off_bytes = ragged ? sizeof(long long) * (size_t)(max_traj + 1) : 0;
     const size_t in_bytes = align256(sizeof(double) * std::max(nt, 1)) + align256(ts_bytes) + align256(y0_bytes) +
@@ -1076,15 +1166,11 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
     for (int i = 0; i < nbuf; i++)
         if ((rc = ev_kernel[i].create()) || (rc = ev_copied[i].create())) return rc;
 
+    StreamDrain drain(&mem);  // from here on every return waits for the streams first
+    drain.s[0] = sk.s, drain.s[1] = sc.s;
     if (nt > 0) CU(cuMemcpyHtoDAsync_v2(d_te, p->teval, sizeof(double) * nt, sk.s));
     CU(cuMemcpyHtoDAsync_v2(d_ts, p->t_span, ts_bytes, sk.s));
-    if (p->y0_stride == 0 || p->y0_stride == n) {
-        CU(cuMemcpyHtoDAsync_v2(d_y0, p->y0, y0_bytes, sk.s));
-    } else {
-        for (long long b = 0; b < B; b++)
-            CU(cuMemcpyHtoDAsync_v2(d_y0 + sizeof(double) * n * (size_t)b, p->y0 + b * p->y0_stride,
-                                    sizeof(double) * n, sk.s));
-    }
+    CU(cuMemcpyHtoDAsync_v2(d_y0, p->y0, y0_bytes, sk.s));
     if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data, p->data, data_bytes, sk.s));
     if (p->rtol_b) CU(cuMemcpyHtoDAsync_v2(d_rtol, p->rtol_b, tol_bytes, sk.s));
     if (p->atol_b) CU(cuMemcpyHtoDAsync_v2(d_atol, p->atol_b, tol_bytes, sk.s));
@@ -1115,8 +1201,8 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
         fill_ivp_launch(&a, p);
         a.B = nb;
         a.t_span = reinterpret_cast<const double*>(d_ts) + (p->t_span_stride ? 2 * (size_t)b0 : 0);
-        a.y0 = reinterpret_cast<const double*>(d_y0) + (p->y0_stride ? (size_t)b0 * n : 0);
-        a.y0_stride = p->y0_stride ? n : 0;
+        a.y0 = reinterpret_cast<const double*>(d_y0) + (size_t)b0 * (size_t)p->y0_stride;
+        a.y0_stride = p->y0_stride;
         a.data = reinterpret_cast<const char*>(d_data) + (p->data_stride > 0 ? (size_t)b0 * p->data_stride : 0);
         a.t_eval = reinterpret_cast<const double*>(d_te);
         a.rtol_b = p->rtol_b ? reinterpret_cast<const double*>(d_rtol) + b0 : nullptr;
@@ -1139,9 +1225,7 @@ extern "C" int b200ode_solve_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p, 
         if (c >= 1 && (rc = copy_back(c - 1))) return rc;
     }
     if ((rc = copy_back(nchunks - 1))) return rc;
-    CU(cuStreamSynchronize(sc.s));
-    CU(cuStreamSynchronize(sk.s));
-    return 0;
+    return drain.wait();
 }
 
 extern "C" int b200ode_solve_ivp_args(b200ode_rhs_t H, long long B, int neq, const double* t_span,

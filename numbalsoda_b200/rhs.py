@@ -14,13 +14,15 @@ spellings of the right-hand side:
 """
 import ctypes as ct
 import gc
+import numbers
 import threading
+import weakref
 
 from . import _lib
 
 _lock = threading.Lock()
 _handles = {}     # (key, solver, neq, flags) -> RhsHandle
-_by_address = {}  # cfunc address -> python function
+_by_address = {}  # cfunc address -> weakref to the CFunc (validated on every lookup)
 
 
 class Builtin:
@@ -65,24 +67,39 @@ class RhsHandle:
 
 
 def register(cfunc):
-    """Remember the Python function behind a numba CFunc (optional: lookups by
-    address also scan the live objects)."""
-    _by_address[cfunc.address] = cfunc._pyfunc
+    """Remember a numba CFunc so that its address resolves without a scan of the live
+    objects (optional)."""
+    _by_address[cfunc.address] = weakref.ref(cfunc)
     return cfunc
 
 
+def _cached(addr):
+    """The Python function of the live CFunc at `addr`, or None.  A cache entry is only a
+    hint: once a cfunc is collected numba may hand its code address to a new one, so the
+    entry counts only while its CFunc is alive and still has that address."""
+    ref = _by_address.get(addr)
+    obj = ref() if ref is not None else None
+    if obj is not None and obj.address == addr:
+        return obj._pyfunc
+    _by_address.pop(addr, None)
+    return None
+
+
 def _pyfunc_from_address(addr):
-    if addr in _by_address:
-        return _by_address[addr]
+    addr = int(addr)
+    f = _cached(addr)
+    if f is not None:
+        return f
     from numba.core.ccallback import CFunc
     for obj in gc.get_objects():
         try:  # (isinstance itself raises on dead weakref proxies)
             if isinstance(obj, CFunc):
-                _by_address[obj.address] = obj._pyfunc
+                _by_address[obj.address] = weakref.ref(obj)
         except Exception:
             pass
-    if addr in _by_address:
-        return _by_address[addr]
+    f = _cached(addr)
+    if f is not None:
+        return f
     raise ValueError(
         "funcptr %#x is not the address of a live numba @cfunc: the GPU solver needs the "
         "Python source of the right-hand side to compile it for the device; pass the cfunc "
@@ -138,6 +155,25 @@ def without_carray(pyfunc):
     return env[fdef.name]
 
 
+_TARGET_CC = (10, 0)  # the solver images are built for sm_100a (build.py ARCH)
+
+
+def _ltoir_cc():
+    """Compute capability handed to numba's NVVM for the right-hand side's LTO-IR.  LTO-IR is
+    target-independent up to the NVVM data layout; nvJitLink generates the sm_100a code.  The
+    target is the solver images' (10.0), lowered to the newest architecture the installed NVVM
+    knows when it predates Blackwell."""
+    try:
+        from numba.cuda.cudadrv import nvvm
+        ccs = [tuple(c[:2]) for c in nvvm.get_supported_ccs()]
+        ok = [c for c in ccs if c <= _TARGET_CC]
+        if ok:
+            return max(ok)
+    except Exception:
+        pass
+    return (9, 0)
+
+
 def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs"):
     """numba.cuda: Python rhs(t, u, du, p) -> LTO-IR of `b200ode_user_rhs` (or, for
     solve_ivp's events(t, y, out, p), of `b200ode_user_events`)."""
@@ -147,7 +183,7 @@ def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs"):
 
     def build(f):
         code, _ = cuda.compile(f, sig, device=True, abi="c",
-                               abi_info={"abi_name": abi_name}, output="ltoir", cc=(9, 0))
+                               abi_info={"abi_name": abi_name}, output="ltoir", cc=_ltoir_cc())
         return bytes(code)
 
     try:
@@ -163,6 +199,11 @@ def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs"):
         return build(rewritten)
 
 
+def _is_address(x):
+    """funcptr as the reference takes it: a Python int or any numpy integer scalar."""
+    return isinstance(x, numbers.Integral) and not isinstance(x, bool)
+
+
 def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False):
     """Link (once per right-hand side, solver, size and mode) and return the handle."""
     flags = _lib.STRICT_FP if strict else (_lib.EXACT_CTRL if exact_ctrl else 0)
@@ -171,7 +212,7 @@ def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False):
     if isinstance(rhs, Builtin):
         key, origin = ("builtin", rhs.name), rhs
     else:
-        if isinstance(rhs, int):
+        if _is_address(rhs):
             rhs = _pyfunc_from_address(rhs)
         elif hasattr(rhs, "_pyfunc") and hasattr(rhs, "address"):
             rhs = rhs._pyfunc
@@ -203,7 +244,7 @@ def _origin(f, what):
     """-> (cache key, Builtin or Python function) of a right-hand side / events function."""
     if isinstance(f, Builtin):
         return ("builtin", f.name), f
-    if isinstance(f, int):
+    if _is_address(f):
         f = _pyfunc_from_address(f)
     elif hasattr(f, "_pyfunc") and hasattr(f, "address"):
         f = f._pyfunc
@@ -221,7 +262,7 @@ def get_ivp_handle(rhs, neq, n_events=0, events=None, strict=False, exact_ctrl=F
     if isinstance(rhs, RhsHandle):
         return rhs
     n_events = int(n_events)
-    if n_events > 0 and (events is None or (isinstance(events, int) and events == 0)):
+    if n_events > 0 and (events is None or (_is_address(events) and int(events) == 0)):
         raise ValueError("n_events = %d but no event function was given" % n_events)
     rkey, rorig = _origin(rhs, "right-hand side")
     ekey, eorig = _origin(events, "event_fcn") if n_events > 0 else (None, None)

@@ -96,16 +96,15 @@ def test_robertson_sweep_against_oracle(strict):
         assert np.array_equal(us, ref)
         assert (cnt[:, 3] >= 1).all() and (cnt[:, 7] == 2).all()  # every one switched to BDF
     else:
-        # fused multiply-adds perturb the last bits, and a chaotic-in-the-rounding step
-        # sequence follows: north_star's bound is 10 * rtol, taken
-        # in the solver's own error weights rtol * |y| + atol
+        # Fused multiply-adds perturb the last bits and a different -- equally valid -- step
+        # sequence follows.  Two such runs agree to their common global error, which for the
+        # reference itself is ~11 units of rtol*|y| + atol on this sweep: the accuracy
+        # statement proper (each mode against a tight-tolerance truth, beside the reference's
+        # own error) is tests/test_gpu_truth.py.  Here only the triangle inequality: the
+        # distance between the two runs cannot exceed the sum of their global errors.
         err = np.abs(us - ref) / (1e-8 * np.abs(ref) + 1e-8)
-        print("fast-mode max weighted error: %.3g" % err.max())
-        # Not a parity criterion (that is the strict run above): two integrations whose
-        # roundings differ select different step sequences, and each is only accurate to
-        # its own global error.  The reference itself moves by 300 such units when one
-        # product of this RHS is re-associated; measured here: 16.5.
-        assert err.max() <= 100.0
+        print("fast-mode max weighted distance to the oracle: %.3g" % err.max())
+        assert err.max() <= 2 * 1.5 * 11.2
         assert np.abs(cnt[:, 0].astype(float) - cr[:, 0]).mean() < 40
 
 

@@ -64,7 +64,10 @@ def test_three_restatements_agree_and_results_are_consistent(cores, n, w, eps, l
         got = run(core, osc.address, span, y0, te, 1, ev_level.address, data, cap=20000, **kw)[0]
         for k in FIELDS:
             assert got[k] == ref[k], k
-        assert np.array_equal(got["t"], ref["t"]) and np.array_equal(got["y"], ref["y"])
+        # (equal_nan: when the last step's x + h rounds one ulp below t_eval[-1] the reference's
+        # solout never writes the final row -- SURVEY.md appendix A, DOP853 item 4 -- and all
+        # three restatements leave it unwritten alike)
+        assert np.array_equal(got["t"], ref["t"]) and np.array_equal(got["y"], ref["y"], equal_nan=True)
         assert np.array_equal(got["y_event"], ref["y_event"])
     assert ref["success"]
     t, y = ref["t"], ref["y"]
@@ -77,7 +80,8 @@ def test_three_restatements_agree_and_results_are_consistent(cores, n, w, eps, l
         assert np.array_equal(t, te[:len(t)]) and (ref["event_found"] or len(t) == len(te))
     else:
         assert t[0] == 0.0 and np.all(np.diff(sgn * t) > 0)
-        assert ref["event_found"] or t[-1] == span[1]
+        # the last step is h = xend - x, and x + h may round one ulp off xend (module :554-557)
+        assert ref["event_found"] or abs(t[-1] - span[1]) <= 2.0 * np.spacing(abs(span[1]))
         assert len(t) == (ref["naccpt"] if ref["event_found"] else ref["naccpt"] + 1)
     if not ref["event_found"] and not with_te and rexp >= 7:
         # round trip: integrate back from the end point
