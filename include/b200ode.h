@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200ODE_VERSION 100
+#define B200ODE_VERSION 101
 
 /* solver */
 #define B200ODE_DOP853 0 /* replaces dop853_wrapper, src/dop853_c_interface.f90:75 */
@@ -127,10 +127,15 @@ int b200ode_lsoda_batched_device(b200ode_rhs_t rhs, long long B, int neq, const 
                                  void* stream);
 
 /* The same two calls with every argument in one structure, plus what the positional
- * entry points cannot express: per-trajectory tolerances (SURVEY.md section 8f, rank 1 --
- * the reference takes one scalar rtol / atol, numbalsoda/driver.py:29; its ewset supports
- * more, LSODA.cpp:1368-1390).  The solver is the one `rhs` was linked for.  Zero-initialise
- * the structure and set `size = sizeof(b200ode_problem)`. */
+ * entry points cannot express: per-trajectory and per-component tolerances (SURVEY.md
+ * section 8f, rank 1 -- the reference's drivers take one scalar rtol / atol,
+ * numbalsoda/driver.py:29; its solvers support one value per component: LSODA's itol_ = 3 / 4,
+ * LSODA.cpp:500-520, :624-640, :1368-1390, and dop853's itol = 1, dop853_module.f90:603-612,
+ * :779-803).  The solver is the one `rhs` was linked for.  Zero-initialise the structure and
+ * set `size = sizeof(b200ode_problem)`. */
+#define B200ODE_TOL_PER_TRAJECTORY 0 /* rtol_b is [B] */
+#define B200ODE_TOL_PER_COMPONENT 1  /* rtol_b is [neq], shared by every trajectory */
+#define B200ODE_TOL_FULL 2           /* rtol_b is [B,neq] */
 typedef struct b200ode_problem {
     size_t size;
     long long B;
@@ -144,12 +149,14 @@ typedef struct b200ode_problem {
     const double* teval;    /* [nt] */
     double* usol;           /* [B,nt,neq] */
     double rtol, atol;      /* used where the arrays below are NULL */
-    const double* rtol_b;   /* [B] or NULL */
-    const double* atol_b;   /* [B] or NULL */
+    const double* rtol_b;   /* [B], [neq] or [B,neq] as rtol_dims says, or NULL */
+    const double* atol_b;   /* likewise with atol_dims */
     int mxstep;
     int exit_on_warning;    /* lsoda only */
     int* success;           /* [B] */
     int* counters;          /* [B,8] or NULL */
+    int rtol_dims;          /* B200ODE_TOL_*: shape of rtol_b (0 = [B]) */
+    int atol_dims;
 } b200ode_problem;
 /* host pointers; copies to / from `device` */
 int b200ode_solve(b200ode_rhs_t rhs, const b200ode_problem* problem, int device);

@@ -13,6 +13,7 @@ IMG_LTOIR, IMG_PTX, IMG_FATBIN, IMG_BUILTIN = 0, 1, 2, 3
 STRICT_FP = 1
 EXACT_CTRL = 2
 NCOUNTERS = 8
+TOL_PER_TRAJECTORY, TOL_PER_COMPONENT, TOL_FULL = 0, 1, 2  # shape of rtol_b / atol_b
 IVP_NRESULT = 12
 IVP_NEVENTS_MAX = 8
 
@@ -29,7 +30,7 @@ class Problem(ct.Structure):
                 ("teval", ct.c_void_p), ("usol", ct.c_void_p), ("rtol", ct.c_double),
                 ("atol", ct.c_double), ("rtol_b", ct.c_void_p), ("atol_b", ct.c_void_p),
                 ("mxstep", ct.c_int), ("exit_on_warning", ct.c_int), ("success", ct.c_void_p),
-                ("counters", ct.c_void_p)]
+                ("counters", ct.c_void_p), ("rtol_dims", ct.c_int), ("atol_dims", ct.c_int)]
 
 
 class IvpProblem(ct.Structure):

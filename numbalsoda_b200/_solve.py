@@ -66,17 +66,10 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
         usol = np.empty((B, nt, n), dtype=np.float64)  # as the reference, driver.py:35
     ok = np.full(B, 999, dtype=np.int32)
     cnt = np.zeros((B, _lib.NCOUNTERS), dtype=np.int32) if counters else None
-    # rtol / atol: the reference's scalars, or one value per trajectory (shape [B])
-    rtol_b = atol_b = None
-    if np.ndim(rtol) > 0:
-        rtol_b = np.ascontiguousarray(rtol, dtype=np.float64)
-        rtol = 0.0
-    if np.ndim(atol) > 0:
-        atol_b = np.ascontiguousarray(atol, dtype=np.float64)
-        atol = 0.0
-    for name, arr in (("rtol", rtol_b), ("atol", atol_b)):
-        if arr is not None and arr.shape != (B,):
-            raise ValueError("%s must be a scalar or have shape (%d,)" % (name, B))
+    # rtol / atol: the reference's scalars, or arrays (tolerance_layout): one value per
+    # trajectory [B], per component [n] / [1,n], or both [B,n]
+    rtol, rtol_b, rtol_dims = tolerance_layout(rtol, B, n, "rtol", batched)
+    atol, atol_b, atol_dims = tolerance_layout(atol, B, n, "atol", batched)
 
     devices = _device_list(device)
 
@@ -93,8 +86,8 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
         pb.data, pb.data_stride = dp.ctypes.data, (rec if batched_data else -rec)
         pb.teval, pb.usol = t_eval.ctypes.data, usol[b0:b1].ctypes.data
         pb.rtol, pb.atol = float(rtol), float(atol)
-        pb.rtol_b = rtol_b[b0:b1].ctypes.data if rtol_b is not None else None
-        pb.atol_b = atol_b[b0:b1].ctypes.data if atol_b is not None else None
+        pb.rtol_b, pb.rtol_dims = _tol_slice(rtol_b, rtol_dims, b0, b1)
+        pb.atol_b, pb.atol_dims = _tol_slice(atol_b, atol_dims, b0, b1)
         pb.mxstep, pb.exit_on_warning = int(mxstep), int(bool(exit_on_warning))
         pb.success = ok[b0:b1].ctypes.data
         pb.counters = cnt[b0:b1].ctypes.data if counters else None
@@ -123,6 +116,41 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
         out = (usol[0], bool(success[0]))
         return out + ((cnt[0],) if counters else ())
     return (usol, success) + ((cnt,) if counters else ())
+
+
+def tolerance_layout(x, B, n, name, batched=True):
+    """rtol / atol as the drivers accept them -> (scalar, array or None, B200ODE_TOL_* shape code).
+
+    scalar          the reference's argument (numbalsoda/driver.py:29)
+    [B]             one value per trajectory
+    [n] or [1, n]   one value per component, shared by the ensemble: the reference's solvers
+                    support it (LSODA itol_ = 3 / 4, LSODA.cpp:1368-1390; dop853 itol = 1,
+                    dop853_module.f90:603-612) although its drivers only pass scalars
+    [B, n]          both
+    A 1-D array whose length fits both readings (B == n) is taken per trajectory when the call
+    is batched; write [1, n] for per component."""
+    if np.ndim(x) == 0:
+        return float(x), None, _lib.TOL_PER_TRAJECTORY
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    if a.ndim == 1 and a.shape[0] == B and (batched or n == 1):
+        return 0.0, a, _lib.TOL_PER_TRAJECTORY
+    if a.ndim == 1 and a.shape[0] == n:
+        return 0.0, a, _lib.TOL_PER_COMPONENT
+    if a.ndim == 2 and a.shape == (1, n):
+        return 0.0, np.ascontiguousarray(a[0]), _lib.TOL_PER_COMPONENT
+    if a.ndim == 2 and a.shape == (B, n):
+        return 0.0, a, _lib.TOL_FULL
+    raise ValueError("%s must be a scalar or have shape (%d,) [per trajectory], (%d,) / (1, %d) "
+                     "[per component] or (%d, %d); got %r" % (name, B, n, n, B, n, a.shape))
+
+
+def _tol_slice(arr, dims, b0, b1):
+    """the part of a tolerance array that belongs to trajectories [b0, b1)"""
+    if arr is None:
+        return None, 0
+    if dims == _lib.TOL_PER_COMPONENT:
+        return arr.ctypes.data, dims
+    return arr[b0:b1].ctypes.data, dims
 
 
 def shard_bounds(B, parts):

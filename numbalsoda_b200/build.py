@@ -83,7 +83,14 @@ def build(force=False, verbose=False):
             continue
         for n in sizes:
             out = os.path.join(OBJ, "%s_n%d.fatbin" % (name, n))
-            if force or _newer(out, [srcp, os.path.abspath(__file__)] + headers):
+            # B200ODE_REBUILD="dop853_n3,lsoda_n3": rebuild exactly these images (launch-geometry
+            # sweeps on the GPU box, tools/sweep_build.sh) and leave the others as they are
+            only = os.environ.get("B200ODE_REBUILD")
+            if only is not None:
+                stale = ("%s_n%d" % (name, n)) in only.split(",")
+            else:
+                stale = force or _newer(out, [srcp, os.path.abspath(__file__)] + headers)
+            if stale:
                 mb = int(os.environ.get("B200ODE_MINBLOCKS", MINBLOCKS.get(name, {}).get(n, 1)))
                 qc = int(os.environ.get("B200ODE_QCAP", QCAP.get(n, 48)))
                 ni = int(os.environ.get("B200ODE_DRAIN_NOINLINE", "0"))

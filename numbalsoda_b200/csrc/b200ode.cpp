@@ -510,6 +510,32 @@ struct CtxRestore {
 };
 }  // namespace
 
+// A tolerance array of the C ABI: pointer + B200ODE_TOL_* shape -> what the kernels take
+// (b200ode_launch.h: value of trajectory b, component i = p[b * sb + (vec ? i : 0)]).
+struct TolArg {
+    const double* p = nullptr;
+    int dims = 0;
+    long long sb(int neq) const { return dims == B200ODE_TOL_PER_COMPONENT ? 0 : dims == B200ODE_TOL_FULL ? neq : 1; }
+    int vec() const { return p && dims != B200ODE_TOL_PER_TRAJECTORY ? 1 : 0; }
+    size_t count(long long B, int neq) const
+    {
+        return dims == B200ODE_TOL_PER_COMPONENT ? (size_t)neq
+                                                 : dims == B200ODE_TOL_FULL ? (size_t)B * neq : (size_t)B;
+    }
+};
+static TolArg tol_arg(const double* p, int dims)
+{
+    TolArg t;
+    t.p = p;
+    t.dims = p ? dims : 0;
+    return t;
+}
+static int check_tol(const TolArg& t, const char* what)
+{
+    if (t.dims < 0 || t.dims > B200ODE_TOL_FULL) return fail(B200ODE_EINVAL, "%s_dims = %d", what, t.dims);
+    return 0;
+}
+
 static int check_args(b200ode_rhs_t H, int solver, long long B, int neq, const void* u0,
                       const void* data, int np, int nt, const void* teval, const void* usol,
                       const void* success)
@@ -578,11 +604,11 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
                         long long u0_stride, const void* data, long long data_stride, int np,
                         int nt, const double* teval, double* usol, double rtol, double atol,
                         int mxstep, int* success, int* counters, int exit_on_warning,
-                        void* stream, const double* rtol_b = nullptr,
-                        const double* atol_b = nullptr)
+                        void* stream, TolArg rt = TolArg(), TolArg at = TolArg())
 {
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
+    if ((rc = check_tol(rt, "rtol")) || (rc = check_tol(at, "atol"))) return rc;
     if (u0_stride != 0 && u0_stride < neq) return fail(B200ODE_EINVAL, "u0_stride = %lld", u0_stride);
     PerDevice* P;
     rc = device_state(H, -1, &P);
@@ -602,8 +628,10 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
     a.usol = usol;
     a.rtol = rtol;
     a.atol = atol;
-    a.rtol_b = rtol_b;
-    a.atol_b = atol_b;
+    a.rtol_b = rt.p;
+    a.atol_b = at.p;
+    a.rtol_sb = rt.sb(neq), a.rtol_vec = rt.vec();
+    a.atol_sb = at.sb(neq), a.atol_vec = at.vec();
     a.mxstep = mxstep;
     a.exit_on_warning = exit_on_warning;
     a.success = success;
@@ -760,10 +788,13 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
                       long long u0_stride, const void* data, long long data_stride, int np,
                       int nt, const double* teval, double* usol, double rtol, double atol,
                       int mxstep, int* success, int* counters, int exit_on_warning, int device,
-                      const double* rtol_b = nullptr, const double* atol_b = nullptr)
+                      TolArg rt = TolArg(), TolArg at = TolArg())
 {
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
+    if ((rc = check_tol(rt, "rtol")) || (rc = check_tol(at, "atol"))) return rc;
+    const double* rtol_b = rt.p;
+    const double* atol_b = at.p;
     if (device < 0) return fail(B200ODE_EINVAL, "device = %d", device);
     if (u0_stride != 0 && u0_stride < neq) return fail(B200ODE_EINVAL, "u0_stride = %lld", u0_stride);
     if (B == 0) return 0;
@@ -789,14 +820,14 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     const size_t rec = data_stride != 0 ? (size_t)(data_stride > 0 ? data_stride : -data_stride)
                                         : (size_t)(np > 0 ? np * 8 : 0);
     const size_t data_bytes = data ? (data_stride > 0 ? (size_t)data_stride * (size_t)B : rec) : 0;
-    const size_t tol_bytes = sizeof(double) * (size_t)B;
+    const size_t rtol_bytes = sizeof(double) * rt.count(B, neq), atol_bytes = sizeof(double) * at.count(B, neq);
     // u0 rows wider than neq travel as the padded block they are (one copy; the kernels take
     // the stride), not as B small copies
     const size_t u0_doubles = u0_stride ? (size_t)(B - 1) * (size_t)u0_stride + (size_t)neq : (size_t)neq;
     const size_t in_bytes = align256(sizeof(double) * nt) +
                             align256(sizeof(double) * u0_doubles) +
-                            align256(data_bytes) + (rtol_b ? align256(tol_bytes) : 0) +
-                            (atol_b ? align256(tol_bytes) : 0);
+                            align256(data_bytes) + (rtol_b ? align256(rtol_bytes) : 0) +
+                            (atol_b ? align256(atol_bytes) : 0);
     // chunk size: at least 4 trajectories per resident lane (a persistent grid needs a few
     // per lane to balance), about 1/8 of the ensemble, at most 1 GiB of rows per buffer
     // (when PCIe binds, what is exposed is the first chunk's kernel and nothing else)
@@ -817,8 +848,8 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     const CUdeviceptr d_te = mem.take(sizeof(double) * nt);
     const CUdeviceptr d_u0 = mem.take(sizeof(double) * u0_doubles);
     const CUdeviceptr d_data = mem.take(data_bytes);
-    const CUdeviceptr d_rtol = rtol_b ? mem.take(tol_bytes) : 0;
-    const CUdeviceptr d_atol = atol_b ? mem.take(tol_bytes) : 0;
+    const CUdeviceptr d_rtol = rtol_b ? mem.take(rtol_bytes) : 0;
+    const CUdeviceptr d_atol = atol_b ? mem.take(atol_bytes) : 0;
     CUdeviceptr d_usol[3], d_ok[3], d_cnt[3] = {0, 0, 0};
     for (int i = 0; i < nbuf; i++) {
         d_usol[i] = mem.take(row_bytes * (size_t)chunk);
@@ -838,8 +869,8 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     CU(cuMemcpyHtoDAsync_v2(d_te, teval, sizeof(double) * nt, sk[0].s));
     CU(cuMemcpyHtoDAsync_v2(d_u0, u0, sizeof(double) * u0_doubles, sk[0].s));
     if (data_bytes) CU(cuMemcpyHtoDAsync_v2(d_data, data, data_bytes, sk[0].s));
-    if (rtol_b) CU(cuMemcpyHtoDAsync_v2(d_rtol, rtol_b, tol_bytes, sk[0].s));
-    if (atol_b) CU(cuMemcpyHtoDAsync_v2(d_atol, atol_b, tol_bytes, sk[0].s));
+    if (rtol_b) CU(cuMemcpyHtoDAsync_v2(d_rtol, rtol_b, rtol_bytes, sk[0].s));
+    if (atol_b) CU(cuMemcpyHtoDAsync_v2(d_atol, atol_b, atol_bytes, sk[0].s));
     CU(cuEventRecord(ev_in.e, sk[0].s));
     CU(cuStreamWaitEvent(sk[1].s, ev_in.e, 0));
 
@@ -873,8 +904,10 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
         a.usol = reinterpret_cast<double*>(d_usol[i]);
         a.rtol = rtol;
         a.atol = atol;
-        a.rtol_b = rtol_b ? reinterpret_cast<const double*>(d_rtol) + b0 : nullptr;
-        a.atol_b = atol_b ? reinterpret_cast<const double*>(d_atol) + b0 : nullptr;
+        a.rtol_b = rtol_b ? reinterpret_cast<const double*>(d_rtol) + b0 * rt.sb(neq) : nullptr;
+        a.atol_b = atol_b ? reinterpret_cast<const double*>(d_atol) + b0 * at.sb(neq) : nullptr;
+        a.rtol_sb = rt.sb(neq), a.rtol_vec = rt.vec();
+        a.atol_sb = at.sb(neq), a.atol_vec = at.vec();
         a.mxstep = mxstep;
         a.exit_on_warning = exit_on_warning;
         a.success = reinterpret_cast<int*>(d_ok[i]);
@@ -935,7 +968,7 @@ extern "C" int b200ode_solve(b200ode_rhs_t H, const b200ode_problem* p, int devi
     return solve_host(H->solver, H, p->B, p->neq, p->u0, p->u0_stride, p->data, p->data_stride,
                       p->np, p->nt, p->teval, p->usol, p->rtol, p->atol, p->mxstep, p->success,
                       p->counters, H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, device,
-                      p->rtol_b, p->atol_b);
+                      tol_arg(p->rtol_b, p->rtol_dims), tol_arg(p->atol_b, p->atol_dims));
 }
 
 extern "C" int b200ode_solve_device(b200ode_rhs_t H, const b200ode_problem* p, void* stream)
@@ -945,8 +978,8 @@ extern "C" int b200ode_solve_device(b200ode_rhs_t H, const b200ode_problem* p, v
     return solve_device(H->solver, H, p->B, p->neq, p->u0, p->u0_stride, p->data,
                         p->data_stride, p->np, p->nt, p->teval, p->usol, p->rtol, p->atol,
                         p->mxstep, p->success, p->counters,
-                        H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, stream, p->rtol_b,
-                        p->atol_b);
+                        H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, stream,
+                        tol_arg(p->rtol_b, p->rtol_dims), tol_arg(p->atol_b, p->atol_dims));
 }
 
 // ---------------------------------------------------------------- solve_ivp

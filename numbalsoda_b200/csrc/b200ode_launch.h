@@ -40,8 +40,11 @@ typedef struct B200OdeLaunch {
     const double* t_eval;     /* [nt] */
     double* usol;             /* [B,nt,n], the reference's row layout per trajectory */
     double rtol, atol;
-    const double* rtol_b;     /* [B] per-trajectory tolerances, or null: the scalars apply */
-    const double* atol_b;
+    const double* rtol_b;     /* tolerance arrays, or null: the scalars apply.  Trajectory b's */
+    const double* atol_b;     /* value is rtol_b[b * rtol_sb] -- or, with rtol_vec, its value for */
+    long long rtol_sb;        /* component i is rtol_b[b * rtol_sb + i]: [B] = (1, 0), [neq] shared */
+    long long atol_sb;        /* by all = (0, 1), [B,neq] = (neq, 1) as (sb, vec) */
+    int rtol_vec, atol_vec;
     int mxstep;
     int exit_on_warning;      /* lsoda only */
     int neq;                  /* system size (run-time for the warp-per-trajectory kernel) */

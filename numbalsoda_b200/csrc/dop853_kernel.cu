@@ -295,6 +295,12 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     // also in shared memory for the same reason
 #define RTOL span[4 + B200_THREADS + threadIdx.x]
 #define ATOL span[4 + 2 * B200_THREADS + threadIdx.x]
+    // Per-component tolerances (the reference's itol = 1 branches,
+    // dop853_module.f90:603-612, :779-803): read from global memory where they are used -- twice
+    // per trajectory in hinit, once per step in the error norm -- so that the scalar case keeps
+    // its registers and shared memory.  rtol_vec / atol_vec are uniform over the launch.
+#define RT_I(i, scalar) (L.rtol_vec ? __ldg(L.rtol_b + (long long)b * L.rtol_sb + (i)) : (scalar))
+#define AT_I(i, scalar) (L.atol_vec ? __ldg(L.atol_b + (long long)b * L.atol_sb + (i)) : (scalar))
 
     double y[N], y1[N], k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], k8[N], k9[N], k10[N];
     double pl[STAGED ? B200ODE_NPMAX : 1];
@@ -329,8 +335,8 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                 } else {
                     pp = const_cast<double*>(pg);
                 }
-                const double rtol = L.rtol_b ? L.rtol_b[b] : L.rtol;
-                const double atol = L.atol_b ? L.atol_b[b] : L.atol;
+                const double rtol = (L.rtol_b && !L.rtol_vec) ? L.rtol_b[(long long)b * L.rtol_sb] : L.rtol;
+                const double atol = (L.atol_b && !L.atol_vec) ? L.atol_b[(long long)b * L.atol_sb] : L.atol;
                 RTOL = rtol;
                 ATOL = atol;
                 x = SPAN_X0;
@@ -342,7 +348,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     // hinit, module :745-823 (itol = 0, iord = 8)
                     double dnf = 0.0, dny = 0.0;
                     FOR_N {
-                        double sk = atol + rtol * fabs(y[i]);
+                        double sk = AT_I(i, atol) + RT_I(i, rtol) * fabs(y[i]);
                         double qq = k1[i] / sk;
                         dnf = dnf + qq * qq;
                         qq = y[i] / sk;
@@ -357,7 +363,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     b200ode_user_rhs(x + hh, y1, k2, pp);
                     double der2 = 0.0;
                     FOR_N {
-                        double sk = atol + rtol * fabs(y[i]);
+                        double sk = AT_I(i, atol) + RT_I(i, rtol) * fabs(y[i]);
                         double qq = (k2[i] - k1[i]) / sk;
                         der2 = der2 + qq * qq;
                     }
@@ -457,7 +463,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     // reciprocals; err holds the *square* of the reference's err (the test
                     // err <= 1 is unchanged by that), ifac = safe / err**(1/8)
                     FOR_N {
-                        const double isk = b200_rcp(atol + rtol * fmax_(fabs(y[i]), fabs(k5[i])));
+                        const double isk = b200_rcp(AT_I(i, atol) + RT_I(i, rtol) * fmax_(fabs(y[i]), fabs(k5[i])));
                         double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
                         double qq = erri * isk;
                         err2 = err2 + qq * qq;
@@ -474,7 +480,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     hnew = h * fmin_(DP_FAC2, fmax_(DP_FAC1, ifac));
                 } else {
                     FOR_N {
-                        double sk = atol + rtol * fmax_(fabs(y[i]), fabs(k5[i]));
+                        double sk = AT_I(i, atol) + RT_I(i, rtol) * fmax_(fabs(y[i]), fabs(k5[i]));
                         double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
                         double qq = erri / sk;
                         err2 = err2 + qq * qq;

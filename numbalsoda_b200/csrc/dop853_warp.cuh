@@ -59,10 +59,15 @@ WV_FN double dw_ordered_sum(const double* t, int n)
 
 // dop853_wrapper for one trajectory.  `w`: B200ODE_DOP853W_DOUBLES(n) doubles of
 // (shared) memory; usol: this trajectory's [nt, n] block.
+// rtol_v / atol_v: per-component tolerances (the reference's itol = 1 branches, module
+// :603-612, :779-803), or null: the scalars apply to every component
 WV_FN void dop853_warp_solve(int n, double* w, const double* u0, double* pp, int nt,
                              const double* te, double* usol, double rtol, double atol, int mxstep,
-                             Dop853WarpStats& st)
+                             Dop853WarpStats& st, const double* rtol_v = nullptr,
+                             const double* atol_v = nullptr)
 {
+#define DW_RT(i) (rtol_v ? rtol_v[i] : rtol)
+#define DW_AT(i) (atol_v ? atol_v[i] : atol)
     double *y = w, *y1 = y + n, *k1 = y1 + n, *k2 = k1 + n, *k3 = k2 + n, *k4 = k3 + n;
     double *k5 = k4 + n, *k6 = k5 + n, *k7 = k6 + n, *k8 = k7 + n, *k9 = k8 + n, *k10 = k9 + n;
     double* cont = k10 + n;     // 8 n
@@ -91,7 +96,7 @@ WV_FN void dop853_warp_solve(int n, double* w, const double* u0, double* pp, int
     {
         // hinit, module :745-823 (itol = 0, iord = 8)
         DW_OWN(i) {
-            const double sk = atol + rtol * fabs(y[i]);
+            const double sk = DW_AT(i) + DW_RT(i) * fabs(y[i]);
             double q = k1[i] / sk;
             t1[i] = q * q;
             q = y[i] / sk;
@@ -108,7 +113,7 @@ WV_FN void dop853_warp_solve(int n, double* w, const double* u0, double* pp, int
         DW_OWN(i) y1[i] = y[i] + hh * k1[i];
         DW_RHS(x + hh, y1, k2);
         DW_OWN(i) {
-            const double sk = atol + rtol * fabs(y[i]);
+            const double sk = DW_AT(i) + DW_RT(i) * fabs(y[i]);
             const double q = (k2[i] - k1[i]) / sk;
             t1[i] = q * q;
         }
@@ -179,7 +184,7 @@ WV_FN void dop853_warp_solve(int n, double* w, const double* u0, double* pp, int
             k4[i] = DP_B1 * k1[i] + DP_B6 * k6[i] + DP_B7 * k7[i] + DP_B8 * k8[i] +
                     DP_B9 * k9[i] + DP_B10 * k10[i] + DP_B11 * k2[i] + DP_B12 * k3[i];
             k5[i] = y[i] + h * k4[i];
-            const double sk = atol + rtol * dw_max(fabs(y[i]), fabs(k5[i]));
+            const double sk = DW_AT(i) + DW_RT(i) * dw_max(fabs(y[i]), fabs(k5[i]));
             double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
             double q = erri / sk;
             t2[i] = q * q;

@@ -24,8 +24,11 @@ b200ode_dop853w_kernel(const B200OdeLaunch L)
         double* pp = reinterpret_cast<double*>(const_cast<char*>(L.data + b * L.data_stride));
         Dop853WarpStats st;
         dop853_warp_solve(n, b200_smem, L.u0 + b * L.u0_stride, pp, nt, L.t_eval,
-                          L.usol + (size_t)b * (size_t)nt * (size_t)n, L.rtol_b ? L.rtol_b[b] : L.rtol,
-                          L.atol_b ? L.atol_b[b] : L.atol, L.mxstep, st);
+                          L.usol + (size_t)b * (size_t)nt * (size_t)n,
+                          (L.rtol_b && !L.rtol_vec) ? L.rtol_b[b * L.rtol_sb] : L.rtol,
+                          (L.atol_b && !L.atol_vec) ? L.atol_b[b * L.atol_sb] : L.atol, L.mxstep, st,
+                          L.rtol_vec ? L.rtol_b + b * L.rtol_sb : nullptr,
+                          L.atol_vec ? L.atol_b + b * L.atol_sb : nullptr);
         if (WV_LANE == 0) {
             // c_interface :125-128
             L.success[b] = (st.idid < 0) ? 0 : 1;

@@ -96,6 +96,18 @@ struct LsRun {
     int istate;   // 1 running; 2 finished; <= 0 failed (as LSODA.cpp:782-976; 0 = t_eval not monotone)
 };
 
+// Tolerances of one trajectory: the two scalars lsoda_update spreads over its private vectors
+// (LSODA.cpp:2267-2270), or -- SURVEY.md section 8f rank 1 -- one value per component, the
+// reference's itol_ = 3 / 4 cases (ewset, LSODA.cpp:1368-1390; checks :500-520; h0's tol
+// :624-640).  A null vector means the scalar applies to every component.
+struct LsTol {
+    double rtol, atol;
+    const double* rv;  // [n] or null
+    const double* av;  // [n] or null
+    LS_MFN double rt(int i) const { return rv ? rv[i] : rtol; }
+    LS_MFN double at(int i) const { return av ? av[i] : atol; }
+};
+
 // std::max / std::min as the reference uses them (they differ from fmax/fmin on NaN)
 LS_FN double ls_max(double a, double b) { return (a < b) ? b : a; }
 LS_FN double ls_min(double a, double b) { return (b < a) ? b : a; }
@@ -335,7 +347,7 @@ LS_FN int ls_orderswitch(LsLane& s, V& v, const B200LsodaTables* T, double rhup,
 // Returns true when the trajectory is already finished (R.istate says how).
 template <class V>
 LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int nt,
-                    const double* teval, double* usol, double rtol, double atol)
+                    const double* teval, double* usol, const LsTol& tol)
 {
     const int n = v.size();
     v.begin(u0, usol);  // usol row 0 = u0 (wrapper.cpp:25-28), y = u0
@@ -366,13 +378,13 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int
     const double t0 = teval[0], tout = teval[1];
     s.tn = t0;
     s.meth = 1;
-    if (rtol < 0.0 || atol < 0.0) {  // LSODA.cpp:509-520
+    if (v.tol_negative(tol)) {  // LSODA.cpp:500-520
         R.istate = -3;
         return true;
     }
     v.rhs_yh2(t0, pp);  // yh[2] = f(t0, y), yh[1] = y (:572-578)
     s.nfe = 1;
-    if (v.set_ewt(rtol, atol)) {
+    if (v.set_ewt(tol)) {
         // LSODA.cpp:585-590 leaves through terminate2 with istate still 1, which
         // wrapper.cpp:41 does not treat as a failure: every later call re-initialises,
         // fails the same way and hands u0 back.
@@ -393,12 +405,12 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int
         R.istate = -3;
         return true;
     }
-    double tol = rtol;
-    if (tol <= 0.0) tol = v.tol_floor(atol, tol);  // :626-634
-    tol = ls_max(tol, 100.0 * LS_ETA);
-    tol = ls_min(tol, 0.001);
+    double tl = v.tol_rtol_max(tol);             // :624-628
+    if (tl <= 0.0) tl = v.tol_floor(tol, tl);    // :629-640
+    tl = ls_max(tl, 100.0 * LS_ETA);
+    tl = ls_min(tl, 0.001);
     double sum = v.norm_yh(2);
-    sum = 1.0 / (tol * w0 * w0) + tol * sum * sum;
+    sum = 1.0 / (tl * w0 * w0) + tl * sum * sum;
     double h0 = 1.0 / sqrt(sum);
     h0 = ls_min(h0, tdist);
     h0 = h0 * ((tout - t0 >= 0.0) ? 1.0 : -1.0);
@@ -432,7 +444,7 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int
 // in lock step -- pins the lanes together between blocks.
 template <class V>
 LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, double* pp, int nt,
-                      const double* teval, double* usol, double rtol, double atol,
+                      const double* teval, double* usol, const LsTol& tol,
                       unsigned long long mxstep_u, int exit_on_warning, unsigned lanes)
 {
 #define LS_SYNC() v.sync(lanes)
@@ -507,7 +519,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
     if (!fin && s.phase == LS_P_STEP) {
         // ewset (:787-798).  Before the first step yh[1] is u0, whose weights ls_begin
         // checked, and the test for non-positive weights is skipped (:776).
-        const bool bad_ewt = v.set_ewt(rtol, atol);
+        const bool bad_ewt = v.set_ewt(tol);
         const double tolsf = LS_ETA * v.norm_yh(1);
         if (s.nst != 0 && (unsigned long long)(long long)(s.nst - R.nslast) >= mxstep_u) {  // :778
             R.istate = -1;

@@ -34,6 +34,19 @@
 
 __constant__ B200LsodaTables b200_lsoda_tables = B200_LSODA_TABLES_INIT;
 
+// The tolerances of trajectory b.  Per-component vectors (rtol_vec / atol_vec) are read from
+// global memory where they are used (once per step, in ewset); the pointers are rebuilt from
+// the launch block and b instead of being carried in registers.
+__device__ __forceinline__ LsTol lane_tol(const B200OdeLaunch& L, long long b, double rtol, double atol)
+{
+    LsTol t;
+    t.rtol = rtol;
+    t.atol = atol;
+    t.rv = L.rtol_vec ? L.rtol_b + b * L.rtol_sb : nullptr;
+    t.av = L.atol_vec ? L.atol_b + b * L.atol_sb : nullptr;
+    return t;
+}
+
 template <bool STAGED>
 __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
 {
@@ -67,8 +80,8 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
                 exhausted = true;
             } else {
                 b = bn;
-                if (L.rtol_b) rtol = L.rtol_b[b];
-                if (L.atol_b) atol = L.atol_b[b];
+                if (L.rtol_b && !L.rtol_vec) rtol = L.rtol_b[b * L.rtol_sb];
+                if (L.atol_b && !L.atol_vec) atol = L.atol_b[b * L.atol_sb];
                 const double* pg = reinterpret_cast<const double*>(L.data + b * L.data_stride);
                 if (STAGED) {
 #pragma unroll
@@ -78,7 +91,7 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
                     pp = const_cast<double*>(pg);
                 }
                 done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te,
-                                L.usol + (size_t)b * (size_t)nt * N, rtol, atol);
+                                L.usol + (size_t)b * (size_t)nt * N, lane_tol(L, b, rtol, atol));
             }
         }
         // lanes with a running trajectory take one pass of the state machine together
@@ -86,7 +99,7 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
         if (lanes == 0 && !__any_sync(FULL, b >= 0)) break;
         if (b >= 0 && !done)
             done = ls_advance(s, R, v, T, pp, nt, te, L.usol + (size_t)b * (size_t)nt * N,
-                              rtol, atol, mxstep_u, L.exit_on_warning, lanes);
+                              lane_tol(L, b, rtol, atol), mxstep_u, L.exit_on_warning, lanes);
         if (b >= 0 && done) {
             // wrapper.cpp:41-45: istate <= 0 -> success = 0
             L.success[b] = (R.istate > 0) ? 1 : 0;

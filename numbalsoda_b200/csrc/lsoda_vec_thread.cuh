@@ -67,12 +67,12 @@ struct LsThreadVec {
         return norm(savf);
     }
 
-    // ewset with itol = 2 and inversion (LSODA.cpp:787-798); true if a weight is <= 0
-    LS_MFN bool set_ewt(double rtol, double atol)
+    // ewset (LSODA.cpp:1368-1390) and inversion (:787-798); true if a weight is <= 0
+    LS_MFN bool set_ewt(const LsTol& tol)
     {
         bool bad = false;
         LS_FOR_N {
-            ewt[i] = rtol * fabs(YH(1, i)) + atol;
+            ewt[i] = tol.rt(i) * fabs(YH(1, i)) + tol.at(i);
             if (ewt[i] <= 0.0) bad = true;
             ewt[i] = ls_div(1.0, ewt[i]);
         }
@@ -187,13 +187,25 @@ struct LsThreadVec {
             YH(2, i) = savf[i];
         }
     }
-    LS_MFN double tol_floor(double atol, double tol) const
+    LS_MFN bool tol_negative(const LsTol& tol) const
+    {
+        bool neg = false;
+        LS_FOR_N if (tol.rt(i) < 0.0 || tol.at(i) < 0.0) neg = true;
+        return neg;
+    }
+    LS_MFN double tol_rtol_max(const LsTol& tol) const
+    {
+        double t = tol.rt(0);
+        LS_FOR_N if (i > 0) t = ls_max(t, tol.rt(i));
+        return t;
+    }
+    LS_MFN double tol_floor(const LsTol& tol, double t) const
     {
         LS_FOR_N {
             const double ayi = fabs(y[i]);
-            if (ayi != 0.0) tol = ls_max(tol, atol / ayi);
+            if (ayi != 0.0) t = ls_max(t, tol.at(i) / ayi);
         }
-        return tol;
+        return t;
     }
     LS_MFN void scale_yh2(double h0) { LS_FOR_N YH(2, i) = YH(2, i) * h0; }
 

@@ -111,11 +111,11 @@ struct LsWarpVec {
         return norm_ptr(savf);
     }
 
-    LS_MFN bool set_ewt(double rtol, double atol)
+    LS_MFN bool set_ewt(const LsTol& tol)
     {
         bool bad = false;
         WV_FOR_OWN(i) {
-            double w = rtol * fabs(WYH(1, i)) + atol;
+            double w = tol.rt(i) * fabs(WYH(1, i)) + tol.at(i);
             if (w <= 0.0) bad = true;
             ewt[i] = ls_div(1.0, w);
         }
@@ -249,14 +249,28 @@ struct LsWarpVec {
         WV_FOR_OWN(i) WYH(1, i) = y[i];
         WV_SYNC();
     }
-    LS_MFN double tol_floor(double atol, double tol) const
+    LS_MFN bool tol_negative(const LsTol& tol) const
+    {
+        bool neg = false;
+#pragma unroll 1
+        WV_FOR_OWN(i) if (tol.rt(i) < 0.0 || tol.at(i) < 0.0) neg = true;
+        return wv_any(neg);
+    }
+    LS_MFN double tol_rtol_max(const LsTol& tol) const
+    {
+        double t = tol.rt(0);
+#pragma unroll 1
+        WV_FOR_OWN(i) t = ls_max(t, tol.rt(i));
+        return wv_max(t);
+    }
+    LS_MFN double tol_floor(const LsTol& tol, double t) const
     {
 #pragma unroll 1
         WV_FOR_OWN(i) {
             const double ayi = fabs(y[i]);
-            if (ayi != 0.0) tol = ls_max(tol, atol / ayi);
+            if (ayi != 0.0) t = ls_max(t, tol.at(i) / ayi);
         }
-        return wv_max(tol);
+        return wv_max(t);
     }
     LS_MFN void scale_yh2(double h0)
     {

@@ -43,13 +43,16 @@ b200ode_lsodaw_kernel(const B200OdeLaunch L)
         if (b >= L.B) break;
         double* pp = reinterpret_cast<double*>(const_cast<char*>(L.data + b * L.data_stride));
         double* usol = L.usol + (size_t)b * (size_t)nt * (size_t)n;
-        const double rtol = L.rtol_b ? L.rtol_b[b] : L.rtol;
-        const double atol = L.atol_b ? L.atol_b[b] : L.atol;
+        LsTol tol;
+        tol.rtol = (L.rtol_b && !L.rtol_vec) ? L.rtol_b[b * L.rtol_sb] : L.rtol;
+        tol.atol = (L.atol_b && !L.atol_vec) ? L.atol_b[b * L.atol_sb] : L.atol;
+        tol.rv = L.rtol_vec ? L.rtol_b + b * L.rtol_sb : nullptr;
+        tol.av = L.atol_vec ? L.atol_b + b * L.atol_sb : nullptr;
         LsLane s;
         LsRun R;
-        bool done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te, usol, rtol, atol);
+        bool done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te, usol, tol);
         while (!done)
-            done = ls_advance(s, R, v, T, pp, nt, te, usol, rtol, atol, mxstep_u,
+            done = ls_advance(s, R, v, T, pp, nt, te, usol, tol, mxstep_u,
                               L.exit_on_warning, 0xffffffffu);
         if (WV_LANE == 0) {
             // wrapper.cpp:41-45: istate <= 0 -> success = 0

@@ -27,6 +27,9 @@ typedef struct {
     double rtol, atol;
     int mxstep, exit_on_warning;
     int *success, *counters;
+    /* per-component tolerance vectors of trajectory b: rtol_v + b * rtol_vs (NULL: the scalar) */
+    const double *rtol_v, *atol_v;
+    long rtol_vs, atol_vs;
     atomic_long next;
 } job_t;
 
@@ -46,8 +49,9 @@ static void *worker(void *arg)
             int ok = 0;
             if (j->solver == 0) {
                 oracle_dop853_stats st;
-                oracle_dop853(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
-                              j->mxstep, &ok, &st);
+                oracle_dop853_v(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
+                                j->rtol_v ? j->rtol_v + b * j->rtol_vs : 0,
+                                j->atol_v ? j->atol_v + b * j->atol_vs : 0, j->mxstep, &ok, &st);
                 if (j->counters) {
                     int *c = j->counters + b * ORACLE_NCOUNTERS;
                     c[0] = st.nstep, c[1] = st.nfcn, c[2] = st.naccpt, c[3] = st.nrejct;
@@ -55,8 +59,10 @@ static void *worker(void *arg)
                 }
             } else {
                 oracle_lsoda_stats st;
-                oracle_lsoda(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
-                             j->mxstep, &ok, j->exit_on_warning, &st);
+                oracle_lsoda_v(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
+                               j->rtol_v ? j->rtol_v + b * j->rtol_vs : 0,
+                               j->atol_v ? j->atol_v + b * j->atol_vs : 0, j->mxstep, &ok,
+                               j->exit_on_warning, &st);
                 if (j->counters) {
                     int *c = j->counters + b * ORACLE_NCOUNTERS;
                     c[0] = st.nst, c[1] = st.nfe, c[2] = st.nje, c[3] = st.nswitch;
@@ -69,14 +75,16 @@ static void *worker(void *arg)
     return 0;
 }
 
-int oracle_solve_batch(int solver, oracle_rhs_fn f, long B, int neq, const double *u0,
-                       long u0_stride, const void *data, long data_stride, int nt,
-                       const double *teval, double *usol, double rtol, double atol,
-                       int mxstep, int exit_on_warning, int *success, int *counters,
-                       int nthreads)
+int oracle_solve_batch_v(int solver, oracle_rhs_fn f, long B, int neq, const double *u0,
+                         long u0_stride, const void *data, long data_stride, int nt,
+                         const double *teval, double *usol, double rtol, double atol,
+                         const double *rtol_v, long rtol_vs, const double *atol_v, long atol_vs,
+                         int mxstep, int exit_on_warning, int *success, int *counters,
+                         int nthreads)
 {
     job_t j = {solver, f,    B,    neq,  u0,     u0_stride,       data,    data_stride,
-               nt,     teval, usol, rtol, atol,   mxstep, exit_on_warning, success, counters, 0};
+               nt,     teval, usol, rtol, atol,   mxstep, exit_on_warning, success, counters,
+               rtol_v, atol_v, rtol_vs, atol_vs, 0};
     pthread_t th[256];
     if (nthreads <= 0)
         nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
@@ -90,6 +98,17 @@ int oracle_solve_batch(int solver, oracle_rhs_fn f, long B, int neq, const doubl
     for (int i = 1; i < nthreads; i++)
         pthread_join(th[i], 0);
     return nthreads;
+}
+
+int oracle_solve_batch(int solver, oracle_rhs_fn f, long B, int neq, const double *u0,
+                       long u0_stride, const void *data, long data_stride, int nt,
+                       const double *teval, double *usol, double rtol, double atol,
+                       int mxstep, int exit_on_warning, int *success, int *counters,
+                       int nthreads)
+{
+    return oracle_solve_batch_v(solver, f, B, neq, u0, u0_stride, data, data_stride, nt, teval, usol,
+                                rtol, atol, 0, 0, 0, 0, mxstep, exit_on_warning, success, counters,
+                                nthreads);
 }
 
 /* ---- solve_ivp ensembles: t_eval given (y_out[B,nt,neq]) or `cap` rows per trajectory

@@ -62,15 +62,20 @@ static inline double dmax(double a, double b) { return (b > a || isnan(a)) ? b :
 static inline double dmin(double a, double b) { return (b < a || isnan(a)) ? b : a; }
 static inline double dsign(double a, double b) { return signbit(b) ? -fabs(a) : fabs(a); }
 
-/* hinit, dop853_module.f90:745-823 (itol == 0 branch, iord == 8). */
+/* rtol_v / atol_v: per-component tolerances (itol = 1: module :603-612, :779-784, :799-803), or
+ * NULL: the scalars apply (itol = 0, what the reference's wrapper always passes) */
+#define RT(i) (rtol_v ? rtol_v[i] : rtol)
+#define AT(i) (atol_v ? atol_v[i] : atol)
+
+/* hinit, dop853_module.f90:745-823 (iord == 8). */
 static double first_step(oracle_rhs_fn f, void *data, int n, double x, const double *y,
                          double posneg, const double *f0, double hmax, double atol,
-                         double rtol, double *f1, double *y1)
+                         double rtol, const double *rtol_v, const double *atol_v, double *f1, double *y1)
 {
     double dnf = 0.0, dny = 0.0, sk, h, h1, der2, der12, q;
     int i;
     for (i = 0; i < n; i++) {
-        sk = atol + rtol * fabs(y[i]);
+        sk = AT(i) + RT(i) * fabs(y[i]);
         q = f0[i] / sk;
         dnf = dnf + q * q;
         q = y[i] / sk;
@@ -87,7 +92,7 @@ static double first_step(oracle_rhs_fn f, void *data, int n, double x, const dou
     f(x + h, y1, f1, data);
     der2 = 0.0;
     for (i = 0; i < n; i++) {
-        sk = atol + rtol * fabs(y[i]);
+        sk = AT(i) + RT(i) * fabs(y[i]);
         q = (f1[i] - f0[i]) / sk;
         der2 = der2 + q * q;
     }
@@ -101,9 +106,10 @@ static double first_step(oracle_rhs_fn f, void *data, int n, double x, const dou
     return dsign(h, posneg);
 }
 
-void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
-                   const double *teval, double *usol, double rtol, double atol, int mxstep,
-                   int *success, oracle_dop853_stats *st)
+void oracle_dop853_v(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                     const double *teval, double *usol, double rtol, double atol,
+                     const double *rtol_v, const double *atol_v, int mxstep,
+                     int *success, oracle_dop853_stats *st)
 {
     const int n = neq;
     oracle_dop853_stats local;
@@ -158,7 +164,7 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
     f(x, y, k1, data);
     hmax = fabs(hmax);
     if (h == 0.0)
-        h = first_step(f, data, n, x, y, posneg, k1, hmax, atol, rtol, k2, y1);
+        h = first_step(f, data, n, x, y, posneg, k1, hmax, atol, rtol, rtol_v, atol_v, k2, y1);
     st->nfcn += 2;
     xold = x;
     /* first solout call (nr == 1), c_interface :56-58 */
@@ -234,7 +240,7 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
         err2 = 0.0;
         for (i = 0; i < n; i++) {
             double q;
-            sk = atol + rtol * dmax(fabs(y[i]), fabs(k5[i]));
+            sk = AT(i) + RT(i) * dmax(fabs(y[i]), fabs(k5[i]));
             erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
             q = erri / sk;
             err2 = err2 + q * q;
@@ -393,4 +399,13 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
     if (st->idid < 0)
         *success = 0; /* c_interface :125-128 */
     free(w);
+}
+#undef RT
+#undef AT
+
+void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                   const double *teval, double *usol, double rtol, double atol, int mxstep,
+                   int *success, oracle_dop853_stats *st)
+{
+    oracle_dop853_v(f, neq, u0, data, nt, teval, usol, rtol, atol, NULL, NULL, mxstep, success, st);
 }

@@ -777,9 +777,15 @@ static void interpolate(const lsoda_ctx *s, double t, double *out)
             out[i] = 1.0 * s->yh[j + 1][i] + sfrac * out[i];
 }
 
-void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
-                  const double *teval, double *usol, double rtol, double atol, int mxstep,
-                  int *success, int exit_on_warning, oracle_lsoda_stats *st)
+/* rtol_v / atol_v: per-component tolerances (the reference's itol_ = 3 / 4 branches,
+ * LSODA.cpp:500-520, :625-640, :1368-1390), or NULL: the scalar applies to every component
+ * (what lsoda_update sets up, :2267-2270). */
+#define RT(i) (rtol_v ? rtol_v[i] : rtol)
+#define AT(i) (atol_v ? atol_v[i] : atol)
+void oracle_lsoda_v(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                    const double *teval, double *usol, double rtol, double atol,
+                    const double *rtol_v, const double *atol_v, int mxstep,
+                    int *success, int exit_on_warning, oracle_lsoda_stats *st)
 {
     const int n = neq;
     /* wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130) */
@@ -830,10 +836,11 @@ void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt
     s->maxord = MXORDN;
     s->jstart = 0;
     s->miter = 0;
-    if (rtol < 0. || atol < 0.) { /* LSODA.cpp:509-520 */
-        istate = -3;
-        goto done;
-    }
+    for (i = 0; i < n; i++)
+        if (RT(i) < 0. || AT(i) < 0.) { /* LSODA.cpp:503-520 */
+            istate = -3;
+            goto done;
+        }
     for (i = 0; i < n; i++)
         s->y[i] = u0[i];
     f(t0, s->y, s->yh[2], data);
@@ -843,7 +850,7 @@ void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt
     s->nq = 1;
     s->h = 1.;
     for (i = 0; i < n; i++) {
-        s->ewt[i] = rtol * fabs(s->y[i]) + atol; /* ewset, itol_ == 2 */
+        s->ewt[i] = RT(i) * fabs(s->y[i]) + AT(i); /* ewset, LSODA.cpp:1368-1390 */
         if (s->ewt[i] <= 0.) {
             /* LSODA.cpp:585-590 returns through terminate2, which leaves istate at 1,
              * so wrapper.cpp:41 does not see a failure: every lsoda_update call
@@ -869,12 +876,14 @@ void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt
         istate = -3;
         goto done;
     }
-    tol = rtol;
+    tol = RT(0); /* :624-628 */
+    for (i = 1; i < n; i++)
+        tol = dmax(tol, RT(i));
     if (tol <= 0.) {
         for (i = 0; i < n; i++) {
             double ayi = fabs(s->y[i]);
             if (ayi != 0.)
-                tol = dmax(tol, atol / ayi);
+                tol = dmax(tol, AT(i) / ayi);
         }
     }
     tol = dmax(tol, 100. * ETA);
@@ -897,7 +906,7 @@ void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt
                 break;
             }
             for (i = 0; i < n; i++) {
-                s->ewt[i] = rtol * fabs(s->yh[1][i]) + atol;
+                s->ewt[i] = RT(i) * fabs(s->yh[1][i]) + AT(i);
                 if (s->ewt[i] <= 0.) {
                     istate = -6;
                     break;
@@ -982,4 +991,14 @@ done:
         *success = 0; /* wrapper.cpp:41-45 */
     free(w);
     free(s->ipvt);
+}
+#undef RT
+#undef AT
+
+void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                  const double *teval, double *usol, double rtol, double atol, int mxstep,
+                  int *success, int exit_on_warning, oracle_lsoda_stats *st)
+{
+    oracle_lsoda_v(f, neq, u0, data, nt, teval, usol, rtol, atol, NULL, NULL, mxstep, success,
+                   exit_on_warning, st);
 }

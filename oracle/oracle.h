@@ -50,6 +50,13 @@ void oracle_dop853(oracle_rhs_fn f, int neq, const double *u0, void *data, int n
                    const double *teval, double *usol, double rtol, double atol, int mxstep,
                    int *success, oracle_dop853_stats *stats);
 
+/* ... with per-component tolerances rtol_v[neq] / atol_v[neq] (NULL: the scalar applies): the
+ * reference's itol = 1 branches, dop853_module.f90:603-612, :779-803 */
+void oracle_dop853_v(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                     const double *teval, double *usol, double rtol, double atol,
+                     const double *rtol_v, const double *atol_v, int mxstep,
+                     int *success, oracle_dop853_stats *stats);
+
 /* test-only, see dop853_oracle.c */
 void oracle_dop853_set_scipy_reject_rule(int on);
 void oracle_dop853_set_fast_ctrl(int on);
@@ -94,6 +101,13 @@ void oracle_lsoda(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt
                   const double *teval, double *usol, double rtol, double atol, int mxstep,
                   int *success, int exit_on_warning, oracle_lsoda_stats *stats);
 
+/* ... with per-component tolerances (NULL: the scalar applies): the reference's itol_ = 3 / 4
+ * branches, LSODA.cpp:500-520, :624-640, :1368-1390 */
+void oracle_lsoda_v(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                    const double *teval, double *usol, double rtol, double atol,
+                    const double *rtol_v, const double *atol_v, int mxstep,
+                    int *success, int exit_on_warning, oracle_lsoda_stats *stats);
+
 /* Ensemble helpers: the way numbalsoda is used for ensembles today is a prange
  * loop of independent calls (README.md:60-67); these do the same with OpenMP.
  * u0 is [B,n] (u0_stride = n) or a single [n] vector (u0_stride = 0); data is
@@ -104,6 +118,14 @@ int oracle_solve_batch(int solver, oracle_rhs_fn f, long B, int neq, const doubl
                        const double *teval, double *usol, double rtol, double atol,
                        int mxstep, int exit_on_warning, int *success, int *counters,
                        int nthreads);
+/* rtol_v / atol_v: trajectory b's per-component tolerances at rtol_v + b * rtol_vs (stride 0 =
+ * one vector for all), NULL = the scalar */
+int oracle_solve_batch_v(int solver, oracle_rhs_fn f, long B, int neq, const double *u0,
+                         long u0_stride, const void *data, long data_stride, int nt,
+                         const double *teval, double *usol, double rtol, double atol,
+                         const double *rtol_v, long rtol_vs, const double *atol_v, long atol_vs,
+                         int mxstep, int exit_on_warning, int *success, int *counters,
+                         int nthreads);
 #define ORACLE_NCOUNTERS 8 /* ints per trajectory written to `counters` (may be NULL) */
 
 /* Built-in right-hand sides written with the operation order numba produces for

@@ -11,6 +11,7 @@
 #include "LSODA.h"
 #undef private
 
+#include <array>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -43,6 +44,69 @@ void ref_lsoda_stats(rhs_t rhs, int neq, const double *u0, void *data, int nt,
         }
         solver.lsoda_update(rhs, neq, y, yout, &t, teval[i], &istate, data, rtol, atol,
                             exit_on_warning != 0);
+        if (solver.meth_ != meth_prev) {
+            nswitch++;
+            meth_prev = solver.meth_;
+        }
+        if (istate <= 0) {
+            *success = 0;
+            break;
+        }
+        for (int j = 0; j < neq; j++) {
+            y[j] = yout[j + 1];
+            usol[j + (size_t)neq * i] = yout[j + 1];
+        }
+        rows = i + 1;
+    }
+    if (stats) {
+        stats[0] = (int)solver.nst;
+        stats[1] = (int)solver.nfe;
+        stats[2] = (int)solver.nje;
+        stats[3] = nswitch;
+        stats[4] = (int)solver.nqu;
+        stats[5] = istate;
+        stats[6] = rows;
+        stats[7] = (int)solver.meth_;
+    }
+}
+
+// The same loop with per-component tolerances: what lsoda_update (LSODA.cpp:2247-2277) does,
+// but with the private tolerance vectors filled per component and itol_ = 4, then the public
+// LSODA::lsoda with lsoda_update's fixed options (itask = 1, iopt = 0, jt = 2).
+void ref_lsoda_stats_vtol(rhs_t rhs, int neq, const double *u0, void *data, int nt,
+                          const double *teval, double *usol, const double *rtol_v,
+                          const double *atol_v, int mxstep, int *success, int exit_on_warning,
+                          int *stats)
+{
+    LSODA solver;
+    solver.mxstep = mxstep;
+    solver.itol_ = 4;
+    std::vector<double> y(neq), yout(neq + 1);
+    int istate = 1, rows = 1, nswitch = 0;
+    size_t meth_prev = 1;
+    *success = 1;
+    for (int i = 0; i < neq; i++) {
+        y[i] = u0[i];
+        usol[i] = u0[i];
+    }
+    double t = teval[0];
+    for (int i = 1; i < nt; i++) {
+        if (teval[i] < teval[i - 1]) {
+            *success = 0;
+            istate = 0;
+            break;
+        }
+        std::array<int, 7> iworks = {{0}};
+        std::array<double, 4> rworks = {{0.0}};
+        solver.rtol_.assign(neq + 1, 0.0);
+        solver.atol_.assign(neq + 1, 0.0);
+        for (int j = 0; j < neq; j++) {
+            solver.rtol_[j + 1] = rtol_v[j];
+            solver.atol_[j + 1] = atol_v[j];
+            yout[j + 1] = y[j];
+        }
+        solver.lsoda(rhs, neq, yout, &t, teval[i], 1, &istate, 0, 2, iworks, rworks, data,
+                     exit_on_warning != 0);
         if (solver.meth_ != meth_prev) {
             nswitch++;
             meth_prev = solver.meth_;

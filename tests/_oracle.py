@@ -106,23 +106,61 @@ def ref_lsoda_wrapper(fptr, u0, t_eval, data, rtol=1e-3, atol=1e-6, mxstep=10000
     return us, ok.value == 1
 
 
+def ref_lsoda_vtol(fptr, u0, t_eval, data, rtol_v, atol_v, mxstep=10000, exit_on_warning=False):
+    """The compiled reference with per-component tolerances: its private rtol_ / atol_ vectors
+    filled per component, itol_ = 4, driven through the public LSODA::lsoda with lsoda_update's
+    fixed options (oracle/ref_shim.cpp)."""
+    u0, te, data, us = _prep(u0, t_eval, data)
+    rv = np.ascontiguousarray(rtol_v, dtype=np.float64)
+    av = np.ascontiguousarray(atol_v, dtype=np.float64)
+    assert rv.shape == av.shape == u0.shape
+    ok = ct.c_int(999)
+    st = (ct.c_int * 8)()
+    ref_probe.ref_lsoda_stats_vtol(ct.c_void_p(fptr), len(u0), _p(u0), _p(data), len(te), _p(te),
+                                   _p(us), _p(rv), _p(av), int(mxstep), ct.byref(ok),
+                                   int(exit_on_warning), st)
+    return us, ok.value == 1, list(st)
+
+
+def _tol_arg(x, B, n):
+    """-> (scalar, vector or None, stride between trajectories) of a tolerance given as a
+    scalar, [B] (per trajectory), [n] / [1,n] (per component) or [B,n]"""
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 0:
+        return float(a), None, 0
+    if a.ndim == 1 and a.shape[0] == B and not (B == 1 and n != 1):
+        return 0.0, np.ascontiguousarray(np.repeat(a[:, None], n, axis=1)), n
+    if a.ndim == 1 and a.shape[0] == n:
+        return 0.0, np.ascontiguousarray(a), 0
+    if a.ndim == 2 and a.shape == (1, n):
+        return 0.0, np.ascontiguousarray(a[0]), 0
+    if a.ndim == 2 and a.shape == (B, n):
+        return 0.0, np.ascontiguousarray(a), n
+    raise ValueError("tolerance of shape %r for B = %d, n = %d" % (a.shape, B, n))
+
+
 def solve_batch(solver, fptr, u0, t_eval, data, rtol, atol, mxstep=10000,
                 exit_on_warning=False, nthreads=0):
-    """solver: 'dop853' | 'lsoda'.  u0 [B,n] or [n]; data [B,p] or [p]."""
+    """solver: 'dop853' | 'lsoda'.  u0 [B,n] or [n]; data [B,p] or [p]; rtol / atol scalars,
+    [B] (per trajectory), [n] or [1,n] (per component) or [B,n]."""
     u0 = np.ascontiguousarray(u0, dtype=np.float64)
     data = np.ascontiguousarray(data, dtype=np.float64)
     te = np.ascontiguousarray(t_eval, dtype=np.float64)
-    B = u0.shape[0] if u0.ndim == 2 else data.shape[0]
+    B = u0.shape[0] if u0.ndim == 2 else (data.shape[0] if data.ndim == 2 else 1)
     n = u0.shape[-1]
     us = np.full((B, len(te), n), np.nan)
     ok = np.zeros(B, dtype=np.int32)
     cnt = np.zeros((B, 8), dtype=np.int32)
-    lib.oracle_solve_batch.restype = ct.c_int
-    lib.oracle_solve_batch(0 if solver == "dop853" else 1, ct.c_void_p(fptr), ct.c_long(B), n,
-                           _p(u0), ct.c_long(n if u0.ndim == 2 else 0), _p(data),
-                           ct.c_long(data.shape[-1] * 8 if data.ndim == 2 else 0), len(te),
-                           _p(te), _p(us), ct.c_double(rtol), ct.c_double(atol), int(mxstep),
-                           int(exit_on_warning), _p(ok), _p(cnt), int(nthreads))
+    rs, rv, rvs = _tol_arg(rtol, B, n)
+    as_, av, avs = _tol_arg(atol, B, n)
+    lib.oracle_solve_batch_v.restype = ct.c_int
+    lib.oracle_solve_batch_v(0 if solver == "dop853" else 1, ct.c_void_p(fptr), ct.c_long(B), n,
+                             _p(u0), ct.c_long(n if u0.ndim == 2 else 0), _p(data),
+                             ct.c_long(data.shape[-1] * 8 if data.ndim == 2 else 0), len(te),
+                             _p(te), _p(us), ct.c_double(rs), ct.c_double(as_),
+                             _p(rv) if rv is not None else None, ct.c_long(rvs),
+                             _p(av) if av is not None else None, ct.c_long(avs), int(mxstep),
+                             int(exit_on_warning), _p(ok), _p(cnt), int(nthreads))
     return us, ok == 1, cnt
 
 

@@ -27,9 +27,31 @@ static const B200LsodaTables g_tables = B200_LSODA_TABLES_INIT;
 
 extern "C" const B200LsodaTables* lsoda_core_tables(void) { return &g_tables; }
 
+static void core_run(rhs_fn f, int neq, const double* u0, void* data, int nt, const double* teval,
+                     double* usol, const LsTol& tol, int mxstep, int* success, int exit_on_warning,
+                     int* counters);
+
 extern "C" void lsoda_core_host(rhs_fn f, int neq, const double* u0, void* data, int nt,
                                 const double* teval, double* usol, double rtol, double atol,
                                 int mxstep, int* success, int exit_on_warning, int* counters)
+{
+    LsTol tol = {rtol, atol, nullptr, nullptr};
+    core_run(f, neq, u0, data, nt, teval, usol, tol, mxstep, success, exit_on_warning, counters);
+}
+
+// per-component tolerance vectors (null: the scalar applies)
+extern "C" void lsoda_core_host_vtol(rhs_fn f, int neq, const double* u0, void* data, int nt,
+                                     const double* teval, double* usol, double rtol, double atol,
+                                     const double* rtol_v, const double* atol_v, int mxstep,
+                                     int* success, int exit_on_warning, int* counters)
+{
+    LsTol tol = {rtol, atol, rtol_v, atol_v};
+    core_run(f, neq, u0, data, nt, teval, usol, tol, mxstep, success, exit_on_warning, counters);
+}
+
+static void core_run(rhs_fn f, int neq, const double* u0, void* data, int nt, const double* teval,
+                     double* usol, const LsTol& tol, int mxstep, int* success, int exit_on_warning,
+                     int* counters)
 {
     g_rhs = f;
     LsLane s;
@@ -56,10 +78,10 @@ extern "C" void lsoda_core_host(rhs_fn f, int neq, const double* u0, void* data,
     v.wmp = wm;
 #endif
     double* pp = static_cast<double*>(data);
-    bool done = ls_begin(s, R, v, u0, pp, nt, teval, usol, rtol, atol);
+    bool done = ls_begin(s, R, v, u0, pp, nt, teval, usol, tol);
     const unsigned long long mxstep_u = (unsigned long long)(long long)mxstep;
     while (!done)
-        done = ls_advance(s, R, v, &g_tables, pp, nt, teval, usol, rtol, atol, mxstep_u,
+        done = ls_advance(s, R, v, &g_tables, pp, nt, teval, usol, tol, mxstep_u,
                           exit_on_warning, 0u);
     *success = R.istate > 0 ? 1 : 0;
     if (counters) {

@@ -17,14 +17,18 @@ HDRS = [os.path.join(ROOT, "numbalsoda_b200", "csrc", f)
         for f in ("dop853_warp.cuh", "b200ode_warp.cuh", "dop853_tableau.cuh", "b200ode_pow.cuh")]
 
 
-@pytest.fixture(scope="module")
-def lib():
+def build_lib():
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
     so = os.path.join(HERE, "_build", "libdop853_warp_host.so")
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in [SRC] + HDRS):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared",
                                "-Wno-unknown-pragmas", "-o", so, SRC])
     return ct.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return build_lib()
 
 
 def run(lib, fptr, u0, te, data, rtol, atol, mxstep=10000):
