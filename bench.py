@@ -66,6 +66,15 @@ WORKLOADS = {
                               t_eval=(0.0, 10.0, 100), rtol=1e-6, atol=1e-8, mxstep=10000,
                               batch=100000, config="BASELINE.json configs[3] (SURVEY 8d C4): "
                               "1-D Brusselator on 32 cells, warp per trajectory"),
+    # the same problem with the species interleaved (ml = mu = 2) and LSODA's
+    # banded finite-difference Jacobian -- 5 right-hand-side calls and a band LU per Jacobian
+    # instead of 64 and a dense one.  The reference has no banded path: its CPU arm runs the
+    # dense solver on the same system, which is what a numbalsoda user has.
+    "brusselator_lsoda_banded": dict(solver="lsoda", rhs="brusselator1d_il", n=64, p=3, u0="brusselator_il",
+                                     t_eval=(0.0, 10.0, 100), rtol=1e-6, atol=1e-8, mxstep=10000, band=(2, 2),
+                                     batch=100000, config="BASELINE.json configs[3] (SURVEY 8d C4) with "
+                                     "lsoda(..., ml=2, mu=2) (SURVEY 8f rank 3): interleaved 1-D Brusselator, "
+                                     "banded finite-difference Jacobian, warp per trajectory"),
     # the reference's third entry point on the C2 sweep, with the terminal
     # event z = 50 (45 % of the trajectories stop in the first transient, the others run to
     # t = 100: the persistent work queue is what keeps the lanes busy)
@@ -88,7 +97,7 @@ def sweep(name, B, seed, level=None):
         return np.ascontiguousarray(np.column_stack([pr.lorenz_sweep(B, seed), np.full(B, level)]))
     if name == "lorenz":
         return pr.lorenz_sweep(B, seed)
-    if name == "brusselator1d":
+    if name in ("brusselator1d", "brusselator1d_il"):
         return pr.brusselator_sweep(B, seed)
     return pr.robertson_sweep(B, seed)
 
@@ -98,12 +107,16 @@ def python_rhs(name):
     the reference's own benchmark functions); numba.cuda compiles it for the device."""
     import _problems as pr
     return {"lorenz": pr.lorenz_rhs, "robertson": pr.robertson_rhs,
-            "brusselator1d": pr.brusselator_rhs}[name]
+            "brusselator1d": pr.brusselator_rhs, "brusselator1d_il": pr.brusselator_il_rhs}[name]
 
 
 def initial_state(wl):
     import _problems as pr
-    return pr.brusselator_u0() if wl["u0"] == "brusselator" else np.array(wl["u0"], dtype=np.float64)
+    if wl["u0"] == "brusselator":
+        return pr.brusselator_u0()
+    if wl["u0"] == "brusselator_il":
+        return pr.interleave(pr.brusselator_u0())
+    return np.array(wl["u0"], dtype=np.float64)
 
 
 # ---------------------------------------------------------------- algorithmic FLOPs
@@ -119,7 +132,7 @@ def dop853_flops(cnt, n, f_rhs, nt):
     return float(fl.sum())
 
 
-def lsoda_flops(cnt, n, f_rhs, nt):
+def lsoda_flops(cnt, n, f_rhs, nt, band=None):
     """SURVEY.md 8(d), LSODA: counted from nst / nfe / nje with the mean order taken
     as nqu (upper estimate of the per-step bookkeeping is avoided: only the terms
     that scale with the counters are included)."""
@@ -132,6 +145,13 @@ def lsoda_flops(cnt, n, f_rhs, nt):
         (3 * n + 30) / (nq + 1)
     per_fe = f_rhs + 2 * n * n + 8 * n + 10
     per_je = (2 * n * n + 4 * n) + (2 * n * n + n) + n + (2.0 / 3.0) * n ** 3 + 0.5 * n * n
+    if band is not None:
+        # the banded algorithm's own counts: dgbsl 2 n (2 ml + mu + 1), matrix fill and DBNORM over
+        # the band, dgbfa 2 n ml (ml + mu) + n
+        ml, mu = band
+        mb = ml + mu + 1
+        per_fe = f_rhs + 2 * n * (2 * ml + mu + 1) + 8 * n + 10
+        per_je = (2 * n * mb + 4 * n) + (2 * n * mb + n) + n + 2 * n * ml * (ml + mu) + n
     fl = nst * per_step + nfe * per_fe + nje * per_je + rows * (n * (3 * nq + 1) + 2)
     return float(fl.sum())
 
@@ -164,7 +184,7 @@ if os.path.exists(_traffic_file):  # newer captures override the round-1 constan
     except Exception:
         pass
 
-F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6, "brusselator1d": 608}
+F_RHS = {"lorenz": 8, "robertson": 13, "lotka_volterra": 6, "brusselator1d": 608, "brusselator1d_il": 608}
 
 
 # ---------------------------------------------------------------- clocks
@@ -389,9 +409,21 @@ class Gpu:
             pb.result, pb.t_event, pb.y_event = res.data_ptr(), t_event.data_ptr(), y_event.data_ptr()
         solver = _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
 
+        band = wl.get("band")
+
         def step():
             if ivp:
                 _lib.check(_lib.lib.b200ode_solve_ivp_device(h.ptr, ct.byref(pb), ct.c_void_p(stream.cuda_stream)))
+                return
+            if band:  # options beyond the positional entry points: the structure
+                q = _lib.Problem()
+                q.size = ct.sizeof(_lib.Problem)
+                q.B, q.neq, q.nt, q.np = B, n, nt, wl["p"]
+                q.u0, q.u0_stride, q.data, q.data_stride = u0.data_ptr(), 0, P.data_ptr(), wl["p"] * 8
+                q.teval, q.usol, q.rtol, q.atol = te.data_ptr(), usol.data_ptr(), wl["rtol"], wl["atol"]
+                q.mxstep, q.success, q.counters = wl["mxstep"], ok.data_ptr(), cnt.data_ptr()
+                q.jt, q.ml, q.mu = 5, band[0], band[1]
+                _lib.check(_lib.lib.b200ode_solve_device(h.ptr, ct.byref(q), ct.c_void_p(stream.cuda_stream)))
                 return
             for b0 in range(0, B, Bl):
                 nb_ = min(Bl, B - b0)
@@ -457,8 +489,14 @@ class Gpu:
         teh = np.linspace(*wl["t_eval"][:2], nt)
         Ph = sweep(wl["rhs"], B, seed, wl.get("level"))
         row_bytes = nt * n * 8
-        # two page-locked buffers of at most ~3.2 GB each per rank (8 ranks pin theirs on one host)
-        per_buf = int(os.environ.get("B200ODE_BENCH_PINNED_MB", "3200")) << 20
+        # two page-locked buffers per rank, each at most 6.4 GB and a fifth of this rank's share
+        # of the host's available memory (8 ranks pin theirs on one host)
+        per_buf = int(os.environ.get("B200ODE_BENCH_PINNED_MB", "6400")) << 20
+        try:
+            avail = [int(ln.split()[1]) << 10 for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0]
+            per_buf = int(min(per_buf, 0.2 * avail / self.world))
+        except Exception:
+            pass
         Bs = int(max(1, min(B, per_buf // row_bytes)))
         nslices = (B + Bs - 1) // Bs
         Bs = (B + nslices - 1) // nslices
@@ -466,6 +504,8 @@ class Gpu:
         rhs = python_rhs(wl["rhs"]) if rhs_kind == "numba" else nb.builtin(wl["rhs"])
         api = nb.dop853 if wl["solver"] == "dop853" else nb.lsoda
         kw = dict(MODES[mode])
+        if wl.get("band"):
+            kw.update(ml=wl["band"][0], mu=wl["band"][1])
 
         def one_pass():
             good = 0
@@ -536,7 +576,10 @@ def roofline_block(workload, wl, leg, peak_tf, peak_src):
         flops = ivp_flops(leg["res"], n, F_RHS[wl["rhs"]], 1)
         rows_h = float(leg["res"][:, 3].mean())
     else:
-        flops = (dop853_flops if wl["solver"] == "dop853" else lsoda_flops)(leg["cnt"], n, F_RHS[wl["rhs"]], nt)
+        if wl["solver"] == "dop853":
+            flops = dop853_flops(leg["cnt"], n, F_RHS[wl["rhs"]], nt)
+        else:
+            flops = lsoda_flops(leg["cnt"], n, F_RHS[wl["rhs"]], nt, wl.get("band"))
     per_launch_s = leg["per_launch_s_rank"]
     achieved_tf = flops / per_launch_s / 1e12
     peaks = measured_peaks()
@@ -578,16 +621,17 @@ def parity_block(gpu, wl, rhs_kind):
     u0 = initial_state(wl)
     f = orc.builtin_rhs(wl["rhs"])
     rtol, atol = wl["rtol"], wl["atol"]
-    ref, okr, cr = orc.solve_batch(wl["solver"], f, u0, te, P, rtol, atol, wl["mxstep"])
+    ref, okr, cr = orc.solve_batch(wl["solver"], f, u0, te, P, rtol, atol, wl["mxstep"], band=wl.get("band"))
     truth, okt, _ = orc.solve_batch(wl["solver"], f, u0, te, P, 1e-13, 1e-13, 1000000)
     w = rtol * np.abs(truth) + atol
     e_ref = float((np.abs(ref - truth) / w).max())
     api = nb.dop853 if wl["solver"] == "dop853" else nb.lsoda
     rhs = python_rhs(wl["rhs"]) if rhs_kind == "numba" else nb.builtin(wl["rhs"])
     out = {}
+    bkw = dict(ml=wl["band"][0], mu=wl["band"][1]) if wl.get("band") else {}
     for mode in MODES:
         us, ok, cnt = api(rhs, u0, te, P, rtol, atol, wl["mxstep"], device=gpu.local, counters=True,
-                          **MODES[mode])
+                          **MODES[mode], **bkw)
         e = float((np.abs(us - truth) / w).max())
         out[mode] = {
             "bit_identical_to_oracle": bool(np.array_equal(us, ref)),

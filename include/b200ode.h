@@ -157,6 +157,16 @@ typedef struct b200ode_problem {
     int* counters;          /* [B,8] or NULL */
     int rtol_dims;          /* B200ODE_TOL_*: shape of rtol_b (0 = [B]) */
     int atol_dims;
+    /* lsoda: how the iteration matrix is formed.  The reference
+     * fixes jt = 2 (LSODA.cpp:2263: dense, by finite differences: neq right-hand-side calls
+     * and a dense LU per Jacobian); its checker also accepts jt = 4 / 5 with ml, mu
+     * (:369-392) but prja / solsy implement miter = 2 only (:1656-1660, :1936-1942).
+     *   jt = 0 or 2        the reference's dense finite-difference Jacobian
+     *   jt = 5, ml, mu     banded finite-difference Jacobian (ODEPACK's DPRJA / DSOLSY miter = 5
+     *                      with LINPACK dgbfa / dgbsl): ml + mu + 1 right-hand-side calls and a
+     *                      band LU.  Requires 0 <= ml, mu < neq.  Systems of up to 8 equations
+     *                      (thread-per-trajectory kernels) keep the dense matrix. */
+    int jt, ml, mu;
 } b200ode_problem;
 /* host pointers; copies to / from `device` */
 int b200ode_solve(b200ode_rhs_t rhs, const b200ode_problem* problem, int device);

@@ -30,7 +30,8 @@ class Problem(ct.Structure):
                 ("teval", ct.c_void_p), ("usol", ct.c_void_p), ("rtol", ct.c_double),
                 ("atol", ct.c_double), ("rtol_b", ct.c_void_p), ("atol_b", ct.c_void_p),
                 ("mxstep", ct.c_int), ("exit_on_warning", ct.c_int), ("success", ct.c_void_p),
-                ("counters", ct.c_void_p), ("rtol_dims", ct.c_int), ("atol_dims", ct.c_int)]
+                ("counters", ct.c_void_p), ("rtol_dims", ct.c_int), ("atol_dims", ct.c_int),
+                ("jt", ct.c_int), ("ml", ct.c_int), ("mu", ct.c_int)]
 
 
 class IvpProblem(ct.Structure):

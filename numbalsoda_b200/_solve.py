@@ -37,7 +37,7 @@ def _data_layout(data, B_hint):
 
 
 def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning=False,
-          strict=False, device=None, counters=False, out=None, exact_ctrl=False):
+          strict=False, device=None, counters=False, out=None, exact_ctrl=False, ml=None, mu=None):
     u0 = _as_f64(u0, "u0")
     t_eval = _as_f64(t_eval, "t_eval")
     if data is None:
@@ -71,6 +71,16 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
     rtol, rtol_b, rtol_dims = tolerance_layout(rtol, B, n, "rtol", batched)
     atol, atol_b, atol_dims = tolerance_layout(atol, B, n, "atol", batched)
 
+    # lsoda: banded finite-difference Jacobian (jt = 5) when ml and mu are given
+    if (ml is None) != (mu is None):
+        raise ValueError("ml and mu must be given together")
+    if ml is not None:
+        if solver != _lib.LSODA:
+            raise ValueError("ml / mu are lsoda options")
+        ml, mu = int(ml), int(mu)
+        if not (0 <= ml < n and 0 <= mu < n):  # the reference's checker, LSODA.cpp:376-391
+            raise ValueError("ml = %d, mu = %d not between 0 and neq - 1 = %d" % (ml, mu, n - 1))
+
     devices = _device_list(device)
 
     def run(dev, b0, b1):
@@ -89,6 +99,8 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
         pb.rtol_b, pb.rtol_dims = _tol_slice(rtol_b, rtol_dims, b0, b1)
         pb.atol_b, pb.atol_dims = _tol_slice(atol_b, atol_dims, b0, b1)
         pb.mxstep, pb.exit_on_warning = int(mxstep), int(bool(exit_on_warning))
+        if ml is not None:
+            pb.jt, pb.ml, pb.mu = 5, ml, mu
         pb.success = ok[b0:b1].ctypes.data
         pb.counters = cnt[b0:b1].ctypes.data if counters else None
         _lib.check(_lib.lib.b200ode_solve(handle.ptr, ct.byref(pb), dev))

@@ -55,7 +55,7 @@ SOLVERS = {
     # solve_ivp: DOP853 with dense output after every step and terminal events
     "ivp": ("solve_ivp_kernel.cu", list(range(1, 9))),
 }
-BUILTIN_RHS = ["lotka_volterra", "lotka_volterra2", "lorenz", "robertson", "brusselator1d"]
+BUILTIN_RHS = ["lotka_volterra", "lotka_volterra2", "lorenz", "robertson", "brusselator1d", "brusselator1d_il"]
 BUILTIN_EVENTS = ["none", "lv_prey", "lorenz_z"]
 
 

@@ -536,6 +536,28 @@ static int check_tol(const TolArg& t, const char* what)
     return 0;
 }
 
+// How lsoda forms its iteration matrix (b200ode_problem.jt / ml / mu): ml < 0 = dense.
+struct JacArg {
+    int jt = 0, ml = -1, mu = -1;
+};
+static JacArg jac_arg(int jt, int ml, int mu)
+{
+    JacArg j;
+    j.jt = jt;
+    if (jt == 5) j.ml = ml, j.mu = mu;
+    return j;
+}
+static int check_jac(const JacArg& j, int solver, int neq)
+{
+    if (j.jt != 0 && j.jt != 2 && j.jt != 5)
+        return fail(B200ODE_ENOSYS, "jt = %d: the Jacobian is generated internally, dense (jt = 2) or banded (jt = 5)", j.jt);
+    if (j.jt == 5 && solver != B200ODE_LSODA) return fail(B200ODE_EINVAL, "jt = 5 is an lsoda option");
+    // the reference's checker, LSODA.cpp:376-391
+    if (j.jt == 5 && (j.ml < 0 || j.mu < 0 || j.ml >= neq || j.mu >= neq))
+        return fail(B200ODE_EINVAL, "ml = %d, mu = %d not between 0 and neq - 1 = %d", j.ml, j.mu, neq - 1);
+    return 0;
+}
+
 static int check_args(b200ode_rhs_t H, int solver, long long B, int neq, const void* u0,
                       const void* data, int np, int nt, const void* teval, const void* usol,
                       const void* success)
@@ -580,6 +602,17 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
     }
     CUfunction fn = (args.np >= 0 && !warp) ? P->fn : P->fn_ptr;
     int dyn_smem = P->dyn_smem;
+    if (!(warp && H->solver == B200ODE_LSODA) || P->wm_scratch ||
+        (args.ml >= 0 && B200ODE_LSODAW_BAND_DOUBLES(H->neq, args.ml, args.mu) >= B200ODE_LSODAW_DOUBLES(H->neq)))
+        args.ml = args.mu = -1;  // thread kernels and bands as wide as the matrix: dense
+    if (args.ml >= 0) {
+        // banded iteration matrix: a trajectory needs far less shared memory, more warps fit an SM
+        dyn_smem = B200ODE_LSODAW_BAND_DOUBLES(H->neq, args.ml, args.mu) * (int)sizeof(double);
+        int nb = 0;
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, (size_t)dyn_smem));
+        if (nb < 1) nb = 1;
+        grid = (int)std::min<long long>(want, (long long)P->sms * nb);
+    }
     args.te_shared = 0;
     if (!warp && H->solver == B200ODE_DOP853) {
         // a copy of t_eval per block, if it costs no resident block (dop853_kernel.cu)
@@ -604,11 +637,11 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
                         long long u0_stride, const void* data, long long data_stride, int np,
                         int nt, const double* teval, double* usol, double rtol, double atol,
                         int mxstep, int* success, int* counters, int exit_on_warning,
-                        void* stream, TolArg rt = TolArg(), TolArg at = TolArg())
+                        void* stream, TolArg rt = TolArg(), TolArg at = TolArg(), JacArg jac = JacArg())
 {
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
-    if ((rc = check_tol(rt, "rtol")) || (rc = check_tol(at, "atol"))) return rc;
+    if ((rc = check_tol(rt, "rtol")) || (rc = check_tol(at, "atol")) || (rc = check_jac(jac, solver, neq))) return rc;
     if (u0_stride != 0 && u0_stride < neq) return fail(B200ODE_EINVAL, "u0_stride = %lld", u0_stride);
     PerDevice* P;
     rc = device_state(H, -1, &P);
@@ -636,6 +669,7 @@ static int solve_device(int solver, b200ode_rhs_t H, long long B, int neq, const
     a.exit_on_warning = exit_on_warning;
     a.success = success;
     a.counters = counters;
+    a.ml = jac.ml, a.mu = jac.mu;
     return launch(H, P, a, static_cast<CUstream>(stream));
 }
 
@@ -788,11 +822,11 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
                       long long u0_stride, const void* data, long long data_stride, int np,
                       int nt, const double* teval, double* usol, double rtol, double atol,
                       int mxstep, int* success, int* counters, int exit_on_warning, int device,
-                      TolArg rt = TolArg(), TolArg at = TolArg())
+                      TolArg rt = TolArg(), TolArg at = TolArg(), JacArg jac = JacArg())
 {
     int rc = check_args(H, solver, B, neq, u0, data, np, nt, teval, usol, success);
     if (rc) return rc;
-    if ((rc = check_tol(rt, "rtol")) || (rc = check_tol(at, "atol"))) return rc;
+    if ((rc = check_tol(rt, "rtol")) || (rc = check_tol(at, "atol")) || (rc = check_jac(jac, solver, neq))) return rc;
     const double* rtol_b = rt.p;
     const double* atol_b = at.p;
     if (device < 0) return fail(B200ODE_EINVAL, "device = %d", device);
@@ -919,6 +953,7 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
         a.exit_on_warning = exit_on_warning;
         a.success = reinterpret_cast<int*>(d_ok[i]);
         a.counters = counters ? reinterpret_cast<int*>(d_cnt[i]) : nullptr;
+        a.ml = jac.ml, a.mu = jac.mu;
         if ((rc = launch(H, P, a, ks))) return rc;
         CU(cuEventRecord(ev_kernel[i].e, ks));
         // the copy of chunk c-1 is enqueued after the launch of chunk c so that a buffer's
@@ -975,7 +1010,8 @@ extern "C" int b200ode_solve(b200ode_rhs_t H, const b200ode_problem* p, int devi
     return solve_host(H->solver, H, p->B, p->neq, p->u0, p->u0_stride, p->data, p->data_stride,
                       p->np, p->nt, p->teval, p->usol, p->rtol, p->atol, p->mxstep, p->success,
                       p->counters, H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, device,
-                      tol_arg(p->rtol_b, p->rtol_dims), tol_arg(p->atol_b, p->atol_dims));
+                      tol_arg(p->rtol_b, p->rtol_dims), tol_arg(p->atol_b, p->atol_dims),
+                      jac_arg(p->jt, p->ml, p->mu));
 }
 
 extern "C" int b200ode_solve_device(b200ode_rhs_t H, const b200ode_problem* p, void* stream)
@@ -986,7 +1022,8 @@ extern "C" int b200ode_solve_device(b200ode_rhs_t H, const b200ode_problem* p, v
                         p->data_stride, p->np, p->nt, p->teval, p->usol, p->rtol, p->atol,
                         p->mxstep, p->success, p->counters,
                         H->solver == B200ODE_LSODA ? p->exit_on_warning : 0, stream,
-                        tol_arg(p->rtol_b, p->rtol_dims), tol_arg(p->atol_b, p->atol_dims));
+                        tol_arg(p->rtol_b, p->rtol_dims), tol_arg(p->atol_b, p->atol_dims),
+                      jac_arg(p->jt, p->ml, p->mu));
 }
 
 // ---------------------------------------------------------------- solve_ivp

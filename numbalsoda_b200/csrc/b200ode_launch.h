@@ -29,6 +29,17 @@
 #define B200ODE_LSODAW_DOUBLES(n) \
     (18 * (n) + B200ODE_LSODAW_MATRIX(n) + B200ODE_LSODAW_JCOLS * ((n) + 1) + (n) + 1)
 
+/* ... and with a banded iteration matrix (ml, mu >= 0): band storage (2 ml + mu + 1) x n, and two
+ * vectors (perturbed state, its right-hand side) for each column group evaluated concurrently */
+#define B200ODE_LSODAW_BAND_MATRIX(n, ml, mu) ((2 * (ml) + (mu) + 1) * (n))
+#define B200ODE_LSODAW_BAND_COPIES(n, ml, mu)                                             \
+    (((ml) + (mu) + 1 < (n) ? (ml) + (mu) + 1 : (n)) < B200ODE_LSODAW_JCOLS              \
+         ? ((ml) + (mu) + 1 < (n) ? (ml) + (mu) + 1 : (n))                                \
+         : B200ODE_LSODAW_JCOLS)
+#define B200ODE_LSODAW_BAND_DOUBLES(n, ml, mu)                         \
+    (18 * (n) + B200ODE_LSODAW_BAND_MATRIX(n, ml, mu) +                \
+     2 * B200ODE_LSODAW_BAND_COPIES(n, ml, mu) * ((n) + 1) + (n) + 1)
+
 typedef struct B200OdeLaunch {
     long long B;              /* trajectories in this launch */
     const double* u0;         /* [B,n] (u0_stride = n) or [n] shared (u0_stride = 0) */
@@ -55,6 +66,8 @@ typedef struct B200OdeLaunch {
     unsigned long long* next; /* work queue head (zeroed before the launch) */
     double* scratch;          /* warp kernel: per-block iteration matrices in global memory
                                  (B200ODE_LSODAW_MATRIX(neq) doubles each), or null = shared */
+    int ml, mu;               /* lsoda: banded finite-difference Jacobian (jt = 5) when ml >= 0 -- used
+                                 by the warp kernel; the thread kernel (n <= 8) keeps the dense one */
     int te_shared;            /* dop853 thread kernel: the launch carries nt more doubles of dynamic
                                  shared memory and every block keeps its own copy of t_eval there */
 } B200OdeLaunch;

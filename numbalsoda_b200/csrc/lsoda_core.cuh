@@ -617,7 +617,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
                 s.nje++;
                 s.jcur = 1;
                 const int ierpj = v.prja(s.tn, s.h, s.h * s.el0, pp, s.pdnorm);
-                s.nfe += n;
+                s.nfe += v.jac_rhs_calls();  // n (LSODA.cpp:1678), or the column groups of a banded one
                 s.ipup = 0;
                 s.rc = 1.0;
                 s.nslp = s.nst;

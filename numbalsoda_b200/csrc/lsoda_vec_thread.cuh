@@ -39,6 +39,7 @@ struct LsThreadVec {
     unsigned ipvt;  // 4 bits per row
 
     LS_MFN int size() const { return N; }
+    LS_MFN int jac_rhs_calls() const { return N; }
     LS_MFN void sync(unsigned lanes)
     {
 #if defined(__CUDA_ARCH__)

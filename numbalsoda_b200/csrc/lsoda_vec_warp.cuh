@@ -72,16 +72,27 @@ double wv_wmax_norm(const double* v, const double* w, int n)
 struct LsWarpVec {
     int n, ld;
     bool fast;  // parallel triangular solves (see above); false = the reference's summation order
+    // Banded iteration matrix (jt = 5 with ml, mu, which the
+    // reference's checker accepts, LSODA.cpp:369-392, and its prja / solsy do not implement):
+    // ml >= 0 selects it.  The matrix then lives in LINPACK band storage, abd[(2 ml + mu + 1) x n]
+    // column-major in the place of wmT, the Jacobian costs min(ml + mu + 1, n) right-hand-side
+    // evaluations (columns j, j + mband, ... perturbed together) instead of n, and the LU and
+    // the solves touch the band only: ODEPACK's DPRJA / DSOLSY miter = 5 with LINPACK's
+    // dgbfa / dgbsl, element for element (oracle/lsoda_oracle.c restates the same routines).
+    int ml, mu;
     double *yh, *y, *savf, *acor, *ewt, *rdiag, *wmT, *ucopy;
     int *ipvt, *perm;
 
     // `matrix`: storage of the iteration matrix outside `base` (the kernel's L2-resident
     // per-block scratch), or null to keep it with the vectors in shared memory
-    LS_MFN void attach(double* base, int neq, bool fast_mode, double* matrix = nullptr)
+    LS_MFN void attach(double* base, int neq, bool fast_mode, double* matrix = nullptr,
+                       int band_ml = -1, int band_mu = -1)
     {
         n = neq;
         ld = neq + 1;
         fast = fast_mode;
+        ml = band_ml;
+        mu = band_mu;
         yh = base;
         y = yh + 13 * n;
         savf = y + n;
@@ -93,12 +104,15 @@ struct LsWarpVec {
             wmT = matrix;
         } else {
             wmT = next;
-            next += n * ld;
+            next += banded() ? B200ODE_LSODAW_BAND_MATRIX(n, ml, mu) : n * ld;
         }
         ucopy = next;
-        ipvt = reinterpret_cast<int*>(ucopy + B200ODE_LSODAW_JCOLS * ld);
+        ipvt = reinterpret_cast<int*>(ucopy + (banded() ? B200ODE_LSODAW_BAND_COPIES(n, ml, mu) * 2
+                                                         : B200ODE_LSODAW_JCOLS) * ld);
         perm = ipvt + n;
     }
+    LS_MFN bool banded() const { return ml >= 0; }
+    LS_MFN int jac_rhs_calls() const { return banded() && ml + mu + 1 < n ? ml + mu + 1 : n; }
     LS_MFN int size() const { return n; }
     LS_MFN void sync(unsigned) {}
 
@@ -187,7 +201,8 @@ struct LsWarpVec {
     {
         WV_FOR_OWN(i) y[i] = h * savf[i] - (WYH(2, i) + acor[i]);
         WV_SYNC();
-        dgesl(y);
+        if (banded()) dgbsl(y);
+        else dgesl(y);
         const double del = norm_ptr(y);
         WV_FOR_OWN(i) {
             acor[i] += y[i];
@@ -449,8 +464,160 @@ struct LsWarpVec {
 
     // prja, LSODA.cpp:1633-1696, with fnorm (:1714-1736) and the LU factorisation.
     // Uses y, savf = f(tn, y), ewt.  Returns ierpj.
+    // ---- banded iteration matrix: A(i,j) at abd[j * lda + (i - j + ml + mu)], lda = 2 ml + mu + 1
+#define WABD(i, j) wmT[(j) * lda + ((i) - (j) + ml + mu)]
+    // dgbfa: partial pivoting by row interchanges inside the band.  One elimination step per k;
+    // the multipliers and the (<= ml x (ml + mu)) block they update are independent elements:
+    // lanes own them, the arithmetic per element is LINPACK's.
+    LS_MFN int dgbfa()
+    {
+        const int lda = 2 * ml + mu + 1, m = ml + mu;
+        int info = 0, ju = 0;
+        // zero the initial fill-in columns
+        const int j1 = (n < m + 1 ? n : m + 1) - 1;
+        for (int jz = mu + 1; jz < j1; jz++)
+            for (int i = m - jz + WV_LANE; i < ml; i += WV_NL) wmT[jz * lda + i] = 0.0;
+        int jz = j1 - 1;
+        WV_SYNC();
+        for (int k = 0; k < n - 1; k++) {
+            jz++;
+            if (jz < n)
+                for (int i = WV_LANE; i < ml; i += WV_NL) wmT[jz * lda + i] = 0.0;
+            const int lm = ml < n - 1 - k ? ml : n - 1 - k;
+            double* ck = wmT + k * lda;
+            // pivot: first largest magnitude among a(k..k+lm, k); every lane finds it
+            int l = m;
+            for (int i = 1; i <= lm; i++)
+                if (fabs(ck[m + i]) > fabs(ck[l])) l = m + i;
+            const double akl = ck[l];
+            WV_SYNC();
+            if (WV_LANE == 0) ipvt[k] = l + k - m;
+            if (akl == 0.0) {
+                info = k + 1;
+                continue;
+            }
+            if (l != m && WV_LANE == 0) {
+                ck[l] = ck[m];
+                ck[m] = akl;
+            }
+            WV_SYNC();
+            const double t = ls_div(-1.0, akl);
+            for (int i = 1 + WV_LANE; i <= lm; i += WV_NL) ck[m + i] = ck[m + i] * t;
+            const int jn = mu + (l + k - m);
+            ju = ju > jn ? ju : jn;
+            if (ju > n - 1) ju = n - 1;
+            // the interchange in the columns to the right, one lane per column ...
+            for (int j = k + 1 + WV_LANE; j <= ju; j += WV_NL) {
+                const int lj = l - (j - k), mj = m - (j - k);
+                if (lj != mj) {
+                    double* cj = wmT + j * lda;
+                    const double tj = cj[lj];
+                    cj[lj] = cj[mj];
+                    cj[mj] = tj;
+                }
+            }
+            WV_SYNC();
+            // ... and the rank-one update of the block below the pivot row, a lane per element
+            const int nj = ju - k;
+            for (int q = WV_LANE; q < nj * lm; q += WV_NL) {
+                const int j = k + 1 + q / lm, i = 1 + q % lm;
+                double* cj = wmT + j * lda;
+                const int mj = m - (j - k);
+                cj[mj + i] = cj[mj + i] + cj[mj] * ck[m + i];
+            }
+            WV_SYNC();
+        }
+        if (WV_LANE == 0) ipvt[n - 1] = n - 1;
+        if (wmT[(n - 1) * lda + m] == 0.0) info = n;
+        WV_SYNC();
+        return info;
+    }
+
+    // dgbsl, job = 0
+    LS_MFN void dgbsl(double* b) const
+    {
+        const int lda = 2 * ml + mu + 1, m = ml + mu;
+        if (ml != 0) {
+            for (int k = 0; k < n - 1; k++) {
+                const int lm = ml < n - 1 - k ? ml : n - 1 - k;
+                const int l = ipvt[k];
+                const double t = b[l];
+                WV_SYNC();
+                if (l != k && WV_LANE == 0) {
+                    b[l] = b[k];
+                    b[k] = t;
+                }
+                const double* ck = wmT + k * lda;
+                for (int i = 1 + WV_LANE; i <= lm; i += WV_NL) b[k + i] = b[k + i] + t * ck[m + i];
+                WV_SYNC();
+            }
+        }
+        for (int k = n - 1; k >= 0; k--) {
+            const double* ck = wmT + k * lda;
+            const double bk = ls_div(b[k], ck[m]);
+            WV_SYNC();
+            if (WV_LANE == 0) b[k] = bk;
+            const int lm = k < m ? k : m;
+            const int la = m - lm, lb = k - lm;
+            const double t = -bk;
+            for (int i = WV_LANE; i < lm; i += WV_NL) b[lb + i] = b[lb + i] + t * ck[la + i];
+            WV_SYNC();
+        }
+    }
+
+    // DPRJA, miter = 5, with DBNORM
+    LS_MFN int prja_band(double tn, double h, double hl0, double* pp, double& pdnorm)
+    {
+        const int lda = 2 * ml + mu + 1, mband = ml + mu + 1;
+        const int mba = mband < n ? mband : n;
+        // column groups evaluated concurrently, one per lane (the host build has one lane)
+        const int ncopy = B200ODE_LSODAW_BAND_COPIES(n, ml, mu) < WV_NL ? B200ODE_LSODAW_BAND_COPIES(n, ml, mu) : WV_NL;
+        const double fac0 = norm_ptr(savf);
+        double r0 = 1000.0 * fabs(h) * LS_ETA * ((double)n) * fac0;
+        if (r0 == 0.0) r0 = 1.0;
+        for (int j0 = 0; j0 < mba; j0 += ncopy) {
+            const int j = j0 + WV_LANE;
+            if (WV_LANE < ncopy && j < mba) {
+                // this lane's group of columns j, j + mband, ...: one perturbed copy of y, one
+                // right-hand-side evaluation
+                double* u = ucopy + (2 * WV_LANE) * ld;
+                double* fu = u + ld;
+                for (int i = 0; i < n; i++) u[i] = y[i];
+                for (int i = j; i < n; i += mband) {
+                    const double r = ls_max(LS_SQRTETA * fabs(y[i]), ls_div(r0, ewt[i]));
+                    u[i] = y[i] + r;
+                }
+                wv_user_rhs(tn, u, fu, pp);
+                for (int jj = j; jj < n; jj += mband) {
+                    const double r = ls_max(LS_SQRTETA * fabs(y[jj]), ls_div(r0, ewt[jj]));
+                    const double fac = ls_div(-hl0, r);
+                    const int i1 = jj - mu > 0 ? jj - mu : 0;
+                    const int i2 = jj + ml < n - 1 ? jj + ml : n - 1;
+                    for (int i = i1; i <= i2; i++) WABD(i, jj) = (fu[i] - savf[i]) * fac;
+                }
+            }
+            WV_SYNC();
+        }
+        double an = 0.0;
+        WV_FOR_OWN(i) {
+            double sum = 0.0;
+            const int i1 = i - ml > 0 ? i - ml : 0;
+            const int i2 = i + mu < n - 1 ? i + mu : n - 1;
+            for (int j = i1; j <= i2; j++) sum += ls_div(fabs(WABD(i, j)), ewt[j]);
+            an = ls_max(an, sum * ewt[i]);
+        }
+        an = wv_max(an);
+        pdnorm = ls_div(an, fabs(hl0));
+        WV_SYNC();
+        WV_FOR_OWN(i) WABD(i, i) = WABD(i, i) + 1.0;
+        WV_SYNC();
+        return dgbfa() != 0 ? 1 : 0;
+    }
+#undef WABD
+
     LS_MFN int prja(double tn, double h, double hl0, double* pp, double& pdnorm)
     {
+        if (banded()) return prja_band(tn, h, hl0, pp, pdnorm);
         const double fac0 = norm_ptr(savf);
         double r0 = 1000.0 * fabs(h) * LS_ETA * ((double)n) * fac0;
         if (r0 == 0.0) r0 = 1.0;

@@ -31,7 +31,7 @@ b200ode_lsodaw_kernel(const B200OdeLaunch L)
     const int n = L.neq;
     LsWarpVec v;
     v.attach(b200_smem, n, L.strict == 0,
-             L.scratch ? L.scratch + (size_t)blockIdx.x * B200ODE_LSODAW_MATRIX(n) : nullptr);
+             L.scratch ? L.scratch + (size_t)blockIdx.x * B200ODE_LSODAW_MATRIX(n) : nullptr, L.ml, L.mu);
     const int nt = L.nt;
     const double* __restrict__ te = L.t_eval;
     // wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130)

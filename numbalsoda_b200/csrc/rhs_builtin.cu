@@ -42,6 +42,22 @@ extern "C" __device__ long long b200ode_user_rhs(double t, double* u, double* du
         du[i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur);
         du[m + i] = B * uu - uuv + D * (vl - 2.0 * v + vr);
     }
+#elif defined(B200_RHS_BRUSSELATOR1D_IL)
+    // the same problem with the species interleaved, y = (u_0, v_0, u_1, v_1, ...): the
+    // Jacobian is banded with ml = mu = 2 (the layout for lsoda(..., ml=2, mu=2))
+    const double A = p[0], B = p[1], D = p[2];
+    const int m = 32;
+#pragma unroll 1
+    for (int i = 0; i < m; i++) {
+        const double uu = u[2 * i], v = u[2 * i + 1];
+        const double ul = (i == 0) ? A : u[2 * i - 2];
+        const double ur = (i == m - 1) ? A : u[2 * i + 2];
+        const double vl = (i == 0) ? B : u[2 * i - 1];
+        const double vr = (i == m - 1) ? B : u[2 * i + 3];
+        const double uuv = uu * uu * v;
+        du[2 * i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur);
+        du[2 * i + 1] = B * uu - uuv + D * (vl - 2.0 * v + vr);
+    }
 #else
 #error "define one of B200_RHS_*"
 #endif

@@ -20,7 +20,7 @@ except Exception:  # numba absent: built-in right-hand sides still work
 
 def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, atol=1.0e-6,
           mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False, out=None,
-          exact_ctrl=False):
+          exact_ctrl=False, ml=None, mu=None):
     """Integrate with the LSODA kernel on the GPU.
 
     funcptr: address of a numba @cfunc(lsoda_sig) (as in the reference), the cfunc, the
@@ -29,10 +29,15 @@ def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, at
     arithmetic), device (index, list of indices or "all"), counters (also return
     [nst, nfe, nje, nswitch, nqu, istate, rows, meth] per trajectory), out (a preallocated
     C-contiguous float64 result buffer of B*nt*n elements -- e.g. from
-    numbalsoda_b200.pinned_empty -- to reuse across calls instead of a fresh np.empty)."""
+    numbalsoda_b200.pinned_empty -- to reuse across calls instead of a fresh np.empty), ml / mu
+    (lower / upper bandwidth of the Jacobian: the iteration matrix is then formed from
+    ml + mu + 1 right-hand-side evaluations instead of n and factored as a band matrix -- the
+    jt = 5 option the reference's solver checks for, LSODA.cpp:369-392, but does not implement;
+    systems of up to 8 equations keep the dense matrix).  rtol / atol may also be arrays: [B] per
+    trajectory, [n] per component, [B,n] both."""
     return solve(_lib.LSODA, funcptr, u0, t_eval, data, rtol, atol, mxstep,
                  exit_on_warning=exit_on_warning, strict=strict, device=device,
-                 counters=counters, out=out, exact_ctrl=exact_ctrl)
+                 counters=counters, out=out, exact_ctrl=exact_ctrl, ml=ml, mu=mu)
 
 
 def address_as_void_pointer(addr):

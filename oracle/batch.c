@@ -33,6 +33,13 @@ typedef struct {
     atomic_long next;
 } job_t;
 
+static int g_ml = -1, g_mu = -1; /* banded Jacobian of the LSODA calls (ml < 0: dense) */
+void oracle_batch_set_band(int ml, int mu)
+{
+    g_ml = ml;
+    g_mu = mu;
+}
+
 static void *worker(void *arg)
 {
     job_t *j = (job_t *)arg;
@@ -59,10 +66,10 @@ static void *worker(void *arg)
                 }
             } else {
                 oracle_lsoda_stats st;
-                oracle_lsoda_v(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
-                               j->rtol_v ? j->rtol_v + b * j->rtol_vs : 0,
-                               j->atol_v ? j->atol_v + b * j->atol_vs : 0, j->mxstep, &ok,
-                               j->exit_on_warning, &st);
+                oracle_lsoda_band(j->f, j->neq, u0b, db, j->nt, j->teval, out, j->rtol, j->atol,
+                                  j->rtol_v ? j->rtol_v + b * j->rtol_vs : 0,
+                                  j->atol_v ? j->atol_v + b * j->atol_vs : 0, g_ml, g_mu, j->mxstep,
+                                  &ok, j->exit_on_warning, &st);
                 if (j->counters) {
                     int *c = j->counters + b * ORACLE_NCOUNTERS;
                     c[0] = st.nst, c[1] = st.nfe, c[2] = st.nje, c[3] = st.nswitch;

@@ -60,6 +60,10 @@ typedef struct {
     int nst, nfe, nje, nqu, nattempt;
     double h, hu, hold, tn, rc, el0, crate, rmax, pdest, pdlast, pdnorm, conit;
     double sqrteta;
+    /* banded iteration matrix (jt = 5): ml / mu as the reference's checker takes them
+     * (LSODA.cpp:369-392, iworks[0..1]); banded < 0 means the dense path (jt = 2) */
+    int banded, ml, mu;
+    double *abd; /* LINPACK band storage, (2 ml + mu + 1) x n, column-major */
 } lsoda_ctx;
 
 /* std::max / std::min semantics (they matter when an operand is NaN) */
@@ -269,9 +273,165 @@ static void lu_solve(lsoda_ctx *s, double *b)
     }
 }
 
+/* ---- jt = 5: banded, internally generated Jacobian ---------------------------------
+ * The reference accepts jt = 4 / 5 with ml, mu (LSODA.cpp:369-392) but its prja and solsy
+ * implement miter = 2 only (:1656-1660, :1936-1942: "not implemented" and exit).  What follows
+ * is therefore an EXTENSION, restating the routines the reference was translated from --
+ * ODEPACK's DPRJA / DSOLSY for miter = 5 with DBNORM, and LINPACK's dgbfa / dgbsl -- in this
+ * file's conventions (inverted ewt, 0-based).  Parity for it: the dense path on the same
+ * problem within the tolerance (tests/test_banded.py), not bit identity with the reference. */
+#define ABD(s, i, j) ((s)->abd[(size_t)(j) * (2 * (s)->ml + (s)->mu + 1) + ((i) - (j) + (s)->ml + (s)->mu)])
+
+/* dgbfa: LU of the band matrix with partial pivoting (row interchanges inside the band) */
+static int band_factor(lsoda_ctx *s)
+{
+    const int n = s->n, ml = s->ml, mu = s->mu;
+    const int m = ml + mu; /* row of the diagonal in a column of abd */
+    const int lda = 2 * ml + mu + 1;
+    double *a = s->abd, t;
+    int info = 0, i, j, k, l, lm, ju = 0, jz, j0, j1, mm;
+    /* zero the initial fill-in columns */
+    j0 = mu + 1;
+    j1 = (n < m + 1 ? n : m + 1) - 1;
+    for (jz = j0; jz < j1; jz++)
+        for (i = m + 1 - (jz + 1); i < ml; i++)
+            a[(size_t)jz * lda + i] = 0.;
+    jz = j1 - 1;
+    for (k = 0; k < n - 1; k++) {
+        /* zero the next fill-in column */
+        jz++;
+        if (jz < n)
+            for (i = 0; i < ml; i++)
+                a[(size_t)jz * lda + i] = 0.;
+        /* pivot: first largest |a(i,k)|, i = k .. k + lm */
+        lm = ml < n - 1 - k ? ml : n - 1 - k;
+        l = m;
+        for (i = 1; i <= lm; i++)
+            if (fabs(a[(size_t)k * lda + m + i]) > fabs(a[(size_t)k * lda + l]))
+                l = m + i;
+        s->ipvt[k] = l + k - m;
+        if (a[(size_t)k * lda + l] == 0.) {
+            info = k + 1;
+            continue;
+        }
+        if (l != m) {
+            t = a[(size_t)k * lda + l];
+            a[(size_t)k * lda + l] = a[(size_t)k * lda + m];
+            a[(size_t)k * lda + m] = t;
+        }
+        t = -1. / a[(size_t)k * lda + m];
+        for (i = 1; i <= lm; i++)
+            a[(size_t)k * lda + m + i] *= t;
+        /* row elimination with column indexing */
+        ju = ju > mu + s->ipvt[k] ? ju : mu + s->ipvt[k];
+        if (ju > n - 1)
+            ju = n - 1;
+        mm = m;
+        for (j = k + 1; j <= ju; j++) {
+            l--;
+            mm--;
+            t = a[(size_t)j * lda + l];
+            if (l != mm) {
+                a[(size_t)j * lda + l] = a[(size_t)j * lda + mm];
+                a[(size_t)j * lda + mm] = t;
+            }
+            for (i = 1; i <= lm; i++)
+                a[(size_t)j * lda + mm + i] += t * a[(size_t)k * lda + m + i];
+        }
+    }
+    s->ipvt[n - 1] = n - 1;
+    if (a[(size_t)(n - 1) * lda + m] == 0.)
+        info = n;
+    return info;
+}
+
+/* dgbsl, job = 0 */
+static void band_solve(lsoda_ctx *s, double *b)
+{
+    const int n = s->n, ml = s->ml, mu = s->mu, m = ml + mu, lda = 2 * ml + mu + 1;
+    const double *a = s->abd;
+    double t;
+    int i, k, l, lm, la, lb;
+    if (ml != 0)
+        for (k = 0; k < n - 1; k++) {
+            lm = ml < n - 1 - k ? ml : n - 1 - k;
+            l = s->ipvt[k];
+            t = b[l];
+            if (l != k) {
+                b[l] = b[k];
+                b[k] = t;
+            }
+            for (i = 1; i <= lm; i++)
+                b[k + i] += t * a[(size_t)k * lda + m + i];
+        }
+    for (k = n - 1; k >= 0; k--) {
+        b[k] /= a[(size_t)k * lda + m];
+        lm = (k < m ? k : m);
+        la = m - lm;
+        lb = k - lm;
+        t = -b[k];
+        for (i = 0; i < lm; i++)
+            b[lb + i] += t * a[(size_t)k * lda + la + i];
+    }
+}
+
+/* DPRJA, miter = 5: columns j, j + mband, j + 2 mband, ... are perturbed together, so the
+ * Jacobian costs min(ml + mu + 1, n) right-hand-side evaluations instead of n */
+static void build_band_iteration_matrix(lsoda_ctx *s)
+{
+    const int n = s->n, ml = s->ml, mu = s->mu, mband = ml + mu + 1;
+    const int mba = mband < n ? mband : n;
+    double fac, hl0, r, r0, an, sum;
+    int i, j, jj, i1, i2;
+    s->nje++;
+    s->ierpj = 0;
+    s->jcur = 1;
+    hl0 = s->h * s->el0;
+    fac = wmax_norm(n, s->savf, s->ewt);
+    r0 = 1000. * fabs(s->h) * ETA * ((double)n) * fac;
+    if (r0 == 0.)
+        r0 = 1.;
+    for (j = 0; j < mba; j++) {
+        for (i = j; i < n; i += mband) {
+            r = dmax(s->sqrteta * fabs(s->yh[1][i]), r0 / s->ewt[i]);
+            s->y[i] += r;
+        }
+        s->f(s->tn, s->y, s->acor, s->data);
+        for (jj = j; jj < n; jj += mband) {
+            s->y[jj] = s->yh[1][jj];
+            r = dmax(s->sqrteta * fabs(s->y[jj]), r0 / s->ewt[jj]);
+            fac = -hl0 / r;
+            i1 = jj - mu > 0 ? jj - mu : 0;
+            i2 = jj + ml < n - 1 ? jj + ml : n - 1;
+            for (i = i1; i <= i2; i++)
+                ABD(s, i, jj) = (s->acor[i] - s->savf[i]) * fac;
+        }
+    }
+    s->nfe += mba;
+    /* DBNORM: the weighted max-norm of the band matrix, rows summed over the band */
+    an = 0.;
+    for (i = 0; i < n; i++) {
+        sum = 0.;
+        i1 = i - ml > 0 ? i - ml : 0;
+        i2 = i + mu < n - 1 ? i + mu : n - 1;
+        for (j = i1; j <= i2; j++)
+            sum += fabs(ABD(s, i, j)) / s->ewt[j];
+        an = dmax(an, sum * s->ewt[i]);
+    }
+    s->pdnorm = an / fabs(hl0);
+    for (i = 0; i < n; i++)
+        ABD(s, i, i) += 1.;
+    if (band_factor(s) != 0)
+        s->ierpj = 1;
+}
+
 /* prja, LSODA.cpp:1633-1696 (miter == 2 only: dense finite-difference Jacobian) */
 static void build_iteration_matrix(lsoda_ctx *s)
 {
+    if (s->banded) {
+        build_band_iteration_matrix(s);
+        return;
+    }
     const int n = s->n;
     double fac, hl0, r, r0, yj, an, sum;
     int i, j;
@@ -365,7 +525,10 @@ static int corrector(lsoda_ctx *s, double pnorm, double *del, double *delp, doub
         } else {
             for (i = 0; i < n; i++)
                 s->y[i] = s->h * s->savf[i] - (s->yh[2][i] + s->acor[i]);
-            lu_solve(s, s->y);
+            if (s->banded)
+                band_solve(s, s->y);
+            else
+                lu_solve(s, s->y);
             *del = wmax_norm(n, s->y, s->ewt);
             for (i = 0; i < n; i++) {
                 s->acor[i] += s->y[i];
@@ -787,6 +950,17 @@ void oracle_lsoda_v(oracle_rhs_fn f, int neq, const double *u0, void *data, int 
                     const double *rtol_v, const double *atol_v, int mxstep,
                     int *success, int exit_on_warning, oracle_lsoda_stats *st)
 {
+    oracle_lsoda_band(f, neq, u0, data, nt, teval, usol, rtol, atol, rtol_v, atol_v, -1, -1, mxstep,
+                      success, exit_on_warning, st);
+}
+
+/* ml, mu >= 0: jt = 5, banded finite-difference Jacobian (see band_factor above); ml < 0: the
+ * reference's jt = 2 */
+void oracle_lsoda_band(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                       const double *teval, double *usol, double rtol, double atol,
+                       const double *rtol_v, const double *atol_v, int ml, int mu, int mxstep,
+                       int *success, int exit_on_warning, oracle_lsoda_stats *st)
+{
     const int n = neq;
     /* wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130) */
     const unsigned long long mxstep_u = (unsigned long long)(long long)mxstep;
@@ -826,6 +1000,17 @@ void oracle_lsoda_v(oracle_rhs_fn f, int neq, const double *u0, void *data, int 
     s->y = s->acor + n;
     s->wm = s->y + n;
     s->ipvt = (int *)calloc((size_t)n, sizeof(int));
+    s->banded = (ml >= 0 && mu >= 0);
+    if (s->banded) {
+        /* the reference's checker, LSODA.cpp:376-391 */
+        if (ml >= n || mu >= n) {
+            istate = -3;
+            goto done;
+        }
+        s->ml = ml;
+        s->mu = mu;
+        s->abd = (double *)calloc((size_t)n * (2 * ml + mu + 1), sizeof(double));
+    }
 
     /* ---- first call, blocks b/c of LSODA::lsoda, LSODA.cpp:341-663 ---- */
     t0 = teval[0];
@@ -991,6 +1176,7 @@ done:
         *success = 0; /* wrapper.cpp:41-45 */
     free(w);
     free(s->ipvt);
+    free(s->abd);
 }
 #undef RT
 #undef AT

@@ -108,6 +108,16 @@ void oracle_lsoda_v(oracle_rhs_fn f, int neq, const double *u0, void *data, int 
                     const double *rtol_v, const double *atol_v, int mxstep,
                     int *success, int exit_on_warning, oracle_lsoda_stats *stats);
 
+/* ... and a banded finite-difference Jacobian (jt = 5 with ml, mu, which the reference's
+ * checker accepts, LSODA.cpp:369-392, and its prja / solsy do not implement): an extension
+ * restating ODEPACK's DPRJA / DSOLSY miter = 5 with LINPACK dgbfa / dgbsl.  ml < 0: jt = 2. */
+void oracle_lsoda_band(oracle_rhs_fn f, int neq, const double *u0, void *data, int nt,
+                       const double *teval, double *usol, double rtol, double atol,
+                       const double *rtol_v, const double *atol_v, int ml, int mu, int mxstep,
+                       int *success, int exit_on_warning, oracle_lsoda_stats *stats);
+/* oracle_solve_batch_v uses these for its LSODA calls (test knob, set before the call) */
+void oracle_batch_set_band(int ml, int mu);
+
 /* Ensemble helpers: the way numbalsoda is used for ensembles today is a prange
  * loop of independent calls (README.md:60-67); these do the same with OpenMP.
  * u0 is [B,n] (u0_stride = n) or a single [n] vector (u0_stride = 0); data is
@@ -135,6 +145,7 @@ void oracle_rhs_lotka_volterra(double t, double *u, double *du, void *p);
 void oracle_rhs_lorenz(double t, double *u, double *du, void *p);
 void oracle_rhs_robertson(double t, double *u, double *du, void *p);
 void oracle_rhs_brusselator1d(double t, double *u, double *du, void *p);
+void oracle_rhs_brusselator1d_il(double t, double *u, double *du, void *p);
 oracle_rhs_fn oracle_builtin_rhs(const char *name);
 
 #ifdef __cplusplus

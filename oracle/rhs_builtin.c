@@ -71,6 +71,27 @@ void oracle_rhs_brusselator1d(double t, double *y, double *dy, void *pv)
     }
 }
 
+/* The same problem with the two species interleaved, y = (u_0, v_0, u_1, v_1, ...): the
+ * Jacobian is then banded with ml = mu = 2 (the layout a method-of-lines user picks for a
+ * banded solver); same operations per cell as above. */
+void oracle_rhs_brusselator1d_il(double t, double *y, double *dy, void *pv)
+{
+    const double *p = (const double *)pv;
+    const double A = p[0], B = p[1], D = p[2];
+    const int m = 32;
+    (void)t;
+    for (int i = 0; i < m; i++) {
+        const double u = y[2 * i], v = y[2 * i + 1];
+        const double ul = (i == 0) ? A : y[2 * i - 2];
+        const double ur = (i == m - 1) ? A : y[2 * i + 2];
+        const double vl = (i == 0) ? B : y[2 * i - 1];
+        const double vr = (i == m - 1) ? B : y[2 * i + 3];
+        const double uuv = u * u * v;
+        dy[2 * i] = A + uuv - (B + 1.0) * u + D * (ul - 2.0 * u + ur);
+        dy[2 * i + 1] = B * u - uuv + D * (vl - 2.0 * v + vr);
+    }
+}
+
 /* Events functions of solve_ivp (numbalsoda_b200/csrc/events_builtin.cu):
  *   lv_prey   /root/reference/solve_ivp.ipynb cell 9: prey population u[0] crosses 1
  *   lorenz_z  z crosses the level in the 4th parameter */
@@ -103,5 +124,7 @@ oracle_rhs_fn oracle_builtin_rhs(const char *name)
         return oracle_rhs_robertson;
     if (!strcmp(name, "brusselator1d"))
         return oracle_rhs_brusselator1d;
+    if (!strcmp(name, "brusselator1d_il"))
+        return oracle_rhs_brusselator1d_il;
     return 0;
 }

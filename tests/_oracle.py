@@ -140,7 +140,7 @@ def _tol_arg(x, B, n):
 
 
 def solve_batch(solver, fptr, u0, t_eval, data, rtol, atol, mxstep=10000,
-                exit_on_warning=False, nthreads=0):
+                exit_on_warning=False, nthreads=0, band=None):
     """solver: 'dop853' | 'lsoda'.  u0 [B,n] or [n]; data [B,p] or [p]; rtol / atol scalars,
     [B] (per trajectory), [n] or [1,n] (per component) or [B,n]."""
     u0 = np.ascontiguousarray(u0, dtype=np.float64)
@@ -153,6 +153,7 @@ def solve_batch(solver, fptr, u0, t_eval, data, rtol, atol, mxstep=10000,
     cnt = np.zeros((B, 8), dtype=np.int32)
     rs, rv, rvs = _tol_arg(rtol, B, n)
     as_, av, avs = _tol_arg(atol, B, n)
+    lib.oracle_batch_set_band(*(band if band is not None else (-1, -1)))  # lsoda: jt = 5 with (ml, mu)
     lib.oracle_solve_batch_v.restype = ct.c_int
     lib.oracle_solve_batch_v(0 if solver == "dop853" else 1, ct.c_void_p(fptr), ct.c_long(B), n,
                              _p(u0), ct.c_long(n if u0.ndim == 2 else 0), _p(data),
@@ -161,6 +162,7 @@ def solve_batch(solver, fptr, u0, t_eval, data, rtol, atol, mxstep=10000,
                              _p(rv) if rv is not None else None, ct.c_long(rvs),
                              _p(av) if av is not None else None, ct.c_long(avs), int(mxstep),
                              int(exit_on_warning), _p(ok), _p(cnt), int(nthreads))
+    lib.oracle_batch_set_band(-1, -1)
     return us, ok == 1, cnt
 
 

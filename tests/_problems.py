@@ -53,6 +53,34 @@ def brusselator_rhs(t, u, du, p):
         du[m + i] = B * uu - uuv + D * (vl - 2.0 * v + vr)
 
 
+def brusselator_il_rhs(t, u, du, p):
+    # the same problem with the species interleaved (u_0, v_0, u_1, v_1, ...): banded, ml = mu = 2
+    A = p[0]
+    B = p[1]
+    D = p[2]
+    m = 32
+    for i in range(m):
+        uu = u[2 * i]
+        v = u[2 * i + 1]
+        ul = A if i == 0 else u[2 * i - 2]
+        ur = A if i == m - 1 else u[2 * i + 2]
+        vl = B if i == 0 else u[2 * i - 1]
+        vr = B if i == m - 1 else u[2 * i + 3]
+        uuv = uu * uu * v
+        du[2 * i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur)
+        du[2 * i + 1] = B * uu - uuv + D * (vl - 2.0 * v + vr)
+
+
+def interleave(y):
+    """[u_0..u_31, v_0..v_31] (last axis) -> [u_0, v_0, u_1, v_1, ...]"""
+    y = np.asarray(y)
+    m = y.shape[-1] // 2
+    out = np.empty_like(y)
+    out[..., 0::2] = y[..., :m]
+    out[..., 1::2] = y[..., m:]
+    return out
+
+
 def growth_rhs(t, u, du, p):
     # tests/test_exit_on_warning.py:13-14
     du[0] = p[0] * u[0] * np.sin(t)

@@ -29,7 +29,17 @@ extern "C" const B200LsodaTables* lsoda_core_tables(void) { return &g_tables; }
 
 static void core_run(rhs_fn f, int neq, const double* u0, void* data, int nt, const double* teval,
                      double* usol, const LsTol& tol, int mxstep, int* success, int exit_on_warning,
-                     int* counters);
+                     int* counters, int ml = -1, int mu = -1);
+
+// banded finite-difference Jacobian (warp backend only)
+extern "C" void lsoda_core_host_band(rhs_fn f, int neq, const double* u0, void* data, int nt,
+                                     const double* teval, double* usol, double rtol, double atol,
+                                     int ml, int mu, int mxstep, int* success, int exit_on_warning,
+                                     int* counters)
+{
+    LsTol tol = {rtol, atol, nullptr, nullptr};
+    core_run(f, neq, u0, data, nt, teval, usol, tol, mxstep, success, exit_on_warning, counters, ml, mu);
+}
 
 extern "C" void lsoda_core_host(rhs_fn f, int neq, const double* u0, void* data, int nt,
                                 const double* teval, double* usol, double rtol, double atol,
@@ -51,7 +61,7 @@ extern "C" void lsoda_core_host_vtol(rhs_fn f, int neq, const double* u0, void* 
 
 static void core_run(rhs_fn f, int neq, const double* u0, void* data, int nt, const double* teval,
                      double* usol, const LsTol& tol, int mxstep, int* success, int exit_on_warning,
-                     int* counters)
+                     int* counters, int ml, int mu)
 {
     g_rhs = f;
     LsLane s;
@@ -61,15 +71,16 @@ static void core_run(rhs_fn f, int neq, const double* u0, void* data, int nt, co
         *success = -99;
         return;
     }
-    std::vector<double> store(B200ODE_LSODAW_DOUBLES(neq), 0.0);
+    std::vector<double> store(ml >= 0 ? B200ODE_LSODAW_BAND_DOUBLES(neq, ml, mu) : B200ODE_LSODAW_DOUBLES(neq), 0.0);
     LsWarpVec v;
-    v.attach(store.data(), neq, (exit_on_warning & 2) != 0);  // bit 1 of the flag: fast solves
+    v.attach(store.data(), neq, (exit_on_warning & 2) != 0, nullptr, ml, mu);  // bit 1 of the flag: fast solves
     exit_on_warning &= 1;
 #else
     if (neq != N) {
         *success = -99;
         return;
     }
+    (void)ml, (void)mu;
     double yh[13 * N], wm[N * N];
     memset(yh, 0, sizeof yh);
     memset(wm, 0, sizeof wm);

@@ -1,0 +1,58 @@
+"""The banded finite-difference Jacobian (lsoda(..., ml=, mu=)) on the
+GPU: strict mode bit for bit against the oracle's band path (pinned in tests/test_banded.py against
+the dense reference path and ODEPACK's own jt = 5), and against the dense run within tolerance."""
+import numpy as np
+import pytest
+
+import _oracle as orc
+import _problems as pr
+
+pytestmark = pytest.mark.gpu
+
+
+def _nb():
+    import numbalsoda_b200 as nb
+    return nb
+
+
+def test_brusselator_n64_band_2_2_strict_bitwise_and_close_to_dense():
+    nb = _nb()
+    B = 200
+    P = pr.brusselator_sweep(B, 3)
+    u0, te = pr.interleave(pr.brusselator_u0()), np.linspace(0, 10, 100)
+    f = orc.builtin_rhs("brusselator1d_il")
+    us, ok, cnt = nb.lsoda(nb.builtin("brusselator1d_il"), u0, te, P, 1e-6, 1e-8, strict=True, counters=True,
+                           ml=2, mu=2)
+    ref, okr, cr = orc.solve_batch("lsoda", f, u0, te, P, 1e-6, 1e-8, band=(2, 2))
+    assert ok.all() and okr.all() and np.array_equal(cnt, cr) and np.array_equal(us, ref)
+    # the dense kernel on the same (interleaved) system, and the dense oracle
+    ud, okd, cd = nb.lsoda(nb.builtin("brusselator1d_il"), u0, te, P, 1e-6, 1e-8, strict=True, counters=True)
+    dref, _, cdr = orc.solve_batch("lsoda", f, u0, te, P, 1e-6, 1e-8)
+    assert okd.all() and np.array_equal(ud, dref) and np.array_equal(cd, cdr)
+    assert (np.abs(us - ud) / (1e-6 * np.abs(ud) + 1e-8)).max() < 10.0  # north_star: 10 rtol
+    assert np.array_equal(cnt[:, 2], cd[:, 2]) and (cnt[:, 1] < cd[:, 1]).all()
+    # default (throughput) mode
+    uf, okf = nb.lsoda(nb.builtin("brusselator1d_il"), u0, te, P, 1e-6, 1e-8, ml=2, mu=2)
+    assert okf.all() and (np.abs(uf - ud) / (1e-6 * np.abs(ud) + 1e-8)).max() < 10.0
+
+
+@pytest.mark.parametrize("n,ml,mu", [(20, 1, 1), (33, 1, 1), (12, 3, 2), (40, 5, 7), (9, 8, 8), (10, 0, 2),
+                                     (10, 2, 0), (128, 1, 1)])
+def test_bandwidths_with_a_numba_rhs_strict_bitwise(n, ml, mu):
+    nb = _nb()
+    u0 = 1.0 + 0.1 * np.arange(n)
+    P = np.array([[200.0 * (1 + b), float(n)] for b in range(7)])
+    te = np.linspace(0, 5, 11)
+    us, ok, cnt = nb.lsoda(pr.chain_rhs, u0, te, P, 1e-7, 1e-9, strict=True, counters=True, ml=ml, mu=mu)
+    ref, okr, cr = orc.solve_batch("lsoda", pr.cfunc_address(pr.chain_rhs), u0, te, P, 1e-7, 1e-9, band=(ml, mu))
+    assert list(ok) == list(okr) and np.array_equal(cnt, cr) and np.array_equal(us, ref)
+
+
+def test_small_systems_keep_the_dense_matrix():
+    """n <= 8 runs one trajectory per thread with the dense matrix in shared memory: ml / mu are
+    accepted and the result is the dense one (a banded matrix is a dense matrix with zeros)."""
+    nb = _nb()
+    p = pr.problem("robertson")
+    a = nb.lsoda(nb.builtin("robertson"), p["u0"], p["t_eval"], p["data"], 1e-8, 1e-8, strict=True, ml=2, mu=2)
+    b = nb.lsoda(nb.builtin("robertson"), p["u0"], p["t_eval"], p["data"], 1e-8, 1e-8, strict=True)
+    assert a[1] and np.array_equal(a[0], b[0])
