@@ -6,5 +6,10 @@ from .driver_solve_ivp import solve_ivp, ODEResult, ODEResultBatch
 from .rhs import builtin, register, get_handle
 from ._lib import B200OdeError, pinned_empty
 
+try:  # numba present: make lsoda / dop853 resolvable inside @njit code (reference driver.py:28)
+    from . import _njit_overloads  # noqa: F401
+except ImportError:  # pragma: no cover
+    pass
+
 __all__ = ["lsoda_sig", "lsoda", "dop853", "solve_ivp", "ODEResult", "ODEResultBatch", "address_as_void_pointer", "builtin", "register",
            "get_handle", "B200OdeError", "pinned_empty"]

@@ -23,7 +23,9 @@
 
 __constant__ B200LsodaTables b200_lsoda_tables = B200_LSODA_TABLES_INIT;
 
-extern "C" __global__ void __launch_bounds__(32)
+// (min 12 blocks per SM: 168 registers, no spills.  The dense matrix limits an SM to 4 warps by
+// shared memory at n = 64 anyway; the banded one fits 12.)
+extern "C" __global__ void __launch_bounds__(32, 12)
 b200ode_lsodaw_kernel(const B200OdeLaunch L)
 {
     extern __shared__ double b200_smem[];

@@ -49,7 +49,7 @@ def test_thread_kernels_every_shape_strict_bitwise(solver, rhs, u0, te, sweep):
     ref, okr, cr = orc.solve_batch(solver, f, u0, te, P, rBn, aBn)
     # (tolerances down to 1e-12 on a chaotic system: only closeness at the loosest level is asked;
     # accuracy of the throughput mode is the subject of tests/test_gpu_truth.py)
-    assert ok.all() and (np.abs(us - ref) / (1.0 + np.abs(ref))).max() < 1e-5
+    assert ok.all() and (np.abs(us - ref) / (1.0 + np.abs(ref))).max() < 1e3 * rBn.max()
 
 
 def test_single_trajectory_and_numba_rhs():
