@@ -117,3 +117,49 @@ def test_solve_ivp_njit_matches_the_oracle():
         k2 = res2[b, 3]
         assert np.array_equal(t2[off2[b]:off2[b] + k2], rb["t"][b, :k2])
         assert np.array_equal(y2[off2[b]:off2[b] + k2], rb["y"][b, :k2])
+
+
+# ---- the reference's own call, verbatim, from inside @njit (README.md:60-67, driver.py:28)
+def _reference_style():
+    import numbalsoda_b200 as b2
+    from numbalsoda_b200 import lsoda, dop853
+    cf = nb.cfunc(b2.lsoda_sig)(pr.lv_rhs)
+    funcptr = cf.address
+    u0, t_eval, data = np.array([5.0, 0.8]), np.linspace(0.0, 10.0, 11), np.array([1.0])
+
+    @nb.njit
+    def test():
+        usol, success = lsoda(funcptr, u0, t_eval, data=data, rtol=1e-8, atol=1e-8)
+        return usol, success
+
+    @nb.njit
+    def test_dop(fp, P):
+        usol, success = dop853(fp, u0, t_eval, P, 1e-8, 1e-8)
+        return usol, success
+
+    return cf, test, test_dop
+
+
+def test_reference_signature_resolves_in_nopython_code_and_fails_loudly_without_a_device():
+    import torch
+    import numbalsoda_b200 as b2
+    cf, test, test_dop = _reference_style()
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    for call in (lambda: test(), lambda: test_dop(cf.address, np.ones((4, 1)))):
+        with pytest.raises(b2.B200OdeError, match="no CPU fallback"):
+            call()
+
+
+@pytest.mark.gpu
+def test_reference_signature_inside_njit_matches_the_reference_known_answer():
+    cf, test, test_dop = _reference_style()
+    usol, success = test()
+    # /root/reference/tests/test_numbalsoda.py:19-20 (default mode: FMA contraction, so isclose)
+    assert success and usol.shape == (11, 2)
+    assert np.all(np.isclose(usol[-1], [0.38583246250193476, 4.602012234037773]))
+    P = np.random.default_rng(1).uniform(0.5, 2.0, (6, 1))
+    us, ok = test_dop(cf.address, P)
+    ref, okr, _ = orc.solve_batch("dop853", cf.address, np.array([5.0, 0.8]), np.linspace(0.0, 10.0, 11), P,
+                                  1e-8, 1e-8)
+    assert us.shape == (6, 11, 2) and ok.all() and (np.abs(us - ref) / (1e-8 * np.abs(ref) + 1e-8)).max() < 10.0
