@@ -72,10 +72,13 @@
 #define LS_P_STEP 0     // about to start a step
 #define LS_P_ATTEMPT 1  // about to predict (first attempt of a step, or a retry)
 #define LS_P_ITER 2     // inside the corrector iteration
+#define LS_P_JACWAIT 3  // deferred backends: the iteration matrix was requested; the corrector
+                        // resumes on the next pass with the right-hand side it already has
 // work a pass leaves for the trajectory's next pass
 #define LS_F_RESCALE 1u  // apply scaleh with the ratio s.rh
 #define LS_F_RMAX10 2u   // ... then rmax = 10 (the rescale ends an accepted step)
 #define LS_F_FINISH 4u   // an accepted step is complete: endstoda, output rows
+#define LS_F_REFRESH 8u  // deferred backends: yh[2] = h f(tn, yh[1]) is due once the retraction is done
 
 // The scalars of class LSODA (LSODA.h:105-143) plus the locals of stoda / correction
 // that outlive a pass of the state machine.
@@ -442,10 +445,20 @@ LS_FN bool ls_begin(LsLane& s, LsRun& R, V& v, const double* u0, double* pp, int
 // the exits instead, and v.sync(lanes) -- __syncwarp over the lanes that entered; a
 // no-op in the host build and for the warp backend, whose 32 lanes run one trajectory
 // in lock step -- pins the lanes together between blocks.
+// Deferred backends (V::kDeferred; the thread-per-trajectory kernel, lsoda_kernel.cu).  The
+// blocks of a pass that few lanes of a warp need at a time -- the Jacobian and its LU, the
+// retraction after a failed attempt, the rescale after a step-size change, the output rows --
+// are what kept 12 of 32 lanes busy (ncu, profiles/r2_lsoda_v0_baseline.txt: 41 % of the warp
+// instructions ran with 2-7 lanes).  Their vector work touches only what already lives in
+// shared memory (yh, the matrix) plus a few values that are cheap to hand over, so a lane that
+// needs one of them *requests* it (v.scale_yh, v.pascal<false>, v.intdy_at, v.request_jac)
+// and the block serves all requests of a pass together, compacted by kind, between the two
+// halves of the pass (ls_advance_a: blocks 0-1; ls_advance_b: blocks 2-5).  Per trajectory the
+// operations and their order are unchanged, so strict mode stays bit-exact.  For the other
+// backends the requests execute on the spot and ls_advance is the two halves back to back.
 template <class V>
-LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, double* pp, int nt,
-                      const double* teval, double* usol, const LsTol& tol,
-                      unsigned long long mxstep_u, int exit_on_warning, unsigned lanes)
+LS_FN bool ls_advance_a(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, int nt,
+                        const double* teval, double* usol, unsigned lanes)
 {
 #define LS_SYNC() v.sync(lanes)
     const int n = v.size();
@@ -496,7 +509,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
                         v.store_y(usol + (size_t)R.row * n);
                     } else {
                         // intdy with k = 0, LSODA.cpp:1435-1453
-                        v.intdy(s.nq, ls_div(tout - s.tn, s.h), usol + (size_t)R.row * n);
+                        v.intdy_at(s.nq, s.tn, s.h, tout, R.row, usol);
                     }
                     first_in_step = false;
                     R.nslast = s.nst;
@@ -515,6 +528,25 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
         }
     }
     LS_SYNC();
+    return fin;
+#undef LS_SYNC
+}
+
+template <class V>
+LS_FN bool ls_advance_b(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, double* pp,
+                        const LsTol& tol, unsigned long long mxstep_u, int exit_on_warning,
+                        unsigned lanes)
+{
+#define LS_SYNC() v.sync(lanes)
+    const int n = v.size();
+    double pdh = 0.0;
+    bool fin = false;
+    if (V::kDeferred && (s.flags & LS_F_REFRESH)) {
+        // (the tail of the three-failures recovery, LSODA.cpp:1347-1353, after the retraction)
+        s.flags &= ~LS_F_REFRESH;
+        v.refresh_yh2(s.tn, s.h, pp);
+        s.nfe++;
+    }
     // ---- (2) start of a step: lsoda's stop tests (:774-845) and stoda's prologue (:1040-1124)
     if (!fin && s.phase == LS_P_STEP) {
         // ewset (:787-798).  Before the first step yh[1] is u0, whose weights ls_begin
@@ -607,24 +639,45 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
     //      The loop is one code site: the kernel does not grow.)
     bool corfail = false, converged = false;
     bool iterate = go;
+    // deferred backends: the matrix requested on the previous pass is there; take it and go on
+    // with the iteration whose right-hand side (savf) this lane still holds
+    bool resumed = false;
+    if (V::kDeferred && go && s.phase == LS_P_JACWAIT) {
+        const int ierpj = v.take_jac(s.pdnorm);
+        s.nfe += v.jac_rhs_calls();
+        s.ipup = 0;
+        s.rc = 1.0;
+        s.nslp = s.nst;
+        s.crate = 0.7;
+        if (ierpj != 0) corfail = true;
+        s.phase = LS_P_ITER;
+        resumed = true;
+    }
 #pragma unroll 1
     for (int it = 0; it < LS_ITERS_PER_PASS; it++) {
-        if (iterate) {
+        if (iterate && !resumed) {
             v.rhs_savf(s.tn, pp);
             s.nfe++;
             if (s.m == 0 && s.ipup > 0) {
                 // prja (LSODA.cpp:1633-1696): finite-difference Jacobian, P = I - h el0 J, LU
                 s.nje++;
                 s.jcur = 1;
-                const int ierpj = v.prja(s.tn, s.h, s.h * s.el0, pp, s.pdnorm);
-                s.nfe += v.jac_rhs_calls();  // n (LSODA.cpp:1678), or the column groups of a banded one
-                s.ipup = 0;
-                s.rc = 1.0;
-                s.nslp = s.nst;
-                s.crate = 0.7;
-                if (ierpj != 0) corfail = true;
+                if (V::kDeferred) {
+                    v.request_jac(s.tn, s.h, s.h * s.el0);
+                    s.phase = LS_P_JACWAIT;
+                    iterate = false;  // this lane's pass ends here
+                } else {
+                    const int ierpj = v.prja(s.tn, s.h, s.h * s.el0, pp, s.pdnorm);
+                    s.nfe += v.jac_rhs_calls();  // n (LSODA.cpp:1678), or the column groups of a banded one
+                    s.ipup = 0;
+                    s.rc = 1.0;
+                    s.nslp = s.nst;
+                    s.crate = 0.7;
+                    if (ierpj != 0) corfail = true;
+                }
             }
         }
+        resumed = false;
         LS_SYNC();
         if (iterate && !corfail) {
             if (s.m == 0) v.acor_zero();
@@ -720,7 +773,7 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
         // both retract the prediction
         s.rmax = 2.0;
         s.tn = s.told;
-        v.template pascal<false>(s.nq);
+        v.request_retract(s.nq);  // pascal<false>: :1290-1295, :1909-1912
         s.phase = LS_P_ATTEMPT;
         const bool h_is_zero = fabs(s.h) <= 0.0 * 1.00001;  // hmin = 0
         if (corfail) {
@@ -748,8 +801,12 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
                 s.rh = 0.1;
                 s.rh = ls_max(ls_hmin_ratio(s.h), s.rh);
                 s.h *= s.rh;
-                v.refresh_yh2(s.tn, s.h, pp);  // y = yh[1]; yh[2] = h f(tn, y)
-                s.nfe++;
+                if (V::kDeferred) {
+                    s.flags |= LS_F_REFRESH;  // after the retraction requested above is served
+                } else {
+                    v.refresh_yh2(s.tn, s.h, pp);  // y = yh[1]; yh[2] = h f(tn, y)
+                    s.nfe++;
+                }
                 s.ipup = miter;
                 s.ialth = 5;
                 if (s.nq != 1) {
@@ -778,6 +835,16 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
     LS_SYNC();
     return fin;
 #undef LS_SYNC
+}
+
+// One pass for a backend that executes every operation on the spot.
+template <class V>
+LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, double* pp, int nt,
+                      const double* teval, double* usol, const LsTol& tol,
+                      unsigned long long mxstep_u, int exit_on_warning, unsigned lanes)
+{
+    if (ls_advance_a(s, R, v, T, nt, teval, usol, lanes)) return true;
+    return ls_advance_b(s, R, v, T, pp, tol, mxstep_u, exit_on_warning, lanes);
 }
 
 #endif

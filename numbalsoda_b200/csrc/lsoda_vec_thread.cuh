@@ -25,6 +25,31 @@
 #endif
 
 #define LS_FOR_N _Pragma("unroll") for (int i = 0; i < N; i++)
+// request fields of the deferred operations (LS_DEFERRED)
+#define LS_OP_RETRACT 1u
+#define LS_OP_SCALE 2u
+#define LS_OP_ROWS 4u
+#define LS_OP_JAC 8u
+#define LS_RD_RH 0
+#define LS_RD_TN 1
+#define LS_RD_H 2
+#define LS_RD_JTN 3  // in: tn; out: pdnorm
+#define LS_RD_JH 4
+#define LS_RD_JHL0 5
+#define LS_RD_COUNT 6
+#define LS_RI_RETRACT_NQ 0
+#define LS_RI_SCALE_L 1
+#define LS_RI_ROW0 2
+#define LS_RI_NROWS 3
+#define LS_RI_NQ 4
+#define LS_RI_IERPJ 5
+#define LS_RI_IPVT 6
+#define LS_RI_BLO 7
+#define LS_RI_BHI 8
+#define LS_RI_COUNT 9
+#define LS_JAC_SLOT_Y 8
+#define LS_JAC_SLOT_F 9
+#define LS_JAC_SLOT_W 10
 // yh[j][i], j = 1..13 (LSODA.h:114); wm[r][c] = d f_r / d y_c (LSODA.cpp:1680)
 #define YH(j, i) yhp[(((j) - 1) * N + (i)) * LS_STRIDE]
 #define WM(r, c) wmp[((r) * N + (c)) * LS_STRIDE]
@@ -40,6 +65,68 @@ struct LsThreadVec {
 
     LS_MFN int size() const { return N; }
     LS_MFN int jac_rhs_calls() const { return N; }
+
+#if defined(LS_DEFERRED)
+    // ---- deferred operations (lsoda_core.cuh: deferred backends; served by ls_serve in
+    //      lsoda_kernel.cu).  A request is a few fields in this thread's slots of the block's
+    //      request area (LS_REQD / LS_REQI: [field][thread], defined by the kernel file) and a
+    //      bit in `ops`; the state the server needs beyond that -- yh, the matrix -- already
+    //      lives in shared memory.  The Jacobian's inputs (y, f(tn, y), the weights) travel in
+    //      yh slots 8-10: a Jacobian is only ever requested by the BDF method, whose orders
+    //      (<= 5) use slots 1-6, and the Adams method initialises every slot it grows into.
+    static const bool kDeferred = true;
+    unsigned ops;
+    LS_MFN void scale_yh(int l, double rh)
+    {
+        LS_REQI(LS_RI_SCALE_L) = l;
+        LS_REQD(LS_RD_RH) = rh;
+        ops |= LS_OP_SCALE;
+    }
+    LS_MFN void request_retract(int nq)
+    {
+        LS_REQI(LS_RI_RETRACT_NQ) = nq;
+        ops |= LS_OP_RETRACT;
+    }
+    LS_MFN void intdy_at(int nq, double tn, double h, double, int row, double*)
+    {
+        if (!(ops & LS_OP_ROWS)) {
+            LS_REQI(LS_RI_ROW0) = row;
+            LS_REQI(LS_RI_NROWS) = 0;
+            LS_REQI(LS_RI_NQ) = nq;
+            LS_REQD(LS_RD_TN) = tn;
+            LS_REQD(LS_RD_H) = h;
+            ops |= LS_OP_ROWS;
+        }
+        LS_REQI(LS_RI_NROWS) = LS_REQI(LS_RI_NROWS) + 1;
+    }
+    LS_MFN void request_jac(double tn, double h, double hl0)
+    {
+        LS_REQD(LS_RD_JTN) = tn;
+        LS_REQD(LS_RD_JH) = h;
+        LS_REQD(LS_RD_JHL0) = hl0;
+        LS_FOR_N {
+            YH(LS_JAC_SLOT_Y, i) = y[i];
+            YH(LS_JAC_SLOT_F, i) = savf[i];
+            YH(LS_JAC_SLOT_W, i) = ewt[i];
+        }
+        ops |= LS_OP_JAC;
+    }
+    LS_MFN int take_jac(double& pdnorm)
+    {
+        pdnorm = LS_REQD(LS_RD_JTN);
+        ipvt = (unsigned)LS_REQI(LS_RI_IPVT);
+        return LS_REQI(LS_RI_IERPJ);
+    }
+#else
+    static const bool kDeferred = false;
+    LS_MFN void request_jac(double, double, double) {}
+    LS_MFN int take_jac(double&) { return 0; }
+    LS_MFN void request_retract(int nq) { pascal<false>(nq); }
+    LS_MFN void intdy_at(int nq, double tn, double h, double tout, int row, double* usol) const
+    {
+        intdy(nq, ls_div(tout - tn, h), usol + (size_t)row * N);
+    }
+#endif
     LS_MFN void sync(unsigned lanes)
     {
 #if defined(__CUDA_ARCH__)
@@ -100,7 +187,7 @@ struct LsThreadVec {
         }
     }
 
-    LS_MFN void scale_yh(int l, double rh)
+    LS_MFN void scale_yh_now(int l, double rh)
     {
         double r = 1.0;
         for (int j = 2; j <= l; j++) {
@@ -108,6 +195,9 @@ struct LsThreadVec {
             LS_FOR_N YH(j, i) = YH(j, i) * r;
         }
     }
+#if !defined(LS_DEFERRED)
+    LS_MFN void scale_yh(int l, double rh) { scale_yh_now(l, rh); }
+#endif
 
     LS_MFN void y_from_yh1() { LS_FOR_N y[i] = YH(1, i); }
     LS_MFN void rhs_savf(double t, double* pp) { b200ode_user_rhs(t, y, savf, pp); }
@@ -291,6 +381,42 @@ struct LsThreadVec {
         }
     }
 
+#if defined(LS_DEFERRED)
+    // prja for a requester (request_jac): the same operations as prja() below, with y,
+    // savf = f(tn, y) and the weights read from the yh slots the requester left them in, so that
+    // the serving thread -- which keeps its own trajectory in registers meanwhile -- needs
+    // registers for one perturbed state and one right-hand side only.  acor of the requester is
+    // not touched (the caller clears it afterwards, LSODA.cpp:1789).  Returns ierpj; ipvt = pivots.
+    LS_MFN int prja_remote(double tn, double h, double hl0, double* pp, double& pdnorm)
+    {
+        double fac = 0.0;
+        LS_FOR_N fac = ls_max(fac, fabs(YH(LS_JAC_SLOT_F, i)) * YH(LS_JAC_SLOT_W, i));
+        double r0 = 1000.0 * fabs(h) * LS_ETA * ((double)N) * fac;
+        if (r0 == 0.0) r0 = 1.0;
+#pragma unroll 1
+        for (int j = 0; j < N; j++) {
+            const double yj = YH(LS_JAC_SLOT_Y, j), ewtj = YH(LS_JAC_SLOT_W, j);
+            const double r = ls_max(LS_SQRTETA * fabs(yj), ls_div_rare(r0, ewtj));
+            double yp[N], fp[N];
+            LS_FOR_N yp[i] = (i == j) ? YH(LS_JAC_SLOT_Y, i) + r : YH(LS_JAC_SLOT_Y, i);
+            fac = ls_div_rare(-hl0, r);
+            b200ode_user_rhs(tn, yp, fp, pp);
+            LS_FOR_N WM(i, j) = (fp[i] - YH(LS_JAC_SLOT_F, i)) * fac;
+        }
+        double an = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            double sum = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; c++) sum += ls_div_rare(fabs(WM(r, c)), YH(LS_JAC_SLOT_W, c));
+            an = ls_max(an, sum * YH(LS_JAC_SLOT_W, r));
+        }
+        pdnorm = ls_div_rare(an, fabs(hl0));
+        LS_FOR_N WM(i, i) = WM(i, i) + 1.0;
+        return dgefa() != 0 ? 1 : 0;
+    }
+#endif
+
     // prja, LSODA.cpp:1633-1696 (miter == 2: dense finite-difference Jacobian), fnorm
     // (:1714-1736) and the LU factorisation.  Uses y, savf = f(tn, y), ewt; acor is
     // scratch (the caller clears it afterwards, :1789).  Returns ierpj.
@@ -329,5 +455,42 @@ struct LsThreadVec {
         return dgefa() != 0 ? 1 : 0;
     }
 };
+
+// One request of a deferred backend, served for the owner whose shared-memory columns `sv`
+// views (LS_REQD_OF / LS_REQI_OF(o, f): field f of owner o's request, defined by the includer):
+//   kind 0  Jacobian + LU                          (prja, dgefa: LSODA.cpp:1633-1696, :173-231)
+//   kind 1  retraction, then the rescale if any    (:1290-1295 / :1909-1912, scaleh :1621-1627)
+//   kind 2  rescale, then the output rows if any   (scaleh; intdy :1435-1453)
+//   kind 3  output rows only
+// pp: the owner's parameters (kind 0); teval / usol: t_eval and the owner's [nt, N] block (kinds 2, 3).
+#if defined(LS_DEFERRED)
+LS_FN void ls_serve_request(int kind, LsThreadVec& sv, int o, double* pp, const double* teval, double* usol)
+{
+    if (kind == 0) {
+        double pdnorm;
+        const int ierpj = sv.prja_remote(LS_REQD_OF(o, LS_RD_JTN), LS_REQD_OF(o, LS_RD_JH),
+                                         LS_REQD_OF(o, LS_RD_JHL0), pp, pdnorm);
+        LS_REQD_OF(o, LS_RD_JTN) = pdnorm;
+        LS_REQI_OF(o, LS_RI_IERPJ) = ierpj;
+        LS_REQI_OF(o, LS_RI_IPVT) = (int)sv.ipvt;
+        return;
+    }
+    if (kind == 1) sv.template pascal<false>(LS_REQI_OF(o, LS_RI_RETRACT_NQ));
+    const int l = LS_REQI_OF(o, LS_RI_SCALE_L);
+    if (kind <= 2 && l > 0) sv.scale_yh_now(l, LS_REQD_OF(o, LS_RD_RH));
+    const int nrows = LS_REQI_OF(o, LS_RI_NROWS);
+    if (kind >= 2 && nrows > 0) {
+        const int row0 = LS_REQI_OF(o, LS_RI_ROW0), nq = LS_REQI_OF(o, LS_RI_NQ);
+        const double tn = LS_REQD_OF(o, LS_RD_TN), h = LS_REQD_OF(o, LS_RD_H);
+        double* out = usol + (size_t)row0 * N;
+        for (int k = 0; k < nrows; k++, out += N) sv.intdy(nq, ls_div(teval[row0 + k] - tn, h), out);
+    }
+}
+// the queue a thread with pending operations `ops` belongs to (-1: none)
+LS_FN int ls_request_kind(unsigned ops)
+{
+    return (ops & LS_OP_JAC) ? 0 : (ops & LS_OP_RETRACT) ? 1 : (ops & LS_OP_SCALE) ? 2 : (ops & LS_OP_ROWS) ? 3 : -1;
+}
+#endif
 
 #endif

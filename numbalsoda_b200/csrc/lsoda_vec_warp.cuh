@@ -115,6 +115,15 @@ struct LsWarpVec {
     LS_MFN int jac_rhs_calls() const { return banded() && ml + mu + 1 < n ? ml + mu + 1 : n; }
     LS_MFN int size() const { return n; }
     LS_MFN void sync(unsigned) {}
+    // every operation executes on the spot (lsoda_core.cuh: deferred backends)
+    static const bool kDeferred = false;
+    LS_MFN void request_jac(double, double, double) {}
+    LS_MFN int take_jac(double&) { return 0; }
+    LS_MFN void request_retract(int nq) { pascal<false>(nq); }
+    LS_MFN void intdy_at(int nq, double tn, double h, double tout, int row, double* usol) const
+    {
+        intdy(nq, ls_div(tout - tn, h), usol + (size_t)row * n);
+    }
 
     LS_MFN double norm_ptr(const double* v) const { return wv_wmax_norm(v, ewt, n); }
     LS_MFN double norm_yh(int j) const { return norm_ptr(yh + (j - 1) * n); }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_lib.lib, n), n
     _lib.lib.b200ode_version.restype = ct.c_int
-    assert _lib.lib.b200ode_version() == 100
+    assert _lib.lib.b200ode_version() == 101  # include/b200ode.h B200ODE_VERSION
 
 
 def test_link_errors_are_reported():
