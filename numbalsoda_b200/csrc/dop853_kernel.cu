@@ -41,6 +41,9 @@
 #ifndef B200_QCAP
 #define B200_QCAP 64
 #endif
+#ifndef B200_ST_HINT
+#define B200_ST_HINT 0  // cache hint of the output-row stores: 0 plain, 1 L2 evict_last, 2 .cs, 3 .cg
+#endif
 #ifndef B200_MINBLOCKS
 #define B200_MINBLOCKS 1
 #endif
@@ -235,16 +238,40 @@ __device__ DRAIN_INLINE void dop853_drain(const char* data, long long data_strid
     }
     // solout rows [row, row_end): xold = x, hout = h
     double* out = usol + ((size_t)b * (size_t)nt + (size_t)row) * N;
+#if B200_ST_HINT == 1
+    // experiment: keep the partially written lines of the output stream in
+    // L2 until their trajectory has completed them
+    unsigned long long st_policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(st_policy));
+#endif
     for (; row < row_end; row++, out += N) {
         const double tq = DRAIN_TE(row);
         const double s = B200ODE_FAST_CTRL() ? b200_div(tq - x, h) : (tq - x) / h;
         const double s1 = 1.0 - s;
         FOR_N {
             double conpar = c4[i] + s * (c5[i] + s1 * (c6[i] + s * c7[i]));
-            out[i] = c0[i] + s * (c1[i] + s1 * (c2[i] + s * (c3[i] + s1 * conpar)));
+            const double val = c0[i] + s * (c1[i] + s1 * (c2[i] + s * (c3[i] + s1 * conpar)));
+#if B200_ST_HINT == 1
+            asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(out + i), "d"(val), "l"(st_policy) : "memory");
+#elif B200_ST_HINT == 2
+            __stcs(out + i, val);
+#elif B200_ST_HINT == 3
+            __stcg(out + i, val);
+#else
+            out[i] = val;
+#endif
         }
     }
 #undef DRAIN_TE
+}
+
+// sk = atol_i + rtol_i * ymax with per-component tolerances (module :603-612): out of line, see SK_I
+__device__ __noinline__ double dop853_sk_vtol(const double* rv, const double* av, double rtol, double atol,
+                                              double ymax)
+{
+    const double rt = rv ? __ldg(rv) : rtol;
+    const double at = av ? __ldg(av) : atol;
+    return at + rt * ymax;
 }
 
 // STAGED: the first L.np doubles of the trajectory's data record are copied into
@@ -301,6 +328,14 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     // its registers and shared memory.  rtol_vec / atol_vec are uniform over the launch.
 #define RT_I(i, scalar) (L.rtol_vec ? __ldg(L.rtol_b + (long long)b * L.rtol_sb + (i)) : (scalar))
 #define AT_I(i, scalar) (L.atol_vec ? __ldg(L.atol_b + (long long)b * L.atol_sb + (i)) : (scalar))
+    // In the step loop the per-component case is a call behind a launch-uniform branch
+    // (dop853_sk_vtol): written in line, the compiler predicates the six loads and their address
+    // arithmetic and issues them in the scalar case too (16 instructions per step).
+#define SK_I(i, ymax)                                                                              \
+    ((L.rtol_vec | L.atol_vec)                                                                     \
+         ? dop853_sk_vtol(L.rtol_vec ? L.rtol_b + (long long)b * L.rtol_sb + (i) : nullptr,        \
+                          L.atol_vec ? L.atol_b + (long long)b * L.atol_sb + (i) : nullptr, rtol, atol, (ymax)) \
+         : (atol + rtol * (ymax)))
 
     double y[N], y1[N], k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], k8[N], k9[N], k10[N];
     double pl[STAGED ? B200ODE_NPMAX : 1];
@@ -463,7 +498,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     // reciprocals; err holds the *square* of the reference's err (the test
                     // err <= 1 is unchanged by that), ifac = safe / err**(1/8)
                     FOR_N {
-                        const double isk = b200_rcp(AT_I(i, atol) + RT_I(i, rtol) * fmax_(fabs(y[i]), fabs(k5[i])));
+                        const double isk = b200_rcp(SK_I(i, fmax_(fabs(y[i]), fabs(k5[i]))));
                         double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
                         double qq = erri * isk;
                         err2 = err2 + qq * qq;
@@ -480,7 +515,7 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
                     hnew = h * fmin_(DP_FAC2, fmax_(DP_FAC1, ifac));
                 } else {
                     FOR_N {
-                        double sk = AT_I(i, atol) + RT_I(i, rtol) * fmax_(fabs(y[i]), fabs(k5[i]));
+                        double sk = SK_I(i, fmax_(fabs(y[i]), fabs(k5[i])));
                         double erri = k4[i] - DP_BHH1 * k1[i] - DP_BHH2 * k9[i] - DP_BHH3 * k3[i];
                         double qq = erri / sk;
                         err2 = err2 + qq * qq;
