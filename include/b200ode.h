@@ -270,6 +270,16 @@ int b200ode_solve_ivp_args(b200ode_rhs_t ivp, long long B, int neq, const double
 int b200ode_host_alloc(size_t bytes, void** ptr);
 int b200ode_host_free(void* ptr);
 
+/* Device copies of the arrays a `data` record points to.  The
+ * reference lets the right-hand side reach further arrays through addresses stored in its data
+ * structure (address_as_void_pointer, numbalsoda/driver.py:45-53;
+ * passing_data_to_rhs_function.ipynb); on the GPU those addresses must be device addresses:
+ * allocate a buffer on `device`, copy the array into it and store *dptr in the record that is
+ * then passed by address (np = -1).  Synchronous. */
+int b200ode_device_alloc(int device, size_t bytes, void** dptr);
+int b200ode_device_upload(int device, void* dptr, const void* host, size_t bytes);
+int b200ode_device_free(int device, void* dptr);
+
 /* Launch geometry and resource usage of the kernel behind `rhs` on the current
  * device: info = {registers/thread, local bytes/thread, static smem bytes,
  * threads/block, blocks/SM, SM count, grid size of the last launch, kernel launches

@@ -79,6 +79,9 @@ def _load(rebuilt=False):
     lib.b200ode_ivp_message.restype = ct.c_char_p
     lib.b200ode_host_alloc.argtypes = [sz, ct.POINTER(vp)]
     lib.b200ode_host_free.argtypes = [vp]
+    lib.b200ode_device_alloc.argtypes = [i, sz, ct.POINTER(vp)]
+    lib.b200ode_device_upload.argtypes = [i, vp, vp, sz]
+    lib.b200ode_device_free.argtypes = [i, vp]
     return lib
 
 
@@ -88,6 +91,33 @@ lib = _load()
 def check(rc):
     if rc != 0:
         raise B200OdeError("libb200ode error %d: %s" % (rc, lib.b200ode_last_error().decode()))
+
+
+class DeviceBuffer:
+    """A copy of a host array on one GPU: `.ptr` is its device address (an int), to be stored in
+    a `data` record in the place of the host address the reference stores there
+    (passing_data_to_rhs_function.ipynb: `arr.ctypes.data`).  Freed with the object."""
+
+    def __init__(self, array, device=0):
+        import numpy as np
+        a = np.ascontiguousarray(array)
+        self.device, self.nbytes, self.shape, self.dtype = int(device), a.nbytes, a.shape, a.dtype
+        p = ct.c_void_p()
+        check(lib.b200ode_device_alloc(self.device, a.nbytes, ct.byref(p)))
+        self._p = p
+        check(lib.b200ode_device_upload(self.device, p, a.ctypes.data, a.nbytes))
+
+    @property
+    def ptr(self):
+        return int(self._p.value)
+
+    def __del__(self):
+        try:
+            if self._p:
+                lib.b200ode_device_free(self.device, self._p)
+                self._p = None
+        except Exception:
+            pass
 
 
 class _PinnedOwner:

@@ -37,7 +37,8 @@ def _data_layout(data, B_hint):
 
 
 def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning=False,
-          strict=False, device=None, counters=False, out=None, exact_ctrl=False, ml=None, mu=None):
+          strict=False, device=None, counters=False, out=None, exact_ctrl=False, ml=None, mu=None,
+          pointers=None):
     u0 = _as_f64(u0, "u0")
     t_eval = _as_f64(t_eval, "t_eval")
     if data is None:
@@ -54,7 +55,12 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
     B = u0.shape[0] if batched_u0 else (dbuf.shape[0] if batched_data else 1)
     n = u0.shape[-1]
     nt = t_eval.shape[0]
-    handle = _rhs.get_handle(funcptr, solver, n, strict=strict, exact_ctrl=exact_ctrl)
+    # a record `data` (structured dtype): the right-hand side receives the record itself
+    record = dbuf.dtype.fields is not None
+    handle = _rhs.get_handle(funcptr, solver, n, strict=strict, exact_ctrl=exact_ctrl,
+                             data_dtype=dbuf.dtype if record else None)
+    if pointers and not record:
+        raise ValueError("pointers= needs a record (structured dtype) `data`")
     if out is not None:
         # caller-owned result buffer, ideally page-locked (numbalsoda_b200.pinned_empty) and
         # reused across calls: allocating and first touching a fresh multi-gigabyte array
@@ -83,12 +89,27 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
 
     devices = _device_list(device)
 
+    def device_records(dev):
+        """`data` with the fields named in pointers= holding the device addresses of copies of
+        their arrays on GPU `dev` (the reference stores host addresses there:
+        passing_data_to_rhs_function.ipynb); the copies live until the call returns."""
+        if not pointers:
+            return dbuf, []
+        patched = dbuf.copy()
+        keep = []
+        for field, arr in pointers.items():
+            buf = _lib.DeviceBuffer(arr, dev)
+            keep.append(buf)
+            patched[field] = buf.ptr
+        return patched, keep
+
     def run(dev, b0, b1):
         nb = b1 - b0
         if nb <= 0:
             return
         u0p = u0[b0:b1] if batched_u0 else u0
-        dp = dbuf[b0:b1] if batched_data else dbuf
+        dsrc, keep = device_records(dev)
+        dp = dsrc[b0:b1] if batched_data else dsrc
         pb = _lib.Problem()
         pb.size = ct.sizeof(_lib.Problem)
         pb.B, pb.neq, pb.nt, pb.np = nb, n, nt, nps

@@ -69,7 +69,7 @@ extern "C" int b200ode_version(void) { return B200ODE_VERSION; }
     X(cuMemFree_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)      \
     X(cuStreamCreate) X(cuStreamDestroy_v2) X(cuStreamSynchronize) X(cuStreamWaitEvent)     \
     X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord) X(cuEventSynchronize)            \
-    X(cuGetErrorString) X(cuMemGetInfo_v2) X(cuMemHostAlloc) X(cuMemFreeHost)
+    X(cuGetErrorString) X(cuMemGetInfo_v2) X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemcpyHtoD_v2)
 
 struct Driver {
     void* lib = nullptr;
@@ -128,6 +128,7 @@ struct PerDevice {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;      // parameters staged in registers (np >= 0)
     CUfunction fn_ptr = nullptr;  // data record passed by address (np < 0)
+    CUfunction fn_band = nullptr; // warp lsoda: the same kernel built for 12 resident warps (banded matrix)
     CUdeviceptr next = 0;  // kCounterSlots work-queue heads
     int regs = 0, local_bytes = 0, smem = 0, blocks_per_sm = 0, sms = 0;
     int dyn_smem = 0;  // dynamic shared memory per block
@@ -367,9 +368,11 @@ static int init_device_state(b200ode_rhs_t H, int device, PerDevice& P)
     CU(cuModuleLoadData(&P.mod, H->cubin.data()));
     const bool warp = warp_kernel(H->solver, H->neq);
     CU(cuModuleGetFunction(&P.fn, P.mod, kernel_name(H->solver, H->neq)));
-    if (warp)
+    if (warp) {
         P.fn_ptr = P.fn;  // the warp kernel always hands the data record over by address
-    else
+        if (H->solver == B200ODE_LSODA)
+            CU(cuModuleGetFunction(&P.fn_band, P.mod, "b200ode_lsodaw_band_kernel"));
+    } else
         CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
                                (std::string(kernel_name(H->solver, H->neq)) + "_ptr").c_str()));
     CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
@@ -431,6 +434,8 @@ static int init_device_state(b200ode_rhs_t H, int device, PerDevice& P)
         CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
         if (P.fn_ptr != P.fn)
             CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
+        if (P.fn_band)
+            CU(cuFuncSetAttribute(P.fn_band, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
     }
     CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
     CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
@@ -607,6 +612,7 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
         args.ml = args.mu = -1;  // thread kernels and bands as wide as the matrix: dense
     if (args.ml >= 0) {
         // banded iteration matrix: a trajectory needs far less shared memory, more warps fit an SM
+        fn = P->fn_band;
         dyn_smem = B200ODE_LSODAW_BAND_DOUBLES(H->neq, args.ml, args.mu) * (int)sizeof(double);
         int nb = 0;
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, (size_t)dyn_smem));
@@ -1352,6 +1358,62 @@ extern "C" int b200ode_host_free(void* ptr)
     if (!driver())
         return fail(B200ODE_ENODEV, "CUDA driver (libcuda.so.1) not available");
     CU(cuMemFreeHost(ptr));
+    return 0;
+}
+
+// ---------------------------------------------------------------- device copies of embedded arrays
+namespace {
+// makes `device`'s primary context current for the scope of a helper call
+struct DeviceCtx {
+    CtxRestore restore;
+    int rc = 0;
+    explicit DeviceCtx(int device)
+    {
+        if (!driver()) {
+            rc = fail(B200ODE_ENODEV, "CUDA driver (libcuda.so.1) not available");
+            return;
+        }
+        if (device < 0) {
+            rc = fail(B200ODE_EINVAL, "device = %d", device);
+            return;
+        }
+        CUdevice dev;
+        CUcontext ctx = nullptr;
+        CUresult r = g_drv.cuDeviceGet(&dev, device);
+        if (r == CUDA_SUCCESS) r = g_drv.cuDevicePrimaryCtxRetain(&ctx, dev);
+        if (r == CUDA_SUCCESS) r = g_drv.cuCtxSetCurrent(ctx);
+        if (r != CUDA_SUCCESS) rc = cu_fail(r, "selecting the device");
+    }
+};
+}  // namespace
+
+extern "C" int b200ode_device_alloc(int device, size_t bytes, void** dptr)
+{
+    if (!dptr) return fail(B200ODE_EINVAL, "dptr is NULL");
+    *dptr = nullptr;
+    DeviceCtx c(device);
+    if (c.rc) return c.rc;
+    CUdeviceptr p = 0;
+    CU(cuMemAlloc_v2(&p, bytes ? bytes : 1));
+    *dptr = reinterpret_cast<void*>(p);
+    return 0;
+}
+
+extern "C" int b200ode_device_upload(int device, void* dptr, const void* host, size_t bytes)
+{
+    if (!dptr || (!host && bytes)) return fail(B200ODE_EINVAL, "NULL argument");
+    DeviceCtx c(device);
+    if (c.rc) return c.rc;
+    if (bytes) CU(cuMemcpyHtoD_v2(reinterpret_cast<CUdeviceptr>(dptr), host, bytes));
+    return 0;
+}
+
+extern "C" int b200ode_device_free(int device, void* dptr)
+{
+    if (!dptr) return 0;
+    DeviceCtx c(device);
+    if (c.rc) return c.rc;
+    CU(cuMemFree_v2(reinterpret_cast<CUdeviceptr>(dptr)));
     return 0;
 }
 

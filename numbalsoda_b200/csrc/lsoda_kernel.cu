@@ -92,11 +92,19 @@ template <bool STAGED>
 __device__ __forceinline__ void ls_serve(const B200OdeLaunch& L, const int* q, const int* qn)
 {
     const int lane = threadIdx.x & 31;
+    // blocks of at least four warps: warp w serves kind w & 3, every (w >> 2)-th batch of 32
+    // requests of it; smaller blocks: warp w serves kinds w, w + warps, ...
+    constexpr int kWarps = B200_THREADS / 32;
+    constexpr int kGroups = kWarps >= LS_NKINDS ? kWarps / LS_NKINDS : 1;
+    const int w = threadIdx.x >> 5;
+    if (kWarps >= LS_NKINDS && w >= kGroups * LS_NKINDS) return;
 #pragma unroll 1
-    for (int kind = threadIdx.x >> 5; kind < LS_NKINDS; kind += B200_THREADS / 32) {
+    for (int kind = kWarps >= LS_NKINDS ? (w & (LS_NKINDS - 1)) : w; kind < LS_NKINDS;
+         kind += kWarps >= LS_NKINDS ? LS_NKINDS : kWarps) {
         const int cnt = qn[kind];
+        const int r0 = kWarps >= LS_NKINDS ? lane + 32 * (w / LS_NKINDS) : lane;
 #pragma unroll 1
-        for (int r = lane; r < cnt; r += 32) {
+        for (int r = r0; r < cnt; r += 32 * kGroups) {
             const int o = q[kind * B200_THREADS + r];  // the owner's thread index
             LsThreadVec sv;  // a view of the owner's shared-memory columns (its registers stay unused)
             sv.yhp = b200_smem + LS_OFF_YH + o;

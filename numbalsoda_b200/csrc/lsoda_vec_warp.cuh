@@ -542,7 +542,10 @@ struct LsWarpVec {
         return info;
     }
 
-    // dgbsl, job = 0
+    // dgbsl, job = 0.  Every step reads what it needs before anybody writes, so one barrier per
+    // step suffices: forward, lane 0 stores the interchange while lanes 1..lm add the pivot row's
+    // multiples (the lane whose row was interchanged takes the swapped-in value); backward, lane 0
+    // stores the quotient while lanes 0..lm-1 subtract its multiples from the rows above.
     LS_MFN void dgbsl(double* b) const
     {
         const int lda = 2 * ml + mu + 1, m = ml + mu;
@@ -550,26 +553,47 @@ struct LsWarpVec {
             for (int k = 0; k < n - 1; k++) {
                 const int lm = ml < n - 1 - k ? ml : n - 1 - k;
                 const int l = ipvt[k];
-                const double t = b[l];
-                WV_SYNC();
-                if (l != k && WV_LANE == 0) {
-                    b[l] = b[k];
-                    b[k] = t;
-                }
+                const double t = b[l], bk = b[k];
                 const double* ck = wmT + k * lda;
-                for (int i = 1 + WV_LANE; i <= lm; i += WV_NL) b[k + i] = b[k + i] + t * ck[m + i];
+                double upd = 0.0;
+                const int i = 1 + WV_LANE;
+                if (WV_NL > 1) {
+                    if (i <= lm) upd = ((k + i == l) ? bk : b[k + i]) + t * ck[m + i];
+                    WV_SYNC();
+                    if (WV_LANE == 0) {
+                        if (l != k && l > k + lm) b[l] = bk;  // (cannot happen: l <= k + lm)
+                        b[k] = t;
+                    }
+                    if (i <= lm) b[k + i] = upd;
+                    for (int i2 = i + WV_NL; i2 <= lm; i2 += WV_NL)  // ml > 32
+                        b[k + i2] = ((k + i2 == l) ? bk : b[k + i2]) + t * ck[m + i2];
+                } else {
+                    if (l != k) {
+                        b[l] = bk;
+                        b[k] = t;
+                    }
+                    for (int i2 = 1; i2 <= lm; i2++) b[k + i2] = b[k + i2] + t * ck[m + i2];
+                }
                 WV_SYNC();
             }
         }
         for (int k = n - 1; k >= 0; k--) {
             const double* ck = wmT + k * lda;
             const double bk = ls_div(b[k], ck[m]);
-            WV_SYNC();
-            if (WV_LANE == 0) b[k] = bk;
             const int lm = k < m ? k : m;
             const int la = m - lm, lb = k - lm;
             const double t = -bk;
-            for (int i = WV_LANE; i < lm; i += WV_NL) b[lb + i] = b[lb + i] + t * ck[la + i];
+            if (WV_NL > 1) {
+                double upd = 0.0;
+                if (WV_LANE < lm) upd = b[lb + WV_LANE] + t * ck[la + WV_LANE];
+                WV_SYNC();
+                if (WV_LANE == 0) b[k] = bk;
+                if (WV_LANE < lm) b[lb + WV_LANE] = upd;
+                for (int i = WV_LANE + WV_NL; i < lm; i += WV_NL) b[lb + i] = b[lb + i] + t * ck[la + i];
+            } else {
+                b[k] = bk;
+                for (int i = 0; i < lm; i++) b[lb + i] = b[lb + i] + t * ck[la + i];
+            }
             WV_SYNC();
         }
     }

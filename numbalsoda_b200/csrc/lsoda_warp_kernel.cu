@@ -23,10 +23,7 @@
 
 __constant__ B200LsodaTables b200_lsoda_tables = B200_LSODA_TABLES_INIT;
 
-// (min 12 blocks per SM: 168 registers, no spills.  The dense matrix limits an SM to 4 warps by
-// shared memory at n = 64 anyway; the banded one fits 12.)
-extern "C" __global__ void __launch_bounds__(32, 12)
-b200ode_lsodaw_kernel(const B200OdeLaunch L)
+__device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L)
 {
     extern __shared__ double b200_smem[];
     const B200LsodaTables* T = &b200_lsoda_tables;
@@ -73,4 +70,19 @@ b200ode_lsodaw_kernel(const B200OdeLaunch L)
         }
         __syncwarp();
     }
+}
+
+// Two entry points, one body: the dense iteration matrix limits an SM to 4 warps by shared memory
+// at n = 64, so that kernel takes the registers it likes (252); the banded one (ml, mu >= 0) fits
+// 12 warps and is compiled for that (168 registers).
+extern "C" __global__ void __launch_bounds__(32)
+b200ode_lsodaw_kernel(const B200OdeLaunch L)
+{
+    lsodaw_ensemble(L);
+}
+
+extern "C" __global__ void __launch_bounds__(32, 12)
+b200ode_lsodaw_band_kernel(const B200OdeLaunch L)
+{
+    lsodaw_ensemble(L);
 }

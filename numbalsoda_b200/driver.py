@@ -20,7 +20,7 @@ except Exception:  # numba absent: built-in right-hand sides still work
 
 def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, atol=1.0e-6,
           mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False, out=None,
-          exact_ctrl=False, ml=None, mu=None):
+          exact_ctrl=False, ml=None, mu=None, pointers=None):
     """Integrate with the LSODA kernel on the GPU.
 
     funcptr: address of a numba @cfunc(lsoda_sig) (as in the reference), the cfunc, the
@@ -34,16 +34,47 @@ def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, at
     ml + mu + 1 right-hand-side evaluations instead of n and factored as a band matrix -- the
     jt = 5 option the reference's solver checks for, LSODA.cpp:369-392, but does not implement;
     systems of up to 8 equations keep the dense matrix).  rtol / atol may also be arrays: [B] per
-    trajectory, [n] per component, [B,n] both."""
+    trajectory, [n] per component, [B,n] both.  pointers: {field: array} for a record `data` whose
+    integer fields hold the addresses of further arrays (the reference's address_as_void_pointer
+    pattern): each array is copied to the device and its device address stored in that field."""
     return solve(_lib.LSODA, funcptr, u0, t_eval, data, rtol, atol, mxstep,
                  exit_on_warning=exit_on_warning, strict=strict, device=device,
-                 counters=counters, out=out, exact_ctrl=exact_ctrl, ml=ml, mu=mu)
+                 counters=counters, out=out, exact_ctrl=exact_ctrl, ml=ml, mu=mu, pointers=pointers)
 
 
-def address_as_void_pointer(addr):
-    """The reference offers this numba intrinsic (driver.py:45-53) to hand a struct
-    with embedded host pointers to the RHS.  Host pointers cannot be dereferenced on
-    the device; pass flat float64 data or a plain record array instead."""
-    raise NotImplementedError(
-        "address_as_void_pointer: data records with embedded host pointers are not "
-        "supported on the GPU; pass float64[p] / float64[B,p] or a numpy record array")
+try:
+    from numba.extending import intrinsic as _intrinsic
+
+    @_intrinsic(target="generic")
+    def address_as_void_pointer(typingctx, src):
+        """returns a void pointer from a given memory address -- the reference's intrinsic
+        (numbalsoda/driver.py:45-53), registered for the CPU and the CUDA target alike"""
+        from numba.core import cgutils
+        sig = _types.voidptr(src)
+
+        def codegen(cgctx, builder, sig, args):
+            return builder.inttoptr(args[0], cgutils.voidptr_t)
+        return sig, codegen
+
+    @_intrinsic(target="generic")
+    def address_as_pointer(typingctx, src, dtype):
+        """address_as_pointer(addr, numba.float64) -> a typed pointer that can be indexed, on the
+        CPU and on the device: what `nb.carray(address_as_void_pointer(addr), n, dtype=...)` is
+        used for in the reference's notebook (numba.cuda has no carray)."""
+        if isinstance(dtype, _types.NumberClass):
+            ty = dtype.instance_type
+        elif isinstance(dtype, _types.DType):
+            ty = dtype.dtype
+        else:
+            return None
+        sig = _types.CPointer(ty)(src, dtype)
+
+        def codegen(cgctx, builder, sig, args):
+            return builder.inttoptr(args[0], cgctx.get_value_type(sig.return_type))
+        return sig, codegen
+except Exception:  # numba absent
+    def address_as_void_pointer(addr):
+        raise NotImplementedError("address_as_void_pointer needs numba")
+
+    def address_as_pointer(addr, dtype):
+        raise NotImplementedError("address_as_pointer needs numba")

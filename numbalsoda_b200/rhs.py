@@ -106,12 +106,21 @@ def _pyfunc_from_address(addr):
         "object or the Python function instead" % addr)
 
 
-def without_carray(pyfunc):
-    """The reference's benchmark right-hand sides view their raw pointers with
-    `nb.carray(ptr, (n,))` and unpack the views (benchmark/benchmark_lorenz.py:10-13).
-    numba.cuda cannot compile carray; for 1-D views it is only a change of type, so the
-    source is rewritten: `x = nb.carray(ptr, (n,))` -> `x = ptr` and `a, b, c = x` ->
-    `a = x[0]; b = x[1]; c = x[2]`.  The arithmetic is untouched."""
+def without_carray(pyfunc, record_data=False):
+    """The reference's right-hand sides view their raw pointers with `nb.carray`
+    (benchmark/benchmark_lorenz.py:10-13; passing_data_to_rhs_function.ipynb); numba.cuda cannot
+    compile carray.  Where the view is only a change of type the source is rewritten:
+
+      x = nb.carray(ptr, (n,))          ->  x = ptr               (1-D view of a double pointer)
+      a, b, c = x                       ->  a = x[0]; b = x[1]; c = x[2]
+      nb.carray(address_as_void_pointer(a), shape, dtype=T)
+                                        ->  address_as_pointer(a, T)    (indexable typed pointer)
+    and, when the data argument is a record (record_data: the 4th parameter is then typed as
+    the record itself, which numba passes by reference):
+      d = nb.carray(data_p, 1); d[0].f  ->  data_p.f
+      nb.carray(data_p, 1)[0].f         ->  data_p.f
+    CPU dispatchers (`nb.njit` functions) the body calls are compiled as device functions.  The
+    arithmetic is untouched."""
     import ast
     import inspect
     import textwrap
@@ -120,17 +129,57 @@ def without_carray(pyfunc):
     if not isinstance(fdef, ast.FunctionDef):
         raise TypeError("cannot rewrite %r" % (pyfunc,))
     fdef.decorator_list = []
+    data_param = fdef.args.args[3].arg if len(fdef.args.args) >= 4 else None
     views = {}
+    recviews = {}
+
+    def fname(node):
+        f = node.func if isinstance(node, ast.Call) else None
+        return getattr(f, "attr", None) or getattr(f, "id", None)
 
     def is_carray(node):
-        f = node.func if isinstance(node, ast.Call) else None
-        return isinstance(f, (ast.Attribute, ast.Name)) and (getattr(f, "attr", None) == "carray" or
-                                                             getattr(f, "id", None) == "carray")
+        return fname(node) == "carray"
+
+    def shape_is_one(node):
+        shape = node.args[1] if len(node.args) > 1 else None
+        if isinstance(shape, ast.Tuple) and len(shape.elts) == 1:
+            shape = shape.elts[0]
+        return isinstance(shape, ast.Constant) and shape.value == 1
+
+    def is_record_view(node):
+        return (record_data and is_carray(node) and isinstance(node.args[0], ast.Name) and
+                node.args[0].id == data_param and shape_is_one(node))
 
     class Rewrite(ast.NodeTransformer):
-        def visit_Assign(self, node):
+        def visit_Call(self, node):
             self.generic_visit(node)
+            if is_carray(node) and node.args and fname(node.args[0]) == "address_as_void_pointer":
+                dt = node.args[2] if len(node.args) > 2 else None
+                for kw in node.keywords:
+                    if kw.arg == "dtype":
+                        dt = kw.value
+                if dt is None:
+                    raise TypeError("nb.carray on a void pointer needs dtype=")
+                return ast.copy_location(ast.Call(func=ast.Name(id="__b200_address_as_pointer", ctx=ast.Load()),
+                                                  args=[node.args[0].args[0], dt], keywords=[]), node)
+            return node
+
+        def visit_Subscript(self, node):
+            self.generic_visit(node)
+            idx = node.slice
+            zero = isinstance(idx, ast.Constant) and idx.value == 0
+            if zero and is_record_view(node.value):
+                return ast.copy_location(ast.Name(id=data_param, ctx=ast.Load()), node)
+            if zero and isinstance(node.value, ast.Name) and node.value.id in recviews:
+                return ast.copy_location(ast.Name(id=data_param, ctx=ast.Load()), node)
+            return node
+
+        def visit_Assign(self, node):
             t = node.targets[0] if len(node.targets) == 1 else None
+            if isinstance(t, ast.Name) and is_record_view(node.value):
+                recviews[t.id] = True
+                return None  # the view itself disappears; its uses become the record parameter
+            self.generic_visit(node)
             if isinstance(t, ast.Name) and is_carray(node.value):
                 shape = node.value.args[1] if len(node.value.args) > 1 else None
                 dims = shape.elts if isinstance(shape, ast.Tuple) else [shape]
@@ -151,6 +200,17 @@ def without_carray(pyfunc):
     env = dict(pyfunc.__globals__)
     cv = inspect.getclosurevars(pyfunc)
     env.update(cv.nonlocals)
+    from .driver import address_as_pointer
+    env["__b200_address_as_pointer"] = address_as_pointer
+    # nb.njit functions called from the body: the same Python function as a device function
+    try:
+        from numba import cuda
+        from numba.core.dispatcher import Dispatcher
+        for k, val in list(env.items()):
+            if isinstance(val, Dispatcher) and getattr(val, "py_func", None) is not None:
+                env[k] = cuda.jit(device=True)(val.py_func)
+    except Exception:
+        pass
     exec(compile(tree, "<numbalsoda_b200: %s without carray>" % pyfunc.__name__, "exec"), env)
     return env[fdef.name]
 
@@ -174,16 +234,48 @@ def _ltoir_cc():
     return (9, 0)
 
 
-def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs"):
+class _nested_device_functions_for:
+    """Device functions the right-hand side calls (cuda.jit(device=True) dispatchers, e.g. the
+    nb.njit helpers without_carray converts) are compiled by numba for the *current device's*
+    compute capability, which needs a CUDA context.  The image is LTO-IR for nvJitLink, linked
+    for sm_100a whatever numba was told, and linking must work on machines without a GPU: for
+    the duration of a compile the nested dispatchers are told the compute capability the outer
+    function is compiled for."""
+
+    class _Device:
+        def __init__(self, cc):
+            self.compute_capability = cc
+
+    def __init__(self, cc):
+        self.cc = cc
+
+    def __enter__(self):
+        import numba.cuda.dispatcher as disp
+        self.disp, self.saved = disp, disp.get_current_device
+        cc = self.cc
+        disp.get_current_device = lambda: _nested_device_functions_for._Device(cc)
+
+    def __exit__(self, *exc):
+        self.disp.get_current_device = self.saved
+        return False
+
+
+def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs", data_dtype=None):
     """numba.cuda: Python rhs(t, u, du, p) -> LTO-IR of `b200ode_user_rhs` (or, for
-    solve_ivp's events(t, y, out, p), of `b200ode_user_events`)."""
+    solve_ivp's events(t, y, out, p), of `b200ode_user_events`).  data_dtype: a structured numpy
+    dtype -- `data` is then a record and the function receives it as one (numba passes records
+    by reference, so the C ABI still sees the record's address)."""
     from numba import cuda, types
-    sig = (types.double, types.CPointer(types.double), types.CPointer(types.double),
-           types.CPointer(types.double))
+    ptype = types.CPointer(types.double)
+    if data_dtype is not None:
+        import numba
+        ptype = numba.from_dtype(data_dtype)
+    sig = (types.double, types.CPointer(types.double), types.CPointer(types.double), ptype)
 
     def build(f):
-        code, _ = cuda.compile(f, sig, device=True, abi="c",
-                               abi_info={"abi_name": abi_name}, output="ltoir", cc=_ltoir_cc())
+        with _nested_device_functions_for(_ltoir_cc()):
+            code, _ = cuda.compile(f, sig, device=True, abi="c",
+                                   abi_info={"abi_name": abi_name}, output="ltoir", cc=_ltoir_cc())
         return bytes(code)
 
     try:
@@ -193,7 +285,7 @@ def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs"):
             import inspect
             if "carray" not in inspect.getsource(pyfunc):
                 raise first
-            rewritten = without_carray(pyfunc)
+            rewritten = without_carray(pyfunc, record_data=data_dtype is not None)
         except Exception:
             raise first
         return build(rewritten)
@@ -204,8 +296,9 @@ def _is_address(x):
     return isinstance(x, numbers.Integral) and not isinstance(x, bool)
 
 
-def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False):
-    """Link (once per right-hand side, solver, size and mode) and return the handle."""
+def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False, data_dtype=None):
+    """Link (once per right-hand side, solver, size, mode and record type of `data`) and return
+    the handle."""
     flags = _lib.STRICT_FP if strict else (_lib.EXACT_CTRL if exact_ctrl else 0)
     if isinstance(rhs, RhsHandle):
         return rhs
@@ -220,7 +313,7 @@ def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False):
             raise TypeError("right-hand side must be a cfunc address, a cfunc, a Python function "
                             "or builtin(name); got %r" % (rhs,))
         key, origin = ("py", rhs), rhs
-    k = (key, solver, neq, flags)
+    k = (key, solver, neq, flags, str(data_dtype) if data_dtype is not None else None)
     with _lock:
         h = _handles.get(k)
         if h is not None:
@@ -231,7 +324,7 @@ def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False):
             rc = _lib.lib.b200ode_link_rhs(solver, neq, name, len(name), _lib.IMG_BUILTIN, flags,
                                            ct.byref(out))
         else:
-            img = compile_ltoir(origin)
+            img = compile_ltoir(origin, data_dtype=data_dtype)
             rc = _lib.lib.b200ode_link_rhs(solver, neq, img, len(img), _lib.IMG_LTOIR, flags,
                                            ct.byref(out))
         _lib.check(rc)
