@@ -635,13 +635,20 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     }
 }
 
-extern "C" __global__ void __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+// (B200_MAXNREG: an explicit register budget instead of the one ptxas derives from the launch
+// bounds -- it rounds 13 or 14 warps per SM down to 128 registers -- for geometry experiments)
+#ifdef B200_MAXNREG
+#define DP_BOUNDS __maxnreg__(B200_MAXNREG)
+#else
+#define DP_BOUNDS __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+#endif
+extern "C" __global__ void DP_BOUNDS
 b200ode_dop853_kernel(const B200OdeLaunch L)
 {
     dop853_ensemble<true>(L);
 }
 
-extern "C" __global__ void __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+extern "C" __global__ void DP_BOUNDS
 b200ode_dop853_kernel_ptr(const B200OdeLaunch L)
 {
     dop853_ensemble<false>(L);

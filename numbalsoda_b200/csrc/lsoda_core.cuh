@@ -843,8 +843,11 @@ LS_FN bool ls_advance(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, doubl
                       const double* teval, double* usol, const LsTol& tol,
                       unsigned long long mxstep_u, int exit_on_warning, unsigned lanes)
 {
-    if (ls_advance_a(s, R, v, T, nt, teval, usol, lanes)) return true;
-    return ls_advance_b(s, R, v, T, pp, tol, mxstep_u, exit_on_warning, lanes);
+    const bool fin = ls_advance_a(s, R, v, T, nt, teval, usol, lanes);
+    // (the lanes that go on: v.sync inside the second half must not wait for the finished ones)
+    const unsigned lanes_b = v.vote(lanes, !fin);
+    if (fin) return true;
+    return ls_advance_b(s, R, v, T, pp, tol, mxstep_u, exit_on_warning, lanes_b);
 }
 
 #endif

@@ -65,6 +65,16 @@ struct LsThreadVec {
 
     LS_MFN int size() const { return N; }
     LS_MFN int jac_rhs_calls() const { return N; }
+    // which of the lanes in `lanes` satisfy `pred` (all of them take part in the vote)
+    LS_MFN unsigned vote(unsigned lanes, bool pred) const
+    {
+#if defined(__CUDA_ARCH__)
+        return __ballot_sync(lanes, pred);
+#else
+        (void)pred;
+        return lanes;
+#endif
+    }
 
 #if defined(LS_DEFERRED)
     // ---- deferred operations (lsoda_core.cuh: deferred backends; served by ls_serve in

@@ -115,6 +115,7 @@ struct LsWarpVec {
     LS_MFN int jac_rhs_calls() const { return banded() && ml + mu + 1 < n ? ml + mu + 1 : n; }
     LS_MFN int size() const { return n; }
     LS_MFN void sync(unsigned) {}
+    LS_MFN unsigned vote(unsigned lanes, bool) const { return lanes; }
     // every operation executes on the spot (lsoda_core.cuh: deferred backends)
     static const bool kDeferred = false;
     LS_MFN void request_jac(double, double, double) {}
