@@ -31,6 +31,8 @@ def _data_layout(data, B_hint):
     # record arrays (passing_data_to_rhs_function.ipynb): opaque bytes, passed by address
     if data.ndim == 0:
         return data.reshape(1), False, data.dtype.itemsize, -1
+    if data.ndim == 1 and data.dtype.fields is not None and (B_hint is None or data.shape[0] == B_hint):
+        return data, True, data.dtype.itemsize, -1  # one record per trajectory
     if data.ndim == 1 and B_hint is not None and data.shape[0] == B_hint:
         return data, True, data.dtype.itemsize, -1
     return data, False, data.nbytes, -1
@@ -48,6 +50,8 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
     batched_u0 = u0.ndim == 2
     data_arr = np.asarray(data)
     B_hint = u0.shape[0] if batched_u0 else (data_arr.shape[0] if data_arr.ndim == 2 else None)
+    if not batched_u0 and data_arr.ndim == 1 and data_arr.dtype.fields is not None:
+        B_hint = data_arr.shape[0]  # a 1-D array of records: one per trajectory
     dbuf, batched_data, rec, nps = _data_layout(data, B_hint)
     if batched_u0 and batched_data and dbuf.shape[0] != u0.shape[0]:
         raise ValueError("u0 has %d trajectories but data has %d" % (u0.shape[0], dbuf.shape[0]))

@@ -128,6 +128,7 @@ struct PerDevice {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;      // parameters staged in registers (np >= 0)
     CUfunction fn_ptr = nullptr;  // data record passed by address (np < 0)
+    CUfunction fn_vtol = nullptr, fn_ptr_vtol = nullptr;  // dop853 thread kernel: per-component tolerances
     CUfunction fn_band = nullptr; // warp lsoda: the same kernel built for 12 resident warps (banded matrix)
     CUdeviceptr next = 0;  // kCounterSlots work-queue heads
     int regs = 0, local_bytes = 0, smem = 0, blocks_per_sm = 0, sms = 0;
@@ -375,6 +376,10 @@ static int init_device_state(b200ode_rhs_t H, int device, PerDevice& P)
     } else
         CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
                                (std::string(kernel_name(H->solver, H->neq)) + "_ptr").c_str()));
+    if (!warp && H->solver == B200ODE_DOP853) {
+        CU(cuModuleGetFunction(&P.fn_vtol, P.mod, "b200ode_dop853_kernel_vtol"));
+        CU(cuModuleGetFunction(&P.fn_ptr_vtol, P.mod, "b200ode_dop853_kernel_ptr_vtol"));
+    }
     CU(cuMemAlloc_v2(&P.next, sizeof(unsigned long long) * kCounterSlots));
     CU(cuFuncGetAttribute(&P.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, P.fn));
     CU(cuFuncGetAttribute(&P.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, P.fn));
@@ -434,8 +439,8 @@ static int init_device_state(b200ode_rhs_t H, int device, PerDevice& P)
         CU(cuFuncSetAttribute(P.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
         if (P.fn_ptr != P.fn)
             CU(cuFuncSetAttribute(P.fn_ptr, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
-        if (P.fn_band)
-            CU(cuFuncSetAttribute(P.fn_band, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
+        for (CUfunction f : {P.fn_band, P.fn_vtol, P.fn_ptr_vtol})
+            if (f) CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, P.max_dyn_smem));
     }
     CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&P.blocks_per_sm, P.fn, P.threads, P.dyn_smem));
     CU(cuDeviceGetAttribute(&P.sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
@@ -606,6 +611,7 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
         args.scratch = reinterpret_cast<double*>(P->wm_scratch + P->wm_set_bytes * set);
     }
     CUfunction fn = (args.np >= 0 && !warp) ? P->fn : P->fn_ptr;
+    if (P->fn_vtol && (args.rtol_vec || args.atol_vec)) fn = args.np >= 0 ? P->fn_vtol : P->fn_ptr_vtol;
     int dyn_smem = P->dyn_smem;
     if (!(warp && H->solver == B200ODE_LSODA) || P->wm_scratch ||
         (args.ml >= 0 && B200ODE_LSODAW_BAND_DOUBLES(H->neq, args.ml, args.mu) >= B200ODE_LSODAW_DOUBLES(H->neq)))

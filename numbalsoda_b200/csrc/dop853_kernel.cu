@@ -265,19 +265,10 @@ __device__ DRAIN_INLINE void dop853_drain(const char* data, long long data_strid
 #undef DRAIN_TE
 }
 
-// sk = atol_i + rtol_i * ymax with per-component tolerances (module :603-612): out of line, see SK_I
-__device__ __noinline__ double dop853_sk_vtol(const double* rv, const double* av, double rtol, double atol,
-                                              double ymax)
-{
-    const double rt = rv ? __ldg(rv) : rtol;
-    const double at = av ? __ldg(av) : atol;
-    return at + rt * ymax;
-}
-
 // STAGED: the first L.np doubles of the trajectory's data record are copied into
 // registers once and the right-hand side reads them there; otherwise it receives
 // the record's global address unchanged (arbitrary record layout).
-template <bool STAGED>
+template <bool STAGED, bool VTOL>
 __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
 {
     extern __shared__ double b200_smem[];
@@ -326,16 +317,14 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
     // dop853_module.f90:603-612, :779-803): read from global memory where they are used -- twice
     // per trajectory in hinit, once per step in the error norm -- so that the scalar case keeps
     // its registers and shared memory.  rtol_vec / atol_vec are uniform over the launch.
-#define RT_I(i, scalar) (L.rtol_vec ? __ldg(L.rtol_b + (long long)b * L.rtol_sb + (i)) : (scalar))
-#define AT_I(i, scalar) (L.atol_vec ? __ldg(L.atol_b + (long long)b * L.atol_sb + (i)) : (scalar))
-    // In the step loop the per-component case is a call behind a launch-uniform branch
-    // (dop853_sk_vtol): written in line, the compiler predicates the six loads and their address
-    // arithmetic and issues them in the scalar case too (16 instructions per step).
-#define SK_I(i, ymax)                                                                              \
-    ((L.rtol_vec | L.atol_vec)                                                                     \
-         ? dop853_sk_vtol(L.rtol_vec ? L.rtol_b + (long long)b * L.rtol_sb + (i) : nullptr,        \
-                          L.atol_vec ? L.atol_b + (long long)b * L.atol_sb + (i) : nullptr, rtol, atol, (ymax)) \
-         : (atol + rtol * (ymax)))
+    // VTOL is a template parameter: the scalar kernels carry none of it.
+#define RT_I(i, scalar) ((VTOL && L.rtol_vec) ? __ldg(L.rtol_b + (long long)b * L.rtol_sb + (i)) : (scalar))
+#define AT_I(i, scalar) ((VTOL && L.atol_vec) ? __ldg(L.atol_b + (long long)b * L.atol_sb + (i)) : (scalar))
+    // (Measured with one kernel for both cases: the loads in line, predicated off in the scalar
+    // case, cost 16 issue slots per step; out of line behind a launch-uniform branch they cost
+    // 5 % -- 8.02 M against 8.47 M Lorenz trajectories/s: the call site splits the scheduling
+    // region of the error norm.  Hence two instantiations.)
+#define SK_I(i, ymax) (AT_I(i, atol) + RT_I(i, rtol) * (ymax))
 
     double y[N], y1[N], k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], k8[N], k9[N], k10[N];
     double pl[STAGED ? B200ODE_NPMAX : 1];
@@ -645,13 +634,26 @@ __device__ __forceinline__ void dop853_ensemble(const B200OdeLaunch& L)
 extern "C" __global__ void DP_BOUNDS
 b200ode_dop853_kernel(const B200OdeLaunch L)
 {
-    dop853_ensemble<true>(L);
+    dop853_ensemble<true, false>(L);
 }
 
 extern "C" __global__ void DP_BOUNDS
 b200ode_dop853_kernel_ptr(const B200OdeLaunch L)
 {
-    dop853_ensemble<false>(L);
+    dop853_ensemble<false, false>(L);
+}
+
+// the same two kernels for per-component tolerances (launches with rtol_vec / atol_vec)
+extern "C" __global__ void DP_BOUNDS
+b200ode_dop853_kernel_vtol(const B200OdeLaunch L)
+{
+    dop853_ensemble<true, true>(L);
+}
+
+extern "C" __global__ void DP_BOUNDS
+b200ode_dop853_kernel_ptr_vtol(const B200OdeLaunch L)
+{
+    dop853_ensemble<false, true>(L);
 }
 
 // Build-time geometry of this image, read once by the host library after loading.

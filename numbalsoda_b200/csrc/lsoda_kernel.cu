@@ -16,18 +16,30 @@
 //  * the method-coefficient tables are staged once per block into shared memory
 //    (lanes of a warp sit at different orders: divergent indices cost bank conflicts
 //    there instead of serialised constant-cache replays);
-//  * lanes are compacted by what they need (north_star: "sorting and compacting lanes by
-//    status between step bursts").  The blocks of a pass that only a few lanes of a warp
-//    need at a time -- Jacobian + LU (9 % of the lanes per pass), retraction after a failed
-//    attempt (10 %), rescale after a step-size change (25 %), output rows (18 % of the
-//    steps) -- ran with 2-4 of 32 lanes and were 31 % of the warp instructions
-//    (profiles/r2_lsoda_v0_baseline.txt).  They are now *requested* (lsoda_vec_thread.cuh,
-//    LS_DEFERRED) and served once per pass for the whole block, between the two halves of
-//    the pass: every thread with a request enters the queue of its kind, and each warp of
-//    the block serves one queue, request r on lane r.  The server needs nothing from the
-//    requester's registers -- yh and the matrix are shared-memory columns it addresses by
-//    the owner's thread index, the few scalars travel in the request -- and performs the
-//    same operations in the same order, so strict mode stays bit-exact;
+//  * block-level compaction of the rare blocks (north_star: "sorting and compacting lanes by
+//    status between step bursts") is built and MEASURED SLOWER, so it is a build option
+//    (-DLS_COMPACT), not the default.  The blocks of a pass that only a few lanes of a warp need
+//    at a time -- Jacobian + LU (9 % of the lanes per pass), retraction after a failed attempt
+//    (10 %), rescale after a step-size change (25 %), output rows (18 % of the steps) -- run
+//    with 2-4 of 32 lanes and are 28 % of the warp instructions
+//    (profiles/r2_lsoda_v0_baseline.txt).  With LS_COMPACT they are *requested*
+//    (lsoda_vec_thread.cuh, LS_DEFERRED) and served once per pass for the whole block, between
+//    the two halves of the pass: every thread with a request enters the queue of its kind, and
+//    each warp of the block serves one queue, request r on lane r.  The server needs nothing
+//    from the requester's registers -- yh and the matrix are shared-memory columns it addresses
+//    by the owner's thread index, the few scalars travel in the request -- and performs the same
+//    operations in the same order, so strict mode stays bit-exact (all 150 GPU tests pass with
+//    it, and tests/test_lsoda_deferred_host.py emulates it on the CPU).  What it buys and costs
+//    (profiles/r2_lsoda_v1_deferred.txt, Robertson): the served blocks shrink from 4.4 G to 2.0 G
+//    warp instructions and SIMT efficiency rises from 11.8 to 13.9 lanes, but a block of 128
+//    trajectories only has 5-12 requests of a kind per pass (served at 5-13 lanes, not 32), the
+//    queues cost 0.6 G, the lanes that wait for a matrix re-enter the corrector, and the two
+//    block barriers per pass show up as the third-largest stall (0.85 warps per issue cycle):
+//    16.5 G instructions against 16.1 G, 8.02 M trajectories/s against 8.66 M.  Larger blocks
+//    (more requests per queue) lose more to the barriers: 192 threads 8.14 M, 384 threads
+//    7.64 M (profiles/r2_sweep_lsoda.log).  The kernel is bound by the latency of dependent
+//    instructions (stall_wait 2.5 warps per issue cycle at 3 warps per scheduler), not by issue
+//    slots, so removing low-lane instructions does not shorten a pass while barriers lengthen it;
 //  * output rows of one trajectory are consecutive in usol[B,nt,N]; a trajectory's rows
 //    stream out as they are passed and the L2 merges them into full sectors.
 #include "b200ode_device.cuh"
@@ -39,7 +51,7 @@
 #define B200_THREADS 128
 #endif
 #define LS_STRIDE B200_THREADS
-#ifndef LS_NO_DEFER
+#ifdef LS_COMPACT
 #define LS_DEFERRED 1
 #endif
 
@@ -54,7 +66,11 @@
 #define LS_OFF_REQD (LS_OFF_WM + N_ * N_ * B200_THREADS)
 #define LS_OFF_REQI (LS_OFF_REQD + 6 * B200_THREADS)
 #define LS_REQI_INTS (9 * B200_THREADS + 4 * B200_THREADS + 8)
+#ifdef LS_COMPACT
 #define LS_SMEM_DOUBLES (LS_OFF_REQI + (LS_REQI_INTS + 1) / 2)
+#else
+#define LS_SMEM_DOUBLES LS_OFF_REQD  // (the request area and the queues exist with LS_COMPACT only)
+#endif
 extern __shared__ double b200_smem[];
 // this thread's request slots (lsoda_vec_thread.cuh)
 #define LS_REQD(f) b200_smem[LS_OFF_REQD + (f) * B200_THREADS + threadIdx.x]
