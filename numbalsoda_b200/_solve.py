@@ -19,6 +19,7 @@ def _as_f64(a, name):
 
 def _data_layout(data, B_hint):
     """-> (buffer, batched, record_bytes, np_staged)"""
+    scalar_record = np.ndim(data) == 0  # (np.ascontiguousarray returns at least 1-D)
     data = np.ascontiguousarray(data)
     if data.dtype == np.float64:
         if data.ndim == 2:
@@ -29,7 +30,7 @@ def _data_layout(data, B_hint):
             return data, False, p * 8, (p if p <= 16 else -1)
         raise ValueError("data must be [p] or [B,p]")
     # record arrays (passing_data_to_rhs_function.ipynb): opaque bytes, passed by address
-    if data.ndim == 0:
+    if scalar_record or data.ndim == 0:
         return data.reshape(1), False, data.dtype.itemsize, -1
     if data.ndim == 1 and data.dtype.fields is not None and (B_hint is None or data.shape[0] == B_hint):
         return data, True, data.dtype.itemsize, -1  # one record per trajectory
@@ -50,7 +51,7 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
     batched_u0 = u0.ndim == 2
     data_arr = np.asarray(data)
     B_hint = u0.shape[0] if batched_u0 else (data_arr.shape[0] if data_arr.ndim == 2 else None)
-    if not batched_u0 and data_arr.ndim == 1 and data_arr.dtype.fields is not None:
+    if not batched_u0 and data_arr.ndim == 1 and data_arr.dtype.fields is not None and np.ndim(data) == 1:
         B_hint = data_arr.shape[0]  # a 1-D array of records: one per trajectory
     dbuf, batched_data, rec, nps = _data_layout(data, B_hint)
     if batched_u0 and batched_data and dbuf.shape[0] != u0.shape[0]:
