@@ -110,6 +110,12 @@ def python_rhs(name):
             "brusselator1d": pr.brusselator_rhs, "brusselator1d_il": pr.brusselator_il_rhs}[name]
 
 
+def python_rhs_lanes(name):
+    """The lane-parallel form of a method-of-lines right-hand side (lsoda(..., rhs_lanes=)), or None."""
+    import _problems as pr
+    return {"brusselator1d": pr.brusselator_lanes, "brusselator1d_il": pr.brusselator_il_lanes}.get(name)
+
+
 def initial_state(wl):
     import _problems as pr
     if wl["u0"] == "brusselator":
@@ -372,7 +378,8 @@ class Gpu:
                 h = self._rhs.get_ivp_handle(f, wl["n"], 1, nb.builtin(wl["events"]), **MODES[mode])
             else:
                 solver = _lib.DOP853 if wl["solver"] == "dop853" else _lib.LSODA
-                h = nb.get_handle(f, solver, wl["n"], **MODES[mode])
+                lanes = python_rhs_lanes(wl["rhs"]) if rhs_kind == "numba" else None
+                h = nb.get_handle(f, solver, wl["n"], rhs_lanes=lanes, **MODES[mode])
             self.handles[key] = h
         return self.handles[key]
 
@@ -506,6 +513,8 @@ class Gpu:
         kw = dict(MODES[mode])
         if wl.get("band"):
             kw.update(ml=wl["band"][0], mu=wl["band"][1])
+        if rhs_kind == "numba" and python_rhs_lanes(wl["rhs"]) is not None:
+            kw.update(rhs_lanes=python_rhs_lanes(wl["rhs"]))
 
         def one_pass():
             good = 0
@@ -629,6 +638,8 @@ def parity_block(gpu, wl, rhs_kind):
     rhs = python_rhs(wl["rhs"]) if rhs_kind == "numba" else nb.builtin(wl["rhs"])
     out = {}
     bkw = dict(ml=wl["band"][0], mu=wl["band"][1]) if wl.get("band") else {}
+    if rhs_kind == "numba" and python_rhs_lanes(wl["rhs"]) is not None:
+        bkw["rhs_lanes"] = python_rhs_lanes(wl["rhs"])
     for mode in MODES:
         us, ok, cnt = api(rhs, u0, te, P, rtol, atol, wl["mxstep"], device=gpu.local, counters=True,
                           **MODES[mode], **bkw)

@@ -82,6 +82,17 @@ typedef struct b200ode_rhs_s* b200ode_rhs_t;
  * Links it with the solver kernels for systems of `neq` equations; needs no GPU. */
 int b200ode_link_rhs(int solver, int neq, const void* image, size_t size, int kind,
                      unsigned flags, b200ode_rhs_t* out);
+/* The same with an optional second device function for systems of more than 8 equations, which
+ * run one trajectory per WARP:
+ * `b200ode_user_rhs_lanes`, a device function with C linkage taking
+ * (double t, double* u, double* du, double* data, int lane, int nlanes) and returning long long,
+ * is called by all `nlanes` (32) lanes of the warp at once and must, between them, write every
+ * du[i] exactly as the scalar function does -- e.g. a method-of-lines loop `for i in
+ * range(lane, m, nlanes)`.  The scalar function is still needed (the finite-difference Jacobian
+ * evaluates one column per lane with it).  lanes_image = NULL: lane 0 calls the scalar function. */
+int b200ode_link_rhs_lanes(int solver, int neq, const void* image, size_t size, int kind,
+                           const void* lanes_image, size_t lanes_size, int lanes_kind,
+                           unsigned flags, b200ode_rhs_t* out);
 void b200ode_rhs_free(b200ode_rhs_t rhs);
 /* The linked sm_100a cubin (for inspection: cuobjdump -sass / -res-usage). */
 int b200ode_rhs_cubin(b200ode_rhs_t rhs, const void** cubin, size_t* size);

@@ -53,7 +53,8 @@ def _load(rebuilt=False):
         _build.build()
         rebuilt = True
     lib = ct.CDLL(LIBPATH)
-    if not hasattr(lib, "b200ode_solve_ivp_args") and not rebuilt:
+    if not all(hasattr(lib, f) for f in ("b200ode_solve_ivp_args", "b200ode_link_rhs_lanes",
+                                         "b200ode_device_alloc")) and not rebuilt:
         # a library built from older sources: rebuild it once
         from . import build as _build
         _build.build(force=True)
@@ -61,6 +62,7 @@ def _load(rebuilt=False):
     vp, ll, i, d, sz = ct.c_void_p, ct.c_longlong, ct.c_int, ct.c_double, ct.c_size_t
     lib.b200ode_last_error.restype = ct.c_char_p
     lib.b200ode_link_rhs.argtypes = [i, i, vp, sz, i, ct.c_uint, ct.POINTER(vp)]
+    lib.b200ode_link_rhs_lanes.argtypes = [i, i, vp, sz, i, vp, sz, i, ct.c_uint, ct.POINTER(vp)]
     lib.b200ode_rhs_free.argtypes = [vp]
     lib.b200ode_rhs_free.restype = None
     lib.b200ode_rhs_cubin.argtypes = [vp, ct.POINTER(vp), ct.POINTER(sz)]

@@ -41,7 +41,7 @@ def _data_layout(data, B_hint):
 
 def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning=False,
           strict=False, device=None, counters=False, out=None, exact_ctrl=False, ml=None, mu=None,
-          pointers=None):
+          pointers=None, rhs_lanes=None):
     u0 = _as_f64(u0, "u0")
     t_eval = _as_f64(t_eval, "t_eval")
     if data is None:
@@ -63,7 +63,7 @@ def solve(solver, funcptr, u0, t_eval, data, rtol, atol, mxstep, exit_on_warning
     # a record `data` (structured dtype): the right-hand side receives the record itself
     record = dbuf.dtype.fields is not None
     handle = _rhs.get_handle(funcptr, solver, n, strict=strict, exact_ctrl=exact_ctrl,
-                             data_dtype=dbuf.dtype if record else None)
+                             data_dtype=dbuf.dtype if record else None, rhs_lanes=rhs_lanes)
     if pointers and not record:
         raise ValueError("pointers= needs a record (structured dtype) `data`")
     if out is not None:

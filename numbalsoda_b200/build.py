@@ -149,6 +149,13 @@ def build(force=False, verbose=False):
             _run([NVCC] + ARCH + NVCC_FLAGS + ["-DB200_EVENTS_%s" % r.upper(), "-o", out, srcp])
         images.append(("events_" + r, out))
 
+    # default of the optional lane-parallel right-hand side (rhs_lanes_default.cu)
+    srcp = os.path.join(CSRC, "rhs_lanes_default.cu")
+    out = os.path.join(OBJ, "rhs_lanes_default.fatbin")
+    if force or _newer(out, [srcp]):
+        _run([NVCC] + ARCH + NVCC_FLAGS + ["-o", out, srcp])
+    images.append(("rhs_lanes_default", out))
+
     # the handle's link flags as a link-time constant (link_flags.cu)
     srcp = os.path.join(CSRC, "link_flags.cu")
     for k in range(4):

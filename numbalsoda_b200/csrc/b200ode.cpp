@@ -207,7 +207,8 @@ static int resolve_image(const void* image, size_t size, int kind, const char* b
 
 // nvJitLink: solver image + right-hand side (+ events function) + link flags -> cubin.
 static int link_handle(int solver, int neq, const char* name, const UserImage& rhs,
-                       const UserImage* events, int n_events, unsigned flags, b200ode_rhs_t* out)
+                       const UserImage* events, int n_events, unsigned flags, b200ode_rhs_t* out,
+                       const UserImage* lanes = nullptr, bool rhs_is_builtin = false)
 {
     const B200EmbeddedImage* solver_img = find_image(name);
     if (!solver_img)
@@ -237,6 +238,23 @@ static int link_handle(int solver, int neq, const char* name, const UserImage& r
     if (events) {
         r = nvJitLinkAddData(h, events->type, events->data, events->size, "b200ode_user_events");
         if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(events)", r);
+    }
+    if (warp_kernel(solver, neq)) {
+        // the lane-parallel form of the right-hand side (b200ode_warp.cuh): the caller's, the
+        // built-in problem's own (its image defines both symbols), or the default that lets
+        // lane 0 call the scalar function
+        if (lanes) {
+            r = nvJitLinkAddData(h, lanes->type, lanes->data, lanes->size, "b200ode_user_rhs_lanes");
+            if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(rhs_lanes)", r);
+        } else if (!rhs_is_builtin) {
+            const B200EmbeddedImage* d = find_image("rhs_lanes_default");
+            if (!d) {
+                nvJitLinkDestroy(&h);
+                return fail(B200ODE_ENOSYS, "image rhs_lanes_default missing");
+            }
+            r = nvJitLinkAddData(h, NVJITLINK_INPUT_FATBIN, d->begin, (size_t)(d->end - d->begin), "rhs_lanes_default");
+            if (r != NVJITLINK_SUCCESS) return log_and_fail("nvJitLinkAddData(rhs_lanes_default)", r);
+        }
     }
     {
         // the flags as a device-side link-time constant (link_flags.cu)
@@ -274,6 +292,13 @@ static int link_handle(int solver, int neq, const char* name, const UserImage& r
 extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t size, int kind,
                                 unsigned flags, b200ode_rhs_t* out)
 {
+    return b200ode_link_rhs_lanes(solver, neq, image, size, kind, nullptr, 0, 0, flags, out);
+}
+
+extern "C" int b200ode_link_rhs_lanes(int solver, int neq, const void* image, size_t size, int kind,
+                                      const void* lanes_image, size_t lanes_size, int lanes_kind,
+                                      unsigned flags, b200ode_rhs_t* out)
+{
     if (!out) return fail(B200ODE_EINVAL, "out is NULL");
     *out = nullptr;
     if (solver == B200ODE_SOLVE_IVP)
@@ -289,10 +314,13 @@ extern "C" int b200ode_link_rhs(int solver, int neq, const void* image, size_t s
     } else {
         snprintf(name, sizeof name, "%s_n%d", solver == B200ODE_DOP853 ? "dop853" : "lsoda", neq);
     }
-    UserImage rhs;
+    UserImage rhs, lanes;
     int rc = resolve_image(image, size, kind, "rhs_", "right-hand side", &rhs);
     if (rc) return rc;
-    return link_handle(solver, neq, name, rhs, nullptr, 0, flags, out);
+    if (lanes_image && (rc = resolve_image(lanes_image, lanes_size, lanes_kind, "rhs_", "lane-parallel right-hand side", &lanes)))
+        return rc;
+    return link_handle(solver, neq, name, rhs, nullptr, 0, flags, out, lanes_image ? &lanes : nullptr,
+                       kind == B200ODE_IMG_BUILTIN);
 }
 
 extern "C" int b200ode_link_ivp(int neq, const void* rhs_image, size_t rhs_size, int rhs_kind,
@@ -320,7 +348,8 @@ extern "C" int b200ode_link_ivp(int neq, const void* rhs_image, size_t rhs_size,
     else
         rc = resolve_image("none", 4, B200ODE_IMG_BUILTIN, "events_", "events function", &ev);
     if (rc) return rc;
-    return link_handle(B200ODE_SOLVE_IVP, neq, name, rhs, &ev, n_events, flags, out);
+    return link_handle(B200ODE_SOLVE_IVP, neq, name, rhs, &ev, n_events, flags, out, nullptr,
+                       rhs_kind == B200ODE_IMG_BUILTIN);
 }
 
 // Frees what init_device_state() created (the device's context must be current).

@@ -25,8 +25,24 @@ __device__ __noinline__ void wv_user_rhs(double t, double* u, double* du, double
 {
     b200ode_user_rhs(t, u, du, p);
 }
+// The same right-hand side evaluated by the whole warp: every lane computes the components it
+// owns (`lane`, `nlanes` are a partition hint; all nlanes lanes call, and together they must
+// write every du[i] exactly as the scalar function does).  A method-of-lines right-hand side is a
+// loop over cells; with one trajectory per warp the scalar function kept 1 of 32 lanes busy for
+// 26 % of the warp instructions of the banded n = 64 workload (profiles/r2_lsodaw_band_v0.txt).
+// Optional: right-hand sides that do not provide it are linked with a default that lets lane 0
+// call the scalar function (rhs_lanes_default.cu).
+extern "C" __device__ long long b200ode_user_rhs_lanes(double t, double* u, double* du, double* p, int lane,
+                                                       int nlanes);
+__device__ __noinline__ void wv_user_rhs_all(double t, double* u, double* du, double* p)
+{
+    __syncwarp();
+    b200ode_user_rhs_lanes(t, u, du, p, (int)(threadIdx.x & 31u), 32);
+    __syncwarp();
+}
 #else
 #define wv_user_rhs(t, u, du, p) b200ode_user_rhs(t, u, du, p)
+#define wv_user_rhs_all(t, u, du, p) b200ode_user_rhs(t, u, du, p)
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -74,12 +74,7 @@ WV_FN void dop853_warp_solve(int n, double* w, const double* u0, double* pp, int
     double* t1 = cont + 8 * n;  // norm terms
     double* t2 = t1 + n;
     st.nstep = st.naccpt = st.nrejct = st.nevent = st.idid = st.rows = 0;
-#define DW_RHS(t, u, du)                                \
-    do {                                                \
-        WV_SYNC();                                      \
-        if (WV_LANE == 0) wv_user_rhs(t, u, du, pp);      \
-        WV_SYNC();                                      \
-    } while (0)
+#define DW_RHS(t, u, du) wv_user_rhs_all(t, u, du, pp)  // (barriers inside)
     // set_parameters: nmax <= 0 is rejected, module :243-246 -> c_interface :106-109
     if (mxstep <= 0) {
         st.idid = -1;

@@ -181,9 +181,7 @@ struct LsWarpVec {
     }
     LS_MFN void rhs_to(double t, double* out, double* pp)
     {
-        WV_SYNC();
-        if (WV_LANE == 0) wv_user_rhs(t, y, out, pp);
-        WV_SYNC();
+        wv_user_rhs_all(t, y, out, pp);  // (barriers inside; lane 0 alone without a lanes function)
     }
     LS_MFN void rhs_savf(double t, double* pp) { rhs_to(t, savf, pp); }
     LS_MFN void acor_zero()
@@ -540,11 +538,6 @@ struct LsWarpVec {
         if (WV_LANE == 0) ipvt[n - 1] = n - 1;
         if (wmT[(n - 1) * lda + m] == 0.0) info = n;
         WV_SYNC();
-        if (fast) {
-            // reciprocals of U's diagonal for the back substitution of the throughput mode
-            WV_FOR_OWN(i) rdiag[i] = ls_div(1.0, wmT[i * lda + m]);
-            WV_SYNC();
-        }
         return info;
     }
 
@@ -552,79 +545,13 @@ struct LsWarpVec {
     // step suffices: forward, lane 0 stores the interchange while lanes 1..lm add the pivot row's
     // multiples (the lane whose row was interchanged takes the swapped-in value); backward, lane 0
     // stores the quotient while lanes 0..lm-1 subtract its multiples from the rows above.
-#if defined(__CUDA_ARCH__)
-    // The same solve with b in registers (lane r & 31 holds rows r, r + 32, ...) and the pivot
-    // row's value travelling by shuffle: a step's critical path is one shuffle and one
-    // multiply-add (plus the division by the diagonal on the way back) instead of a shared-memory
-    // round trip and a barrier -- the solve was 28 % of the banded kernel's stall samples
-    // (profiles/r2_lsodaw_band_v0.txt).  Bands of up to 32 sub- and 32 super-diagonals after
-    // fill-in; the operations per element are dgbsl's.
-    LS_MFN void dgbsl_regs(double* b) const
-    {
-        const int lda = 2 * ml + mu + 1, m = ml + mu;
-        double bq[WV_NPL];
-#pragma unroll
-        for (int q = 0; q < WV_NPL; q++) bq[q] = (WV_LANE + WV_NL * q < n) ? b[WV_LANE + WV_NL * q] : 0.0;
-#define BQ_OF(row) ((row) < 32 ? bq[0] : (row) < 64 ? bq[1] : (row) < 96 ? bq[2] : bq[3])
-#define BQ_SET(row, val)                      \
-    do {                                      \
-        const double v_ = (val);              \
-        const int q_ = (row) >> 5;            \
-        if (q_ == 0) bq[0] = v_;              \
-        if (q_ == 1) bq[1] = v_;              \
-        if (q_ == 2) bq[2] = v_;              \
-        if (q_ == 3) bq[3] = v_;              \
-    } while (0)
-        if (ml != 0) {
-            for (int k = 0; k < n - 1; k++) {
-                const int lm = ml < n - 1 - k ? ml : n - 1 - k;
-                const int l = ipvt[k];
-                const double t = __shfl_sync(0xffffffffu, BQ_OF(l), l & 31);
-                if (l != k) {
-                    const double bk = __shfl_sync(0xffffffffu, BQ_OF(k), k & 31);
-                    if (WV_LANE == (l & 31)) BQ_SET(l, bk);
-                    if (WV_LANE == (k & 31)) BQ_SET(k, t);
-                }
-                const int i = ((WV_LANE - (k + 1)) & 31) + 1;  // this lane's row among k+1 .. k+32
-                if (i <= lm) {
-                    const int r = k + i;
-                    const double c = wmT[k * lda + m + i];
-                    BQ_SET(r, BQ_OF(r) + t * c);
-                }
-            }
-        }
-        for (int k = n - 1; k >= 0; k--) {
-            const double* ck = wmT + k * lda;
-            const double num = __shfl_sync(0xffffffffu, BQ_OF(k), k & 31);
-            const double bk = fast ? num * rdiag[k] : ls_div(num, ck[m]);
-            if (WV_LANE == (k & 31)) BQ_SET(k, bk);
-            const int lm = k < m ? k : m;
-            const double t = -bk;
-            int j = (k - WV_LANE) & 31;  // this lane's row k - j among k-32 .. k-1
-            if (j == 0) j = 32;
-            if (j <= lm) {
-                const int r = k - j;
-                BQ_SET(r, BQ_OF(r) + t * ck[m - j]);
-            }
-        }
-#undef BQ_OF
-#undef BQ_SET
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < WV_NPL; q++)
-            if (WV_LANE + WV_NL * q < n) b[WV_LANE + WV_NL * q] = bq[q];
-        __syncwarp();
-    }
-#endif
-
+    // (Measured and dropped: the same solve with b in registers and the pivot row's value
+    // travelling by shuffle -- one shuffle + one multiply-add per step on the critical path instead
+    // of a shared-memory round trip and a barrier -- ran the C4 banded workload at 128 k traj/s
+    // against 199 k: with 11 warps per SM the barriers' latency is hidden and the ~30
+    // select / shuffle instructions per step, executed by all 32 lanes, are not.)
     LS_MFN void dgbsl(double* b) const
     {
-#if defined(__CUDA_ARCH__)
-        if (ml <= 32 && ml + mu <= 32) {
-            dgbsl_regs(b);
-            return;
-        }
-#endif
         const int lda = 2 * ml + mu + 1, m = ml + mu;
         if (ml != 0) {
             for (int k = 0; k < n - 1; k++) {

@@ -64,3 +64,45 @@ extern "C" __device__ long long b200ode_user_rhs(double t, double* u, double* du
     (void)t;
     return 0;
 }
+
+// The lane-parallel form (b200ode_warp.cuh): the method-of-lines problems split their loop over
+// cells, cell i on lane i % nlanes -- the same operations per component as above, so strict mode
+// stays bit-exact; the small systems never run on the warp kernels and let lane 0 do the work.
+extern "C" __device__ long long b200ode_user_rhs_lanes(double t, double* u, double* du, double* p, int lane,
+                                                       int nlanes)
+{
+#if defined(B200_RHS_BRUSSELATOR1D)
+    const double A = p[0], B = p[1], D = p[2];
+    const int m = 32;
+#pragma unroll 1
+    for (int i = lane; i < m; i += nlanes) {
+        const double uu = u[i], v = u[m + i];
+        const double ul = (i == 0) ? A : u[i - 1];
+        const double ur = (i == m - 1) ? A : u[i + 1];
+        const double vl = (i == 0) ? B : u[m + i - 1];
+        const double vr = (i == m - 1) ? B : u[m + i + 1];
+        const double uuv = uu * uu * v;
+        du[i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur);
+        du[m + i] = B * uu - uuv + D * (vl - 2.0 * v + vr);
+    }
+#elif defined(B200_RHS_BRUSSELATOR1D_IL)
+    const double A = p[0], B = p[1], D = p[2];
+    const int m = 32;
+#pragma unroll 1
+    for (int i = lane; i < m; i += nlanes) {
+        const double uu = u[2 * i], v = u[2 * i + 1];
+        const double ul = (i == 0) ? A : u[2 * i - 2];
+        const double ur = (i == m - 1) ? A : u[2 * i + 2];
+        const double vl = (i == 0) ? B : u[2 * i - 1];
+        const double vr = (i == m - 1) ? B : u[2 * i + 3];
+        const double uuv = uu * uu * v;
+        du[2 * i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur);
+        du[2 * i + 1] = B * uu - uuv + D * (vl - 2.0 * v + vr);
+    }
+#else
+    (void)nlanes;
+    if (lane == 0) b200ode_user_rhs(t, u, du, p);
+#endif
+    (void)t;
+    return 0;
+}

@@ -195,12 +195,7 @@ WV_FN void ivp_warp_solve(int n, double* w, const B200IvpLaunch& L, const double
     R.nt_out = R.rows_needed = R.event_found = R.ind_event = R.idid = 0;
     R.nstep = R.naccpt = R.nrejct = 0;
     R.t_event = 0.0;
-#define IW_RHS(t, u, du)                              \
-    do {                                              \
-        WV_SYNC();                                    \
-        if (WV_LANE == 0) wv_user_rhs(t, u, du, pp);  \
-        WV_SYNC();                                    \
-    } while (0)
+#define IW_RHS(t, u, du) wv_user_rhs_all(t, u, du, pp)  // (barriers inside)
 #define IW_EVENTS(t, u, ev)                              \
     do {                                                 \
         WV_SYNC();                                       \

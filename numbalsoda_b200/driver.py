@@ -20,7 +20,7 @@ except Exception:  # numba absent: built-in right-hand sides still work
 
 def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, atol=1.0e-6,
           mxstep=10000, exit_on_warning=False, *, strict=False, device=None, counters=False, out=None,
-          exact_ctrl=False, ml=None, mu=None, pointers=None):
+          exact_ctrl=False, ml=None, mu=None, pointers=None, rhs_lanes=None):
     """Integrate with the LSODA kernel on the GPU.
 
     funcptr: address of a numba @cfunc(lsoda_sig) (as in the reference), the cfunc, the
@@ -39,7 +39,7 @@ def lsoda(funcptr, u0, t_eval, data=np.array([0.0], np.float64), rtol=1.0e-3, at
     pattern): each array is copied to the device and its device address stored in that field."""
     return solve(_lib.LSODA, funcptr, u0, t_eval, data, rtol, atol, mxstep,
                  exit_on_warning=exit_on_warning, strict=strict, device=device,
-                 counters=counters, out=out, exact_ctrl=exact_ctrl, ml=ml, mu=mu, pointers=pointers)
+                 counters=counters, out=out, exact_ctrl=exact_ctrl, ml=ml, mu=mu, pointers=pointers, rhs_lanes=rhs_lanes)
 
 
 try:

@@ -260,7 +260,7 @@ class _nested_device_functions_for:
         return False
 
 
-def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs", data_dtype=None):
+def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs", data_dtype=None, lanes=False):
     """numba.cuda: Python rhs(t, u, du, p) -> LTO-IR of `b200ode_user_rhs` (or, for
     solve_ivp's events(t, y, out, p), of `b200ode_user_events`).  data_dtype: a structured numpy
     dtype -- `data` is then a record and the function receives it as one (numba passes records
@@ -271,6 +271,8 @@ def compile_ltoir(pyfunc, abi_name="b200ode_user_rhs", data_dtype=None):
         import numba
         ptype = numba.from_dtype(data_dtype)
     sig = (types.double, types.CPointer(types.double), types.CPointer(types.double), ptype)
+    if lanes:  # rhs_lanes(t, u, du, p, lane, nlanes): the lane-parallel form (include/b200ode.h)
+        sig = sig + (types.int32, types.int32)
 
     def build(f):
         with _nested_device_functions_for(_ltoir_cc()):
@@ -296,7 +298,7 @@ def _is_address(x):
     return isinstance(x, numbers.Integral) and not isinstance(x, bool)
 
 
-def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False, data_dtype=None):
+def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False, data_dtype=None, rhs_lanes=None):
     """Link (once per right-hand side, solver, size, mode and record type of `data`) and return
     the handle."""
     flags = _lib.STRICT_FP if strict else (_lib.EXACT_CTRL if exact_ctrl else 0)
@@ -313,7 +315,9 @@ def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False, data_dtype=None
             raise TypeError("right-hand side must be a cfunc address, a cfunc, a Python function "
                             "or builtin(name); got %r" % (rhs,))
         key, origin = ("py", rhs), rhs
-    k = (key, solver, neq, flags, str(data_dtype) if data_dtype is not None else None)
+    if rhs_lanes is not None and hasattr(rhs_lanes, "_pyfunc"):
+        rhs_lanes = rhs_lanes._pyfunc
+    k = (key, solver, neq, flags, str(data_dtype) if data_dtype is not None else None, rhs_lanes)
     with _lock:
         h = _handles.get(k)
         if h is not None:
@@ -325,8 +329,13 @@ def get_handle(rhs, solver, neq, strict=False, exact_ctrl=False, data_dtype=None
                                            ct.byref(out))
         else:
             img = compile_ltoir(origin, data_dtype=data_dtype)
-            rc = _lib.lib.b200ode_link_rhs(solver, neq, img, len(img), _lib.IMG_LTOIR, flags,
-                                           ct.byref(out))
+            if rhs_lanes is not None and neq > 8:
+                limg = compile_ltoir(rhs_lanes, "b200ode_user_rhs_lanes", data_dtype=data_dtype, lanes=True)
+                rc = _lib.lib.b200ode_link_rhs_lanes(solver, neq, img, len(img), _lib.IMG_LTOIR, limg, len(limg),
+                                                     _lib.IMG_LTOIR, flags, ct.byref(out))
+            else:
+                rc = _lib.lib.b200ode_link_rhs(solver, neq, img, len(img), _lib.IMG_LTOIR, flags,
+                                               ct.byref(out))
         _lib.check(rc)
         h = RhsHandle(out, solver, neq, flags, origin)
         _handles[k] = h

@@ -71,6 +71,43 @@ def brusselator_il_rhs(t, u, du, p):
         du[2 * i + 1] = B * uu - uuv + D * (vl - 2.0 * v + vr)
 
 
+def brusselator_il_lanes(t, u, du, p, lane, nlanes):
+    # brusselator_il_rhs in the lane-parallel form (lsoda(..., rhs_lanes=)): the cells lane,
+    # lane + nlanes, ... -- the same operations per component
+    A = p[0]
+    B = p[1]
+    D = p[2]
+    m = 32
+    for i in range(lane, m, nlanes):
+        uu = u[2 * i]
+        v = u[2 * i + 1]
+        ul = A if i == 0 else u[2 * i - 2]
+        ur = A if i == m - 1 else u[2 * i + 2]
+        vl = B if i == 0 else u[2 * i - 1]
+        vr = B if i == m - 1 else u[2 * i + 3]
+        uuv = uu * uu * v
+        du[2 * i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur)
+        du[2 * i + 1] = B * uu - uuv + D * (vl - 2.0 * v + vr)
+
+
+def brusselator_lanes(t, u, du, p, lane, nlanes):
+    # brusselator_rhs, lane-parallel
+    A = p[0]
+    B = p[1]
+    D = p[2]
+    m = 32
+    for i in range(lane, m, nlanes):
+        uu = u[i]
+        v = u[m + i]
+        ul = A if i == 0 else u[i - 1]
+        ur = A if i == m - 1 else u[i + 1]
+        vl = B if i == 0 else u[m + i - 1]
+        vr = B if i == m - 1 else u[m + i + 1]
+        uuv = uu * uu * v
+        du[i] = A + uuv - (B + 1.0) * uu + D * (ul - 2.0 * uu + ur)
+        du[m + i] = B * uu - uuv + D * (vl - 2.0 * v + vr)
+
+
 def interleave(y):
     """[u_0..u_31, v_0..v_31] (last axis) -> [u_0, v_0, u_1, v_1, ...]"""
     y = np.asarray(y)

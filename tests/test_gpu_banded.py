@@ -67,3 +67,30 @@ def test_small_systems_keep_the_dense_matrix():
     a = nb.lsoda(nb.builtin("robertson"), p["u0"], p["t_eval"], p["data"], 1e-8, 1e-8, strict=True, ml=2, mu=2)
     b = nb.lsoda(nb.builtin("robertson"), p["u0"], p["t_eval"], p["data"], 1e-8, 1e-8, strict=True)
     assert a[1] and np.array_equal(a[0], b[0])
+
+
+def test_lane_parallel_rhs_strict_bitwise():
+    """lsoda / dop853(..., rhs_lanes=f): all 32 lanes of a trajectory's warp share the evaluation of
+    the right-hand side (a method-of-lines loop split over the lanes) instead of lane 0 doing it
+    alone -- the same operations per component, so the result is the scalar one bit for bit:
+    numba-compiled pair against the oracle, dense and banded, and the built-in pair."""
+    nb = _nb()
+    B = 60
+    P = pr.brusselator_sweep(B, 4)
+    u0, te = pr.interleave(pr.brusselator_u0()), np.linspace(0, 10, 100)
+    fo = pr.cfunc_address(pr.brusselator_il_rhs)
+    for kw, band in ((dict(ml=2, mu=2), (2, 2)), (dict(), None)):
+        us, ok, cnt = nb.lsoda(pr.brusselator_il_rhs, u0, te, P, 1e-6, 1e-8, strict=True, counters=True,
+                               rhs_lanes=pr.brusselator_il_lanes, **kw)
+        ref, okr, cr = orc.solve_batch("lsoda", fo, u0, te, P, 1e-6, 1e-8, band=band)
+        assert ok.all() and np.array_equal(cnt, cr) and np.array_equal(us, ref)
+        # without the lanes function (lane 0 alone): the same bits
+        us2, ok2 = nb.lsoda(pr.brusselator_il_rhs, u0, te, P, 1e-6, 1e-8, strict=True, **kw)
+        assert np.array_equal(us2, us)
+    # dop853, warp per trajectory (mild diffusion: non-stiff)
+    Pd = np.stack([P[:, 0], P[:, 1], 10.0 ** np.random.default_rng(1).uniform(-1, 0.5, B)], axis=1)
+    te2 = np.linspace(0, 2, 21)
+    us, ok, cnt = nb.dop853(pr.brusselator_il_rhs, u0, te2, Pd, 1e-7, 1e-9, strict=True, counters=True,
+                            rhs_lanes=pr.brusselator_il_lanes)
+    ref, okr, cr = orc.solve_batch("dop853", fo, u0, te2, Pd, 1e-7, 1e-9)
+    assert ok.all() and np.array_equal(cnt[:, :7], cr[:, :7]) and np.array_equal(us, ref)
