@@ -28,7 +28,10 @@ NVCC_FLAGS = ["-O3", "-lineinfo", "-rdc=true", "-fatbin", "-std=c++17"]
 # threads that must fit one SM); chosen so that ptxas does not spill (checked by
 # tests/test_abi.py on the linked cubin).
 MINBLOCKS = {"dop853": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1},
-             "lsoda": {1: 3, 2: 3, 3: 3, 4: 2, 5: 4, 6: 3, 7: 2, 8: 2},
+             # (lsoda n <= 3: four blocks = 128 registers with 4 doubles spilled beat three blocks at
+             # 161 registers by 4.7 % on Robertson -- 9.08 M against 8.68 M traj/s,
+             # profiles/r2_sweep_lsoda_occupancy.log; 120 registers or 5 blocks lose)
+             "lsoda": {1: 4, 2: 4, 3: 4, 4: 2, 5: 4, 6: 3, 7: 2, 8: 2},
              "ivp": {1: 4, 2: 4, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1}}
 # lsoda keeps (13 n + n^2) doubles per thread in shared memory (lsoda_kernel.cu):
 # blocks of 64 threads from n = 5 so that several blocks still fit the 227 KB of an SM

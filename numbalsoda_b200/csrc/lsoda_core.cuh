@@ -85,18 +85,23 @@
 struct LsLane {
     double h, hu, hold, tn, rc, el0, crate, rmax, pdest, pdlast, pdnorm;
     double told, pnorm, del, delp, rate, rh;
-    int nq, meth, mused, ialth, ipup, nslp, icount, irflag, jstart, jcur, kflag;
-    int nst, nfe, nje, nqu;
-    int m, phase;
-    unsigned flags;
+    int nq, nslp;
+    int nst, nfe, nje;
+    int nqu : 16, icount : 16;  // (order of the last step; -1..20)
+    // The small state variables share one register (the kernel carries ~75 values per thread
+    // across a pass; at 128 registers -- 16 warps per SM -- every word counts).  Ranges: meth 1-2,
+    // mused 0-2, jcur 0-1, irflag 0-2, ipup 0 / 2 / 5 (miter), m 0-3 (LS_MAXCOR), phase LS_P_*,
+    // flags LS_F_*, ialth 0-13, jstart -1..1, kflag -10..0.
+    unsigned meth : 2, mused : 2, jcur : 1, irflag : 2, ipup : 3, m : 3, phase : 3, flags : 4;
+    int jstart : 2, kflag : 5, ialth : 5;
 };
 
 struct LsRun {
     int row;      // next usol row to write
     int nslast;   // nst at the last output (mxstep is per output interval, LSODA.cpp:671,:778)
-    int nhnil;    // t + h == t warnings
     int nswitch;  // Adams <-> BDF switches
-    int istate;   // 1 running; 2 finished; <= 0 failed (as LSODA.cpp:782-976; 0 = t_eval not monotone)
+    unsigned nhnil : 8;  // t + h == t warnings, counted up to LS_MXHNIL + 1 (only "<= LS_MXHNIL" is ever asked)
+    int istate : 8;      // 1 running; 2 finished; <= 0 failed (as LSODA.cpp:782-976; 0 = t_eval not monotone)
 };
 
 // Tolerances of one trajectory: the two scalars lsoda_update spreads over its private vectors
@@ -564,7 +569,7 @@ LS_FN bool ls_advance_b(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, dou
             fin = true;
         } else {
             if ((s.tn + s.h) == s.tn) {  // :820-845
-                R.nhnil++;
+                if (R.nhnil <= LS_MXHNIL) R.nhnil++;
                 if (R.nhnil <= LS_MXHNIL && exit_on_warning) {
                     R.istate = -2;
                     fin = true;

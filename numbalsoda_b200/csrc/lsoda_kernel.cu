@@ -87,11 +87,13 @@ __constant__ B200LsodaTables b200_lsoda_tables = B200_LSODA_TABLES_INIT;
 // The tolerances of trajectory b.  Per-component vectors (rtol_vec / atol_vec) are read from
 // global memory where they are used (once per step, in ewset); the pointers are rebuilt from
 // the launch block and b instead of being carried in registers.
-__device__ __forceinline__ LsTol lane_tol(const B200OdeLaunch& L, long long b, double rtol, double atol)
+__device__ __forceinline__ LsTol lane_tol(const B200OdeLaunch& L, long long b)
 {
     LsTol t;
-    t.rtol = rtol;
-    t.atol = atol;
+    // (scalars from the launch block -- the constant bank -- or this trajectory's entry, read
+    // where they are used, once per step: two registers less than carrying them)
+    t.rtol = (L.rtol_b && !L.rtol_vec) ? L.rtol_b[b * L.rtol_sb] : L.rtol;
+    t.atol = (L.atol_b && !L.atol_vec) ? L.atol_b[b * L.atol_sb] : L.atol;
     t.rv = L.rtol_vec ? L.rtol_b + b * L.rtol_sb : nullptr;
     t.av = L.atol_vec ? L.atol_b + b * L.atol_sb : nullptr;
     return t;
@@ -167,24 +169,20 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
 #endif
     double pl[STAGED ? B200ODE_NPMAX : 1];
     double* pp = pl;
-    long long b = -1;  // trajectory of this lane, -1 = idle
-    bool exhausted = false;
+    long long b = -1;  // trajectory of this lane; -1 = idle, -2 = idle and the work counter has run out
     const int nt = L.nt;
     const double* __restrict__ te = L.t_eval;
-    double rtol = L.rtol, atol = L.atol;  // of this lane's trajectory
     // wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130)
-    const unsigned long long mxstep_u = (unsigned long long)(long long)L.mxstep;
+#define MXSTEP_U ((unsigned long long)(long long)L.mxstep)
 
     for (unsigned pass = 0;; pass++) {
         bool done = false;
-        if (b < 0 && !exhausted) {
+        if (b == -1) {
             const long long bn = b200ode_fetch(L.next);
             if (bn >= L.B) {
-                exhausted = true;
+                b = -2;
             } else {
                 b = bn;
-                if (L.rtol_b && !L.rtol_vec) rtol = L.rtol_b[b * L.rtol_sb];
-                if (L.atol_b && !L.atol_vec) atol = L.atol_b[b * L.atol_sb];
                 const double* pg = reinterpret_cast<const double*>(L.data + b * L.data_stride);
                 if (STAGED) {
 #pragma unroll
@@ -198,7 +196,7 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
                 LS_REQI(LS_RI_BHI) = (int)(b >> 32);
 #endif
                 done = ls_begin(s, R, v, L.u0 + b * L.u0_stride, pp, nt, te,
-                                L.usol + (size_t)b * (size_t)nt * N, lane_tol(L, b, rtol, atol));
+                                L.usol + (size_t)b * (size_t)nt * N, lane_tol(L, b));
             }
         }
 #if defined(LS_DEFERRED)
@@ -229,7 +227,7 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
             v.ops = 0;
         }
         // (the barrier also decides whether the block is finished: nobody holds or can fetch work)
-        if (!__syncthreads_or((b >= 0 || !exhausted) ? 1 : 0)) break;
+        if (!__syncthreads_or((b >= -1) ? 1 : 0)) break;
         if (threadIdx.x < LS_NKINDS) qn[((pass + 1u) & 1u) * LS_NKINDS + threadIdx.x] = 0;
         ls_serve<STAGED>(L, q, qc);
         __syncthreads();
@@ -237,14 +235,14 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
         active = b >= 0 && !done;
         lanes = __ballot_sync(FULL, active);
         if (active)
-            done = ls_advance_b(s, R, v, T, pp, lane_tol(L, b, rtol, atol), mxstep_u, L.exit_on_warning, lanes);
+            done = ls_advance_b(s, R, v, T, pp, lane_tol(L, b), MXSTEP_U, L.exit_on_warning, lanes);
 #else
         // lanes with a running trajectory take one pass of the state machine together
         const unsigned lanes = __ballot_sync(FULL, b >= 0 && !done);
         if (lanes == 0 && !__any_sync(FULL, b >= 0)) break;
         if (b >= 0 && !done)
             done = ls_advance(s, R, v, T, pp, nt, te, L.usol + (size_t)b * (size_t)nt * N,
-                              lane_tol(L, b, rtol, atol), mxstep_u, L.exit_on_warning, lanes);
+                              lane_tol(L, b), MXSTEP_U, L.exit_on_warning, lanes);
 #endif
         if (b >= 0 && done) {
             // wrapper.cpp:41-45: istate <= 0 -> success = 0
@@ -268,13 +266,20 @@ __device__ __forceinline__ void lsoda_ensemble(const B200OdeLaunch& L)
     }
 }
 
-extern "C" __global__ void __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+// (B200_MAXNREG: an explicit register budget instead of the one ptxas derives from the launch
+// bounds, for geometry experiments: tools/sweep_lsoda.sh)
+#ifdef B200_MAXNREG
+#define LS_BOUNDS __maxnreg__(B200_MAXNREG)
+#else
+#define LS_BOUNDS __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+#endif
+extern "C" __global__ void LS_BOUNDS
 b200ode_lsoda_kernel(const B200OdeLaunch L)
 {
     lsoda_ensemble<true>(L);
 }
 
-extern "C" __global__ void __launch_bounds__(B200_THREADS, B200_MINBLOCKS)
+extern "C" __global__ void LS_BOUNDS
 b200ode_lsoda_kernel_ptr(const B200OdeLaunch L)
 {
     lsoda_ensemble<false>(L);

@@ -58,7 +58,14 @@ def test_link_builtin_and_numba_rhs(solver, strict):
 def test_linked_kernel_keeps_state_in_registers(tmp_path, solver, mode):
     """cuobjdump on the linked cubin, every link mode: no local-memory spills, no stack, the
     user RHS inlined (no CALL to b200ode_user_rhs survives); the libm-exact pow (its tables)
-    is linked out of the default mode's thread kernels."""
+    is linked out of the default mode's thread kernels.
+
+    One measured exception: LSODA n = 3 runs four blocks of 128 threads per SM (128 registers,
+    build.py MINBLOCKS).  The default mode fits without a spill; the two verification modes
+    (strict, exact_ctrl: IEEE division and the double-precision pow as out-of-line calls) park
+    up to three rarely used words (pnorm, the packed order counters) on the stack and are still
+    faster than with three blocks at 161 registers (5.42 M against 5.13 M trajectories/s,
+    profiles/r2_sweep_lsoda_occupancy.log)."""
     import numbalsoda_b200 as nb
     from numbalsoda_b200 import _lib
     h = nb.get_handle(pr.lorenz_rhs, _lib.DOP853 if solver == "dop853" else _lib.LSODA, 3,
@@ -69,7 +76,8 @@ def test_linked_kernel_keeps_state_in_registers(tmp_path, solver, mode):
     m = re.search(r"Function b200ode_%s_kernel:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)" % solver, res)
     assert m, res
     regs, stack, shared, local = map(int, m.groups())
-    assert stack == 0 and local == 0 and regs <= 255
+    allowed = 32 if (solver == "lsoda" and mode != "fast") else 0
+    assert stack <= allowed and local == 0 and regs <= 255
     sass = subprocess.run(["cuobjdump", "-sass", str(f)], capture_output=True, text=True).stdout
     assert "b200ode_user_rhs" not in sass
     assert "DFMA" in sass

@@ -252,7 +252,8 @@ def test_device_resident_entry_point():
                                   te.cpu().numpy(), P.cpu().numpy(), 1e-8, 1e-8)
     assert bool((ok == 1).all()) and np.array_equal(usol.cpu().numpy(), ref)
     info = h.kernel_info()
-    assert info["local_bytes"] == 0 and info["launches"] >= 1
+    # (strict mode at 128 registers: up to three rarely used words on the stack, tests/test_abi.py)
+    assert info["local_bytes"] <= 32 and info["launches"] >= 1
 
 
 # ---------------------------------------------------------------- warp-per-trajectory kernel
