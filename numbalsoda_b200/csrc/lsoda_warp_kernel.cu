@@ -74,8 +74,10 @@ __device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L)
 
 // Two entry points, one body: the dense iteration matrix limits an SM to 4 warps by shared memory
 // at n = 64, so that kernel takes the registers it likes (252); the banded one (ml, mu >= 0) fits
-// 12 warps and is compiled for that (168 registers).
-extern "C" __global__ void __launch_bounds__(32)
+// 12 warps and is compiled for that (168 registers).  (The dense bound is explicit -- 8 blocks of
+// one warp = 255 registers: left to itself ptxas once settled on 128 registers and 144 bytes of
+// spills for this kernel.)
+extern "C" __global__ void __launch_bounds__(32, 8)
 b200ode_lsodaw_kernel(const B200OdeLaunch L)
 {
     lsodaw_ensemble(L);

@@ -84,6 +84,26 @@ def test_linked_kernel_keeps_state_in_registers(tmp_path, solver, mode):
     assert "b200ode_link_flags" not in sass  # the mode is a link-time constant
 
 
+@pytest.mark.parametrize("solver", ["dop853", "lsoda"])
+@pytest.mark.parametrize("mode", ["fast", "exact_ctrl", "strict"])
+def test_warp_kernels_do_not_spill(tmp_path, solver, mode):
+    """The warp-per-trajectory images (n = 9..128; dense and banded LSODA entry points, DOP853):
+    every kernel of the linked cubin without stack or local memory."""
+    import numbalsoda_b200 as nb
+    from numbalsoda_b200 import _lib
+    h = nb.get_handle(nb.builtin("brusselator1d_il"), _lib.DOP853 if solver == "dop853" else _lib.LSODA, 64,
+                      strict=mode == "strict", exact_ctrl=mode == "exact_ctrl")
+    f = tmp_path / "k.cubin"
+    f.write_bytes(h.cubin())
+    res = subprocess.run(["cuobjdump", "-res-usage", str(f)], capture_output=True, text=True).stdout
+    found = re.findall(r"Function (b200ode_\w+_kernel\w*):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", res)
+    assert found, res
+    if solver == "lsoda":
+        assert {k for k, *_ in found} >= {"b200ode_lsodaw_kernel", "b200ode_lsodaw_band_kernel"}
+    for name, regs, stack, local in found:
+        assert int(stack) == 0 and int(local) == 0 and int(regs) <= 255, (name, regs, stack, local)
+
+
 def test_cfunc_address_is_resolved():
     import numba
     import numbalsoda_b200 as nb
