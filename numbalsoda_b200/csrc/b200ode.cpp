@@ -130,6 +130,7 @@ struct PerDevice {
     CUfunction fn_ptr = nullptr;  // data record passed by address (np < 0)
     CUfunction fn_vtol = nullptr, fn_ptr_vtol = nullptr;  // dop853 thread kernel: per-component tolerances
     CUfunction fn_band = nullptr; // warp lsoda: the same kernel built for 12 resident warps (banded matrix)
+    CUfunction fn_tmem = nullptr; // warp lsoda, 32 < n <= 64: dense matrix in tensor memory, 8 warps per block
     CUdeviceptr next = 0;  // kCounterSlots work-queue heads
     int regs = 0, local_bytes = 0, smem = 0, blocks_per_sm = 0, sms = 0;
     int dyn_smem = 0;  // dynamic shared memory per block
@@ -402,6 +403,11 @@ static int init_device_state(b200ode_rhs_t H, int device, PerDevice& P)
         P.fn_ptr = P.fn;  // the warp kernel always hands the data record over by address
         if (H->solver == B200ODE_LSODA)
             CU(cuModuleGetFunction(&P.fn_band, P.mod, "b200ode_lsodaw_band_kernel"));
+        if (H->solver == B200ODE_LSODA && H->neq > 32 && H->neq <= B200ODE_LSODAW_TMEM_NMAX) {
+            CU(cuModuleGetFunction(&P.fn_tmem, P.mod, "b200ode_lsodaw_tmem_kernel"));
+            CU(cuFuncSetAttribute(P.fn_tmem, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                  B200ODE_LSODAW_TMEM_WARPS * B200ODE_LSODAW_TMEM_DOUBLES(H->neq) * (int)sizeof(double)));
+        }
     } else
         CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
                                (std::string(kernel_name(H->solver, H->neq)) + "_ptr").c_str()));
@@ -654,6 +660,19 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
         if (nb < 1) nb = 1;
         grid = (int)std::min<long long>(want, (long long)P->sms * nb);
     }
+    int threads = kThreads;
+    if (P->fn_tmem && fn == P->fn_ptr && !P->wm_scratch && P->blocks_per_sm < B200ODE_LSODAW_TMEM_WARPS) {
+        // dense matrix, fewer than eight trajectories per SM in shared memory: keep the matrices in
+        // tensor memory instead (B200ODE_LSODAW_TMEM=0: the shared-memory kernel, for comparisons)
+        const char* e = getenv("B200ODE_LSODAW_TMEM");
+        if (!(e && !strcmp(e, "0"))) {
+            fn = P->fn_tmem;
+            threads = 32 * B200ODE_LSODAW_TMEM_WARPS;
+            dyn_smem = B200ODE_LSODAW_TMEM_WARPS * B200ODE_LSODAW_TMEM_DOUBLES(H->neq) * (int)sizeof(double);
+            grid = (int)std::min<long long>((want + B200ODE_LSODAW_TMEM_WARPS - 1) / B200ODE_LSODAW_TMEM_WARPS,
+                                            (long long)P->sms);
+        }
+    }
     args.te_shared = 0;
     if (!warp && H->solver == B200ODE_DOP853) {
         // a copy of t_eval per block, if it costs no resident block (dop853_kernel.cu)
@@ -667,7 +686,7 @@ static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, C
         }
     }
     void* params[] = {&args};
-    CU(cuLaunchKernel(fn, grid, 1, 1, kThreads, 1, 1, (unsigned)dyn_smem, stream, params, nullptr));
+    CU(cuLaunchKernel(fn, grid, 1, 1, threads, 1, 1, (unsigned)dyn_smem, stream, params, nullptr));
     if (P->wm_scratch) CU(cuEventRecord(P->wm_done[set], stream));
     H->last_grid = grid;
     H->launches++;

@@ -29,6 +29,13 @@
 #define B200ODE_LSODAW_DOUBLES(n) \
     (18 * (n) + B200ODE_LSODAW_MATRIX(n) + B200ODE_LSODAW_JCOLS * ((n) + 1) + (n) + 1)
 
+/* ... with the dense matrix in tensor memory (32 < n <= 64; lsoda_vec_warp.cuh): blocks of eight
+ * independent warps, each with 32 lanes x 256 columns of the block's 512-column allocation; shared
+ * memory keeps the vectors, the perturbed copies of y and their right-hand sides */
+#define B200ODE_LSODAW_TMEM_NMAX 64
+#define B200ODE_LSODAW_TMEM_WARPS 8
+#define B200ODE_LSODAW_TMEM_DOUBLES(n) (18 * (n) + 2 * B200ODE_LSODAW_JCOLS * ((n) + 1) + (n) + 1)
+
 /* ... and with a banded iteration matrix (ml, mu >= 0): band storage (2 ml + mu + 1) x n, and two
  * vectors (perturbed state, its right-hand side) for each column group evaluated concurrently */
 #define B200ODE_LSODAW_BAND_MATRIX(n, ml, mu) ((2 * (ml) + (mu) + 1) * (n))

@@ -49,7 +49,13 @@
 // and the n/8 rounds of RHS evaluations stay a small part of prja next to the LU
 #define WV_JCOLS (WV_NL < B200ODE_LSODAW_JCOLS ? WV_NL : B200ODE_LSODAW_JCOLS)
 #define WV_NPL (WV_NMAX / WV_NL)  // rows a lane can own
+// (a lane owns at most WV_NPL = 4 components: unrolling these loops only grows the code, and the
+// warp kernels are bound by instruction fetch -- 140 KB of SASS against a 32 KB instruction cache)
+#if defined(__CUDA_ARCH__)
+#define WV_FOR_OWN(i) _Pragma("unroll 1") for (int i = WV_LANE; i < n; i += WV_NL)
+#else
 #define WV_FOR_OWN(i) for (int i = WV_LANE; i < n; i += WV_NL)
+#endif
 #define WYH(j, i) yh[((j) - 1) * n + (i)]
 #define WMT(r, c) wmT[(c) * ld + (r)]  // a[r][c]
 
@@ -69,7 +75,98 @@ double wv_wmax_norm(const double* v, const double* w, int n)
     return wv_max(vm);
 }
 
-struct LsWarpVec {
+// ---- tensor memory as row storage (sm_100a).  A warp owns the 32 TMEM lanes of its quadrant
+// (warp index mod 4): lane l keeps rows l and l + 32 of the iteration matrix, row block q at
+// columns 2 (64 q + c) .. + 1 (a double is two 32-bit columns).  tcgen05.ld / .st move the same
+// column range of every lane at once: eight consecutive entries of each lane's row per
+// instruction (.32x32b.x16), or one entry (.x2); the column address is a run-time value
+// (tools/tmem_probe.cu checks all of this on the device).  Loads and stores are asynchronous:
+// a load's wait is part of the same asm statement, so that no use of the registers can move above
+// it; stores are followed by wv_tm_wait_st() before their columns are read again.
+#define WV_TM_STRIDE 64  // doubles per row block in tensor memory (n <= 64)
+#if defined(__CUDA_ARCH__)
+// (the 32-bit halves are paired inside the asm statement: ptxas then loads straight into the
+// register pairs of the doubles instead of moving sixteen words around)
+#define WV_TM_REGS "t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15"
+__device__ __forceinline__ void wv_tm_ld8(unsigned taddr, double (&v)[8])
+{
+    asm volatile("{\n .reg .b32 t<16>;\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {" WV_TM_REGS "}, [%8];\n"
+                 "tcgen05.wait::ld.sync.aligned;\n"
+                 "mov.b64 %0, {t0,t1};\n mov.b64 %1, {t2,t3};\n mov.b64 %2, {t4,t5};\n mov.b64 %3, {t6,t7};\n"
+                 "mov.b64 %4, {t8,t9};\n mov.b64 %5, {t10,t11};\n mov.b64 %6, {t12,t13};\n mov.b64 %7, {t14,t15};\n}"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// two windows, one wait
+__device__ __forceinline__ void wv_tm_ld8x2(unsigned ta, unsigned tb, double (&v)[8], double (&w)[8])
+{
+    asm volatile("{\n .reg .b32 t<16>;\n .reg .b32 s<16>;\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {" WV_TM_REGS "}, [%16];\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {s0,s1,s2,s3,s4,s5,s6,s7,s8,s9,s10,s11,s12,s13,s14,s15}, [%17];\n"
+                 "tcgen05.wait::ld.sync.aligned;\n"
+                 "mov.b64 %0, {t0,t1};\n mov.b64 %1, {t2,t3};\n mov.b64 %2, {t4,t5};\n mov.b64 %3, {t6,t7};\n"
+                 "mov.b64 %4, {t8,t9};\n mov.b64 %5, {t10,t11};\n mov.b64 %6, {t12,t13};\n mov.b64 %7, {t14,t15};\n"
+                 "mov.b64 %8, {s0,s1};\n mov.b64 %9, {s2,s3};\n mov.b64 %10, {s4,s5};\n mov.b64 %11, {s6,s7};\n"
+                 "mov.b64 %12, {s8,s9};\n mov.b64 %13, {s10,s11};\n mov.b64 %14, {s12,s13};\n mov.b64 %15, {s14,s15};\n}"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]),
+                   "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]), "=d"(w[4]), "=d"(w[5]), "=d"(w[6]), "=d"(w[7])
+                 : "r"(ta), "r"(tb)
+                 : "memory");
+}
+// (asynchronous: wv_tm_wait_st before the stored columns are loaded again)
+__device__ __forceinline__ void wv_tm_st8(unsigned taddr, const double (&v)[8])
+{
+    asm volatile("{\n .reg .b32 t<16>;\n"
+                 "mov.b64 {t0,t1}, %1;\n mov.b64 {t2,t3}, %2;\n mov.b64 {t4,t5}, %3;\n mov.b64 {t6,t7}, %4;\n"
+                 "mov.b64 {t8,t9}, %5;\n mov.b64 {t10,t11}, %6;\n mov.b64 {t12,t13}, %7;\n mov.b64 {t14,t15}, %8;\n"
+                 "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {" WV_TM_REGS "};\n}"
+                 :
+                 : "r"(taddr), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void wv_tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ double wv_tm_ld1(unsigned taddr)
+{
+    double x;
+    asm volatile("{\n .reg .b32 t<2>;\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x2.b32 {t0,t1}, [%1];\n"
+                 "tcgen05.wait::ld.sync.aligned;\n"
+                 "mov.b64 %0, {t0,t1};\n}"
+                 : "=d"(x)
+                 : "r"(taddr)
+                 : "memory");
+    return x;
+}
+__device__ __forceinline__ void wv_tm_st1(unsigned taddr, double x)
+{
+    asm volatile("{\n .reg .b32 t<2>;\n"
+                 "mov.b64 {t0,t1}, %1;\n"
+                 "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {t0,t1};\n}"
+                 :
+                 : "r"(taddr), "d"(x)
+                 : "memory");
+}
+#else
+// (host builds instantiate the shared-memory backend only)
+static inline void wv_tm_ld8(unsigned, double (&)[8]) {}
+static inline void wv_tm_ld8x2(unsigned, unsigned, double (&)[8], double (&)[8]) {}
+static inline void wv_tm_st8(unsigned, const double (&)[8]) {}
+static inline void wv_tm_wait_st() {}
+static inline double wv_tm_ld1(unsigned) { return 0.0; }
+static inline void wv_tm_st1(unsigned, double) {}
+#endif
+
+// TM: the dense iteration matrix lives in tensor memory instead of shared memory (32 < n <= 64).
+// At n = 64 the matrix is 32 KB of the 47 KB a trajectory needs, and shared memory holds four
+// trajectories per SM -- one warp per scheduler, nothing to hide latency with.  Tensor memory is
+// another 256 KB per SM that this kernel has no other use for: eight matrices, eight warps.
+template <bool TM>
+struct LsWarpVecT {
+    unsigned tm;  // TM: tensor-memory address of this warp's 32 lanes x 256 columns
+    double* fcopy;  // TM: right-hand sides of the perturbed copies (the matrix columns' staging)
+    LS_MFN unsigned tma(int q, int c) const { return tm + 2u * (unsigned)(q * WV_TM_STRIDE + c); }
     int n, ld;
     bool fast;  // parallel triangular solves (see above); false = the reference's summation order
     // Banded iteration matrix (jt = 5 with ml, mu, which the
@@ -100,7 +197,11 @@ struct LsWarpVec {
         ewt = acor + n;
         rdiag = ewt + n;
         double* next = rdiag + n;
-        if (matrix) {
+        if (TM) {
+            wmT = nullptr;
+            fcopy = next;
+            next += B200ODE_LSODAW_JCOLS * ld;
+        } else if (matrix) {
             wmT = matrix;
         } else {
             wmT = next;
@@ -303,8 +404,152 @@ struct LsWarpVec {
 
     // ---- linear algebra
     // dgefa, LSODA.cpp:173-231.  Returns nonzero when a zero pivot was met.
+    // The same factorisation with the matrix in tensor memory.  Row k is first copied to shared
+    // memory by the lane that owns it (the pivot search and every row's update read it); then
+    // each lane updates eight entries of its own rows per load / store.  Element for element the
+    // arithmetic is the loop below's.  The pivots (the diagonal of the factors) are collected in
+    // rdiag on the way: a lane's diagonal entries sit at different columns, which a tensor-memory
+    // load cannot address at once.
+    LS_MFN int dgefa_tm()
+    {
+        int info = 0;
+        // row k in shared memory, double buffered: the lane that owns row k + 1 files it while it
+        // updates it (ucopy is free between the Jacobian's evaluation and the next one)
+        double* prow = ucopy;
+        double* pnext = ucopy + WV_TM_STRIDE;
+        bool have = false;
+        const int nblk = (n + 31) >> 5;
+        for (int k = 0; k < n - 1; k++) {
+            const int qk = k >> 5, lk = k & 31, ck0 = k & ~7;
+            if (!have) {
+                for (int c0 = ck0; c0 < n; c0 += 8) {
+                    double v[8];
+                    wv_tm_ld8(tma(qk, c0), v);
+                    if (WV_LANE == lk) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) prow[c0 + e] = v[e];
+                    }
+                }
+                WV_SYNC();
+            }
+            have = false;
+            unsigned long long best = 0;
+            int bj = n;
+            for (int c = k + WV_LANE; c < n; c += WV_NL) {
+                const unsigned long long v = ls_trunc_u64(prow[c]);
+                if (v > best) {
+                    best = v;
+                    bj = c;
+                }
+            }
+            wv_argmax(best, bj);
+            const int j = (best == 0) ? k : bj;
+            const double akj = prow[j];
+            WV_SYNC();
+            if (WV_LANE == 0) {
+                ipvt[k] = j;
+                rdiag[k] = akj;
+            }
+            if (akj == 0.0) {
+                info = k + 1;
+                continue;
+            }
+            if (j != k && WV_LANE == 0) {
+                prow[j] = prow[k];
+                prow[k] = akj;
+            }
+            WV_SYNC();
+            const double t = ls_div(-1.0, akj);
+            for (int c = k + 1 + WV_LANE; c < n; c += WV_NL) prow[c] = t * prow[c];
+            WV_SYNC();
+            for (int q = 0; q < nblk; q++) {
+                const bool has_rows = 32 * q + 31 >= k;  // rows k.. in this block
+                if (!has_rows && !(fast && j != k)) continue;
+                const int r = WV_LANE + 32 * q;
+                const bool below = r > k && r < n, isk = r == k, isnext = r == k + 1;
+                // the interchange of columns j and k: rows below the pivot row, and in fast mode the
+                // multipliers of the rows above it; the entry left at column k is the multiplier
+                const double tr = wv_tm_ld1(tma(q, j));
+                if (j != k) {
+                    const double ark = wv_tm_ld1(tma(q, k));
+                    const bool swap = below || (fast && r < k);
+                    wv_tm_st1(tma(q, k), swap ? tr : ark);
+                    wv_tm_st1(tma(q, j), swap ? ark : tr);
+                    wv_tm_wait_st();
+                }
+                if (!has_rows) continue;
+                for (int c0 = ck0; c0 < n; c0 += 8) {
+                    double v[8], p[8];
+                    wv_tm_ld8(tma(q, c0), v);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) p[e] = prow[c0 + e];
+                    if (c0 == ck0) {
+                        // (the chunk that holds column k: entries up to it stay)
+                        if (below) {
+#pragma unroll
+                            for (int e = 0; e < 8; e++)
+                                if (c0 + e > k) v[e] = tr * p[e] + v[e];
+                        } else if (isk) {
+#pragma unroll
+                            for (int e = 0; e < 8; e++)
+                                if (c0 + e >= k) v[e] = p[e];
+                        }
+                    } else if (below) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) v[e] = tr * p[e] + v[e];
+                    } else if (isk) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) v[e] = p[e];
+                    }
+                    if (isnext) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) pnext[c0 + e] = v[e];
+                    }
+                    wv_tm_st8(tma(q, c0), v);
+                }
+            }
+            wv_tm_wait_st();
+            WV_SYNC();
+            {
+                double* sw = prow;
+                prow = pnext;
+                pnext = sw;
+            }
+            have = true;
+        }
+        // the last diagonal entry: its owner reads it, everybody learns it
+        double ann = wv_tm_ld1(tma((n - 1) >> 5, n - 1));
+        ann = wv_bcast(ann, (n - 1) & 31);
+        if (WV_LANE == 0) {
+            ipvt[n - 1] = n - 1;
+            rdiag[n - 1] = ann;
+        }
+        if (ann == 0.0) info = n;
+        WV_SYNC();
+        if (fast) {
+            WV_FOR_OWN(i) {
+                rdiag[i] = ls_div(1.0, rdiag[i]);
+                perm[i] = i;
+            }
+            WV_SYNC();
+            if (WV_LANE == 0) {
+                for (int k = n - 2; k >= 0; k--) {
+                    const int j = ipvt[k];
+                    if (j != k) {
+                        const int pk = perm[k];
+                        perm[k] = perm[j];
+                        perm[j] = pk;
+                    }
+                }
+            }
+            WV_SYNC();
+        }
+        return info;
+    }
+
     LS_MFN int dgefa()
     {
+        if constexpr (TM) return dgefa_tm();
         int info = 0;
         for (int k = 0; k < n - 1; k++) {
             // idamax1 along row k (integer-truncated magnitudes, first maximum)
@@ -382,8 +627,112 @@ struct LsWarpVec {
     }
 
     // dgesl with job = 0, LSODA.cpp:119-144
+    // ... and the solve: the sweeps below with eight columns of each lane's rows per load.
+    // rdiag holds the pivots (strict) or their reciprocals (fast).
+    LS_MFN void dgesl_tm(double* b) const
+    {
+        const bool two = n > 32;
+        // forward.  t[q2]: the running sum of this lane's row in block q2 -- read when that row's
+        // column comes up, dead afterwards, so rows already solved may go on accumulating.
+        double t[2] = {0.0, 0.0};
+        for (int c0 = 0; c0 < n; c0 += 8) {
+            const int q = c0 >> 5;  // the block of rows c0 .. c0 + 7
+            double w0[8], w1[8];
+            if (q == 0 && two) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
+            else if (q == 0) wv_tm_ld8(tma(0, c0), w0);
+            else wv_tm_ld8(tma(1, c0), w1);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int c = c0 + e;
+                if (c >= n) break;
+                const int cc = c & 31;
+                double bc = 0.0;
+                if (WV_LANE == cc) {
+                    const double tq = (q == 0) ? t[0] : t[1];
+                    bc = fast ? (b[c] - tq) * rdiag[c] : ls_div(b[c] - tq, rdiag[c]);
+                    b[c] = bc;
+                }
+                bc = wv_bcast(bc, cc);
+                if (q == 0) t[0] += w0[e] * bc;
+                if (two) t[1] += w1[e] * bc;
+            }
+        }
+        WV_SYNC();
+        if (fast) {
+            t[0] = t[1] = 0.0;
+            for (int c0 = (n - 1) & ~7; c0 >= 0; c0 -= 8) {
+                const int q = c0 >> 5;
+                double w0[8], w1[8];
+                if (q == 1) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
+                else wv_tm_ld8(tma(0, c0), w0);
+#pragma unroll
+                for (int e = 7; e >= 0; e--) {
+                    const int c = c0 + e;
+                    if (c >= n) continue;
+                    const int cc = c & 31;
+                    double wc = 0.0;
+                    if (WV_LANE == cc) {
+                        wc = b[c] + ((q == 0) ? t[0] : t[1]);
+                        b[c] = wc;
+                    }
+                    wc = wv_bcast(wc, cc);
+                    t[0] += w0[e] * wc;
+                    if (q == 1) t[1] += w1[e] * wc;
+                }
+            }
+            WV_SYNC();
+            double x[2];
+#pragma unroll
+            for (int q2 = 0; q2 < 2; q2++) {
+                const int i = WV_LANE + 32 * q2;
+                x[q2] = (i < n) ? b[perm[i]] : 0.0;
+            }
+            WV_SYNC();
+#pragma unroll
+            for (int q2 = 0; q2 < 2; q2++) {
+                const int i = WV_LANE + 32 * q2;
+                if (i < n) b[i] = x[q2];
+            }
+            WV_SYNC();
+            return;
+        }
+        // backward, the reference's order: the owner of row k forms the dot product over ascending
+        // c (the other lanes run the same instructions on their own rows; their sums are unused)
+        for (int k = n - 2; k >= 0; k--) {
+            const int qk = k >> 5;
+            double tk = 0.0;
+            for (int c0 = (k + 1) & ~7; c0 < n; c0 += 8) {
+                double v[8];
+                wv_tm_ld8(tma(qk, c0), v);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int c = c0 + e;
+                    if (c > k && c < n) tk += v[e] * b[c];
+                }
+            }
+            tk = wv_bcast(tk, k & 31);
+            WV_SYNC();
+            if (WV_LANE == 0) {
+                const double bk = b[k] + tk;
+                const int j = ipvt[k];
+                if (j != k) {
+                    const double tt = b[j];
+                    b[j] = bk;
+                    b[k] = tt;
+                } else {
+                    b[k] = bk;
+                }
+            }
+            WV_SYNC();
+        }
+    }
+
     LS_MFN void dgesl(double* b) const
     {
+        if constexpr (TM) {
+            dgesl_tm(b);
+            return;
+        }
         // forward: t_k = sum_{c<k} a[k][c] b[c] accumulated column by column
         double t[WV_NPL];
 #pragma unroll
@@ -652,8 +1001,70 @@ struct LsWarpVec {
     }
 #undef WABD
 
+    // prja with the matrix in tensor memory: the perturbed right-hand sides land in shared memory
+    // (fcopy), and each lane then forms eight columns' entries of its own rows, adds them to its
+    // rows' fnorm sums (ascending j, as the reference), adds the identity and stores them.
+    LS_MFN int prja_tm(double tn, double h, double hl0, double* pp, double& pdnorm)
+    {
+        const double fac0 = norm_ptr(savf);
+        double r0 = 1000.0 * fabs(h) * LS_ETA * ((double)n) * fac0;
+        if (r0 == 0.0) r0 = 1.0;
+        const int nblk = (n + 31) >> 5;
+        double sum[2] = {0.0, 0.0};
+        for (int j0 = 0; j0 < n; j0 += WV_JCOLS) {
+            const int j = j0 + WV_LANE;
+            double fac = 0.0;
+            if (WV_LANE < WV_JCOLS && j < n) {
+                double* u = ucopy + WV_LANE * ld;
+                for (int i = 0; i < n; i++) u[i] = y[i];
+                const double yj = y[j];
+                const double r = ls_max(LS_SQRTETA * fabs(yj), ls_div(r0, ewt[j]));
+                u[j] = yj + r;
+                fac = ls_div(-hl0, r);
+                wv_user_rhs(tn, u, fcopy + WV_LANE * ld, pp);
+            }
+            WV_SYNC();
+            for (int g = 0; g < WV_JCOLS && j0 + g < n; g += 8) {
+                double fe[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) fe[e] = wv_bcast(fac, (g + e) & 31);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    if (q < nblk) {
+                        const int i = WV_LANE + 32 * q;
+                        const double si = (i < n) ? savf[i] : 0.0;
+                        double v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const int jj = j0 + g + e;
+                            v[e] = 0.0;
+                            if (i < n && jj < n) {
+                                v[e] = (fcopy[(g + e) * ld + i] - si) * fe[e];
+                                sum[q] += ls_div(fabs(v[e]), ewt[jj]);
+                                if (i == jj) v[e] = v[e] + 1.0;
+                            }
+                        }
+                        wv_tm_st8(tma(q, j0 + g), v);
+                    }
+                }
+            }
+            WV_SYNC();
+        }
+        wv_tm_wait_st();
+        double an = 0.0;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int i = WV_LANE + 32 * q;
+            if (i < n) an = ls_max(an, sum[q] * ewt[i]);
+        }
+        an = wv_max(an);
+        pdnorm = ls_div(an, fabs(hl0));
+        return dgefa() != 0 ? 1 : 0;
+    }
+
     LS_MFN int prja(double tn, double h, double hl0, double* pp, double& pdnorm)
     {
+        if constexpr (TM) return prja_tm(tn, h, hl0, pp, pdnorm);
         if (banded()) return prja_band(tn, h, hl0, pp, pdnorm);
         const double fac0 = norm_ptr(savf);
         double r0 = 1000.0 * fabs(h) * LS_ETA * ((double)n) * fac0;
@@ -687,5 +1098,6 @@ struct LsWarpVec {
         return dgefa() != 0 ? 1 : 0;
     }
 };
+typedef LsWarpVecT<false> LsWarpVec;
 
 #endif

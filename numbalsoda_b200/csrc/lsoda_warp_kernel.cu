@@ -23,14 +23,21 @@
 
 __constant__ B200LsodaTables b200_lsoda_tables = B200_LSODA_TABLES_INIT;
 
-__device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L)
+template <bool TM>
+__device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L, unsigned tm = 0)
 {
     extern __shared__ double b200_smem[];
     const B200LsodaTables* T = &b200_lsoda_tables;
     const int n = L.neq;
-    LsWarpVec v;
-    v.attach(b200_smem, n, L.strict == 0,
-             L.scratch ? L.scratch + (size_t)blockIdx.x * B200ODE_LSODAW_MATRIX(n) : nullptr, L.ml, L.mu);
+    LsWarpVecT<TM> v;
+    if (TM) {
+        // a block of independent warps: each its own slice of shared and of tensor memory
+        v.tm = tm;
+        v.attach(b200_smem + (size_t)(threadIdx.x >> 5) * B200ODE_LSODAW_TMEM_DOUBLES(n), n, L.strict == 0);
+    } else {
+        v.attach(b200_smem, n, L.strict == 0,
+                 L.scratch ? L.scratch + (size_t)blockIdx.x * B200ODE_LSODAW_MATRIX(n) : nullptr, L.ml, L.mu);
+    }
     const int nt = L.nt;
     const double* __restrict__ te = L.t_eval;
     // wrapper.cpp:16 stores the int in a size_t member (LSODA.h:130)
@@ -80,11 +87,34 @@ __device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L)
 extern "C" __global__ void __launch_bounds__(32, 8)
 b200ode_lsodaw_kernel(const B200OdeLaunch L)
 {
-    lsodaw_ensemble(L);
+    lsodaw_ensemble<false>(L);
 }
 
 extern "C" __global__ void __launch_bounds__(32, 12)
 b200ode_lsodaw_band_kernel(const B200OdeLaunch L)
 {
-    lsodaw_ensemble(L);
+    lsodaw_ensemble<false>(L);
+}
+
+// Dense matrix in tensor memory (lsoda_vec_warp.cuh), 32 < n <= 64: one block of eight warps per
+// SM, each warp a trajectory of its own.  Warp 0 allocates all 512 columns; warp w works in the
+// lanes of its quadrant (w mod 4) and in the column half w / 4.  The only block-wide
+// synchronisation is around the allocation and the release.
+extern "C" __global__ void __launch_bounds__(32 * B200ODE_LSODAW_TMEM_WARPS, 1)
+b200ode_lsodaw_tmem_kernel(const B200OdeLaunch L)
+{
+    __shared__ unsigned tm_base;
+    const unsigned warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(&tm_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    lsodaw_ensemble<true>(L, tm_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 256u);
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tm_base));
 }

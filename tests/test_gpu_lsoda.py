@@ -352,6 +352,40 @@ def test_pivoting_lu_strict_bitwise_and_fast_close(n):
     assert err.max() < 50.0, err.max()
 
 
+@pytest.mark.parametrize("n", [47, 56, 64])
+def test_tensor_memory_matrix_strict_bitwise_and_same_as_shared_memory(n, monkeypatch):
+    """32 < n <= 64 with fewer than eight trajectories per SM in shared memory: the dense
+    iteration matrix lives in tensor memory (lsoda_vec_warp.cuh, dgefa_tm / dgesl_tm / prja_tm;
+    blocks of eight warps).  Storage only: strict mode is bit-for-bit the oracle -- on a system
+    whose pivot search interchanges columns and on the nonlinear chain, sizes that are and are not
+    multiples of 8 and of 32 -- and every mode gives the bits of the shared-memory kernel
+    (B200ODE_LSODAW_TMEM=0)."""
+    nb = _nb()
+    from numbalsoda_b200 import _lib
+    B = 19  # (more warps than one block holds, not a multiple of 8)
+    te = np.linspace(0.0, 2.0, 9)
+    for rhs, u0, P, tol in (
+            (pr.upper_rhs, np.ones(n), np.array([[1000.0 * (1 + 0.1 * b), 5000.0, float(n)] for b in range(B)]),
+             (1e-6, 1e-9)),
+            (pr.chain_rhs, 1.0 + 0.1 * np.arange(n), np.array([[50.0 * (1 + b), float(n)] for b in range(B)]),
+             (1e-7, 1e-9))):
+        monkeypatch.delenv("B200ODE_LSODAW_TMEM", raising=False)
+        us, ok, cnt = nb.lsoda(rhs, u0, te, P, *tol, strict=True, counters=True)
+        h = nb.get_handle(rhs, _lib.LSODA, n, strict=True)
+        assert h.kernel_info()["last_grid"] == (B + 7) // 8  # blocks of eight warps: the tensor-memory kernel
+        ref, okr, cr = orc.solve_batch("lsoda", pr.cfunc_address(rhs), u0, te, P, *tol)
+        assert ok.all() and okr.all() and np.array_equal(cnt, cr) and np.array_equal(us, ref), rhs.__name__
+        assert (cnt[:, 2] > 0).sum() >= B // 2  # Jacobians, factorisations and solves took place
+        usf, okf, cntf = nb.lsoda(rhs, u0, te, P, *tol, counters=True)
+        monkeypatch.setenv("B200ODE_LSODAW_TMEM", "0")
+        us0, ok0, cnt0 = nb.lsoda(rhs, u0, te, P, *tol, strict=True, counters=True)
+        assert h.kernel_info()["last_grid"] == B  # one warp per block: the shared-memory kernel
+        usf0, okf0, cntf0 = nb.lsoda(rhs, u0, te, P, *tol, counters=True)
+        assert np.array_equal(us0, us) and np.array_equal(cnt0, cnt)
+        assert okf.all() and np.array_equal(usf0, usf) and np.array_equal(cntf0, cntf), rhs.__name__
+    monkeypatch.delenv("B200ODE_LSODAW_TMEM", raising=False)
+
+
 def test_data_record_passed_by_address():
     """Records of more than 16 doubles are not staged into registers: the RHS gets the
     record's device address (the kernels' `_ptr` entry points), as it would a C struct."""

@@ -20,7 +20,7 @@ from numbalsoda_b200 import _lib  # noqa: E402
 
 h = nb.get_handle(nb.builtin(rhs), _lib.LSODA if solver.startswith("lsoda") else _lib.DOP853, neq)
 open("/tmp/_k.cubin", "wb").write(h.cubin())
-kname = "b200ode_%s_kernel" % solver
+kname = os.environ.get("NCU_KERNEL", "b200ode_%s_kernel" % solver)
 dis = subprocess.run(["nvdisasm", "-gi", "/tmp/_k.cubin"], capture_output=True, text=True).stdout
 line_of = []  # per instruction, in order; innermost inlined location
 cur = ("?", 0)
