@@ -410,6 +410,28 @@ struct LsWarpVecT {
     // arithmetic is the loop below's.  The pivots (the diagonal of the factors) are collected in
     // rdiag on the way: a lane's diagonal entries sit at different columns, which a tensor-memory
     // load cannot address at once.
+    // eight entries of this lane's row r, columns right of the pivot column: the rank-one update
+    // (rows below the pivot row), the scaled pivot row itself (row k), and row k + 1 filed for
+    // the next step
+    LS_MFN void tm_update8(double (&v)[8], const double* prow8, double* pnext8, double tr, bool below,
+                           bool isk, bool isnext) const
+    {
+        double p[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) p[e] = prow8[e];
+        if (below) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = tr * p[e] + v[e];
+        } else if (isk) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = p[e];
+        }
+        if (isnext) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) pnext8[e] = v[e];
+        }
+    }
+
     LS_MFN int dgefa_tm()
     {
         int info = 0;
@@ -478,33 +500,41 @@ struct LsWarpVecT {
                     wv_tm_wait_st();
                 }
                 if (!has_rows) continue;
-                for (int c0 = ck0; c0 < n; c0 += 8) {
+                {
+                    // the chunk that holds column k: entries up to it stay
                     double v[8], p[8];
-                    wv_tm_ld8(tma(q, c0), v);
+                    wv_tm_ld8(tma(q, ck0), v);
 #pragma unroll
-                    for (int e = 0; e < 8; e++) p[e] = prow[c0 + e];
-                    if (c0 == ck0) {
-                        // (the chunk that holds column k: entries up to it stay)
-                        if (below) {
+                    for (int e = 0; e < 8; e++) p[e] = prow[ck0 + e];
+                    if (below) {
 #pragma unroll
-                            for (int e = 0; e < 8; e++)
-                                if (c0 + e > k) v[e] = tr * p[e] + v[e];
-                        } else if (isk) {
-#pragma unroll
-                            for (int e = 0; e < 8; e++)
-                                if (c0 + e >= k) v[e] = p[e];
-                        }
-                    } else if (below) {
-#pragma unroll
-                        for (int e = 0; e < 8; e++) v[e] = tr * p[e] + v[e];
+                        for (int e = 0; e < 8; e++)
+                            if (ck0 + e > k) v[e] = tr * p[e] + v[e];
                     } else if (isk) {
 #pragma unroll
-                        for (int e = 0; e < 8; e++) v[e] = p[e];
+                        for (int e = 0; e < 8; e++)
+                            if (ck0 + e >= k) v[e] = p[e];
                     }
                     if (isnext) {
 #pragma unroll
-                        for (int e = 0; e < 8; e++) pnext[c0 + e] = v[e];
+                        for (int e = 0; e < 8; e++) pnext[ck0 + e] = v[e];
                     }
+                    wv_tm_st8(tma(q, ck0), v);
+                }
+                int c0 = ck0 + 8;
+                // ... then two chunks per round trip
+                for (; c0 + 8 < n; c0 += 16) {
+                    double v[8], w[8];
+                    wv_tm_ld8x2(tma(q, c0), tma(q, c0 + 8), v, w);
+                    tm_update8(v, prow + c0, pnext + c0, tr, below, isk, isnext);
+                    tm_update8(w, prow + c0 + 8, pnext + c0 + 8, tr, below, isk, isnext);
+                    wv_tm_st8(tma(q, c0), v);
+                    wv_tm_st8(tma(q, c0 + 8), w);
+                }
+                if (c0 < n) {
+                    double v[8];
+                    wv_tm_ld8(tma(q, c0), v);
+                    tm_update8(v, prow + c0, pnext + c0, tr, below, isk, isnext);
                     wv_tm_st8(tma(q, c0), v);
                 }
             }
@@ -632,54 +662,77 @@ struct LsWarpVecT {
     LS_MFN void dgesl_tm(double* b) const
     {
         const bool two = n > 32;
-        // forward.  t[q2]: the running sum of this lane's row in block q2 -- read when that row's
-        // column comes up, dead afterwards, so rows already solved may go on accumulating.
-        double t[2] = {0.0, 0.0};
-        for (int c0 = 0; c0 < n; c0 += 8) {
-            const int q = c0 >> 5;  // the block of rows c0 .. c0 + 7
+        // The right-hand side and the running sums stay in registers (lane l: rows l, l + 32), so a
+        // step of a sweep is subtract, multiply, broadcast, multiply-add -- no shared-memory round
+        // trip and no branch: every lane forms the candidate for its own row each step, the
+        // broadcast takes the lane whose row it is.
+        // t0 / t1: running sums of this lane's rows; read when the row's column comes up, dead
+        // afterwards, so rows already solved may go on accumulating.
+        const int i0 = WV_LANE, i1 = WV_LANE + 32;
+        double b0 = b[i0 < n ? i0 : 0], b1 = b[i1 < n ? i1 : 0];
+        const double d0 = rdiag[i0 < n ? i0 : 0], d1 = rdiag[i1 < n ? i1 : 0];
+        double t0 = 0.0, t1 = 0.0;
+        const int n0 = n < 32 ? n : 32;
+        for (int c0 = 0; c0 < n0; c0 += 8) {
             double w0[8], w1[8];
-            if (q == 0 && two) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
-            else if (q == 0) wv_tm_ld8(tma(0, c0), w0);
-            else wv_tm_ld8(tma(1, c0), w1);
+            if (two) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
+            else wv_tm_ld8(tma(0, c0), w0);
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 const int c = c0 + e;
                 if (c >= n) break;
-                const int cc = c & 31;
-                double bc = 0.0;
-                if (WV_LANE == cc) {
-                    const double tq = (q == 0) ? t[0] : t[1];
-                    bc = fast ? (b[c] - tq) * rdiag[c] : ls_div(b[c] - tq, rdiag[c]);
-                    b[c] = bc;
-                }
-                bc = wv_bcast(bc, cc);
-                if (q == 0) t[0] += w0[e] * bc;
-                if (two) t[1] += w1[e] * bc;
+                const double cand = fast ? (b0 - t0) * d0 : ls_div(b0 - t0, d0);
+                const double bc = wv_bcast(cand, c);
+                if (WV_LANE == c) b0 = cand;
+                t0 += w0[e] * bc;
+                if (two) t1 += w1[e] * bc;
             }
         }
-        WV_SYNC();
+        for (int c0 = 32; c0 < n; c0 += 8) {
+            double w1[8];
+            wv_tm_ld8(tma(1, c0), w1);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int c = c0 + e;
+                if (c >= n) break;
+                const double cand = fast ? (b1 - t1) * d1 : ls_div(b1 - t1, d1);
+                const double bc = wv_bcast(cand, c - 32);
+                if (WV_LANE == c - 32) b1 = cand;
+                t1 += w1[e] * bc;
+            }
+        }
         if (fast) {
-            t[0] = t[1] = 0.0;
-            for (int c0 = (n - 1) & ~7; c0 >= 0; c0 -= 8) {
-                const int q = c0 >> 5;
+            t0 = t1 = 0.0;
+            for (int c0 = (n - 1) & ~7; c0 >= 32; c0 -= 8) {
                 double w0[8], w1[8];
-                if (q == 1) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
-                else wv_tm_ld8(tma(0, c0), w0);
+                wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
 #pragma unroll
                 for (int e = 7; e >= 0; e--) {
                     const int c = c0 + e;
                     if (c >= n) continue;
-                    const int cc = c & 31;
-                    double wc = 0.0;
-                    if (WV_LANE == cc) {
-                        wc = b[c] + ((q == 0) ? t[0] : t[1]);
-                        b[c] = wc;
-                    }
-                    wc = wv_bcast(wc, cc);
-                    t[0] += w0[e] * wc;
-                    if (q == 1) t[1] += w1[e] * wc;
+                    const double cand = b1 + t1;
+                    const double wc = wv_bcast(cand, c - 32);
+                    if (WV_LANE == c - 32) b1 = cand;
+                    t0 += w0[e] * wc;
+                    t1 += w1[e] * wc;
                 }
             }
+            for (int c0 = (n0 - 1) & ~7; c0 >= 0; c0 -= 8) {
+                double w0[8];
+                wv_tm_ld8(tma(0, c0), w0);
+#pragma unroll
+                for (int e = 7; e >= 0; e--) {
+                    const int c = c0 + e;
+                    if (c >= n) continue;
+                    const double cand = b0 + t0;
+                    const double wc = wv_bcast(cand, c);
+                    if (WV_LANE == c) b0 = cand;
+                    t0 += w0[e] * wc;
+                }
+            }
+            // x[i] = w[perm[i]]
+            if (i0 < n) b[i0] = b0;
+            if (i1 < n) b[i1] = b1;
             WV_SYNC();
             double x[2];
 #pragma unroll
@@ -696,6 +749,9 @@ struct LsWarpVecT {
             WV_SYNC();
             return;
         }
+        if (i0 < n) b[i0] = b0;
+        if (i1 < n) b[i1] = b1;
+        WV_SYNC();
         // backward, the reference's order: the owner of row k forms the dot product over ascending
         // c (the other lanes run the same instructions on their own rows; their sums are unused)
         for (int k = n - 2; k >= 0; k--) {
