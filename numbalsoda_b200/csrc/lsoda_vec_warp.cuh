@@ -662,47 +662,55 @@ struct LsWarpVecT {
     LS_MFN void dgesl_tm(double* b) const
     {
         const bool two = n > 32;
-        // The right-hand side and the running sums stay in registers (lane l: rows l, l + 32), so a
-        // step of a sweep is subtract, multiply, broadcast, multiply-add -- no shared-memory round
-        // trip and no branch: every lane forms the candidate for its own row each step, the
-        // broadcast takes the lane whose row it is.
-        // t0 / t1: running sums of this lane's rows; read when the row's column comes up, dead
-        // afterwards, so rows already solved may go on accumulating.
+        // The right-hand side and the running sums stay in registers (lane l: rows l, l + 32): no
+        // shared-memory round trip and no branch in a step of a sweep -- every lane forms the
+        // candidate for its own row each step, the broadcast takes the lane whose row it is.
         const int i0 = WV_LANE, i1 = WV_LANE + 32;
         double b0 = b[i0 < n ? i0 : 0], b1 = b[i1 < n ? i1 : 0];
         const double d0 = rdiag[i0 < n ? i0 : 0], d1 = rdiag[i1 < n ? i1 : 0];
-        double t0 = 0.0, t1 = 0.0;
         const int n0 = n < 32 ? n : 32;
-        for (int c0 = 0; c0 < n0; c0 += 8) {
-            double w0[8], w1[8];
-            if (two) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
-            else wv_tm_ld8(tma(0, c0), w0);
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int c = c0 + e;
-                if (c >= n) break;
-                const double cand = fast ? (b0 - t0) * d0 : ls_div(b0 - t0, d0);
-                const double bc = wv_bcast(cand, c);
-                if (WV_LANE == c) b0 = cand;
-                t0 += w0[e] * bc;
-                if (two) t1 += w1[e] * bc;
-            }
-        }
-        for (int c0 = 32; c0 < n; c0 += 8) {
-            double w1[8];
-            wv_tm_ld8(tma(1, c0), w1);
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int c = c0 + e;
-                if (c >= n) break;
-                const double cand = fast ? (b1 - t1) * d1 : ls_div(b1 - t1, d1);
-                const double bc = wv_bcast(cand, c - 32);
-                if (WV_LANE == c - 32) b1 = cand;
-                t1 += w1[e] * bc;
-            }
-        }
         if (fast) {
-            t0 = t1 = 0.0;
+            // The sweeps as recurrences on the candidates themselves: forward s = (b - t) d is
+            // kept as s -= (a[k][c] d) x_c, backward s = b + t as s += a[r][c] x_c -- one
+            // multiply-add between two broadcasts instead of three operations (the scaled
+            // entries are formed off the critical path).  Same mathematics as the sweeps of the
+            // shared-memory kernel, different rounding: last-bit differences.
+            double s0 = b0 * d0, s1 = b1 * d1;
+            for (int c0 = 0; c0 < n0; c0 += 8) {
+                double w0[8], w1[8];
+                if (two) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
+                else wv_tm_ld8(tma(0, c0), w0);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    w0[e] = -(w0[e] * d0);
+                    if (two) w1[e] = -(w1[e] * d1);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int c = c0 + e;
+                    if (c >= n) break;
+                    const double x = wv_bcast(s0, c);
+                    if (WV_LANE == c) b0 = x;
+                    s0 = fma(w0[e], x, s0);
+                    if (two) s1 = fma(w1[e], x, s1);
+                }
+            }
+            for (int c0 = 32; c0 < n; c0 += 8) {
+                double w1[8];
+                wv_tm_ld8(tma(1, c0), w1);
+#pragma unroll
+                for (int e = 0; e < 8; e++) w1[e] = -(w1[e] * d1);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int c = c0 + e;
+                    if (c >= n) break;
+                    const double x = wv_bcast(s1, c - 32);
+                    if (WV_LANE == c - 32) b1 = x;
+                    s1 = fma(w1[e], x, s1);
+                }
+            }
+            s0 = b0;
+            s1 = b1;
             for (int c0 = (n - 1) & ~7; c0 >= 32; c0 -= 8) {
                 double w0[8], w1[8];
                 wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
@@ -710,11 +718,10 @@ struct LsWarpVecT {
                 for (int e = 7; e >= 0; e--) {
                     const int c = c0 + e;
                     if (c >= n) continue;
-                    const double cand = b1 + t1;
-                    const double wc = wv_bcast(cand, c - 32);
-                    if (WV_LANE == c - 32) b1 = cand;
-                    t0 += w0[e] * wc;
-                    t1 += w1[e] * wc;
+                    const double x = wv_bcast(s1, c - 32);
+                    if (WV_LANE == c - 32) b1 = x;
+                    s0 = fma(w0[e], x, s0);
+                    s1 = fma(w1[e], x, s1);
                 }
             }
             for (int c0 = (n0 - 1) & ~7; c0 >= 0; c0 -= 8) {
@@ -724,10 +731,9 @@ struct LsWarpVecT {
                 for (int e = 7; e >= 0; e--) {
                     const int c = c0 + e;
                     if (c >= n) continue;
-                    const double cand = b0 + t0;
-                    const double wc = wv_bcast(cand, c);
-                    if (WV_LANE == c) b0 = cand;
-                    t0 += w0[e] * wc;
+                    const double x = wv_bcast(s0, c);
+                    if (WV_LANE == c) b0 = x;
+                    s0 = fma(w0[e], x, s0);
                 }
             }
             // x[i] = w[perm[i]]
@@ -748,6 +754,38 @@ struct LsWarpVecT {
             }
             WV_SYNC();
             return;
+        }
+        // strict: the reference's operations in its order.  t0 / t1: running sums of this lane's
+        // rows; read when the row's column comes up, dead afterwards, so rows already solved may
+        // go on accumulating.
+        double t0 = 0.0, t1 = 0.0;
+        for (int c0 = 0; c0 < n0; c0 += 8) {
+            double w0[8], w1[8];
+            if (two) wv_tm_ld8x2(tma(0, c0), tma(1, c0), w0, w1);
+            else wv_tm_ld8(tma(0, c0), w0);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int c = c0 + e;
+                if (c >= n) break;
+                const double cand = ls_div(b0 - t0, d0);
+                const double bc = wv_bcast(cand, c);
+                if (WV_LANE == c) b0 = cand;
+                t0 += w0[e] * bc;
+                if (two) t1 += w1[e] * bc;
+            }
+        }
+        for (int c0 = 32; c0 < n; c0 += 8) {
+            double w1[8];
+            wv_tm_ld8(tma(1, c0), w1);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int c = c0 + e;
+                if (c >= n) break;
+                const double cand = ls_div(b1 - t1, d1);
+                const double bc = wv_bcast(cand, c - 32);
+                if (WV_LANE == c - 32) b1 = cand;
+                t1 += w1[e] * bc;
+            }
         }
         if (i0 < n) b[i0] = b0;
         if (i1 < n) b[i1] = b1;
