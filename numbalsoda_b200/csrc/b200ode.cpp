@@ -922,9 +922,11 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
                             align256(sizeof(double) * u0_doubles) +
                             align256(data_bytes) + (rtol_b ? align256(rtol_bytes) : 0) +
                             (atol_b ? align256(atol_bytes) : 0);
-    // chunk size.  Compute-bound shapes (few output bytes per trajectory): at least 4
-    // trajectories per resident lane -- a persistent grid needs a few per lane to balance --
-    // and about 1/8 of the ensemble.  Copy-bound shapes (>= 8 KB of rows per trajectory: the
+    // chunk size.  Compute-bound shapes (few output bytes per trajectory): one trajectory per
+    // resident lane and at least 1/16 of the ensemble -- the chunks run two at a time on the two
+    // kernel streams, so a chunk's stragglers share the SMs with the next chunk's head, and what
+    // stays exposed is the last chunk's copy (Robertson, 2^20 trajectories, e2e: 4 per lane
+    // 8.05 M traj/s, 2 per lane 8.19 M, 1 per lane 8.51 M, 1/2 per lane 7.19 M).  Copy-bound shapes (>= 8 KB of rows per trajectory: the
     // device-to-host copy of a chunk takes longer than integrating it, e.g. Lorenz with 1001
     // rows): small chunks, half the resident lanes each -- two chunks run side by side on the
     // two kernel streams -- so that the first rows are on their way after one trajectory's
@@ -934,7 +936,7 @@ static int solve_host(int solver, b200ode_rhs_t H, long long B, int neq, const d
     CU(cuMemGetInfo_v2(&free_b, &total_b));
     const bool copy_bound = row_bytes >= 8192;
     long long chunk = copy_bound ? std::max<long long>(resident / 2, (B + 15) / 16)
-                                 : std::max<long long>(4 * resident, (B + 7) / 8);
+                                 : std::max<long long>(resident, (B + 15) / 16);
     if (const char* e = getenv("B200ODE_CHUNK")) chunk = std::max<long long>(1, atoll(e));  // experiments
     const size_t cap = std::min<size_t>((size_t)1 << 30, std::max<size_t>(free_b / 8, (size_t)64 << 20));
     chunk = std::min<long long>(chunk, (long long)std::max<size_t>(1, cap / per_traj));
