@@ -326,7 +326,7 @@ def test_warp_kernel_numba_rhs_sizes_and_edge_cases():
         du[n - 1] = k * (u[n - 2] - u[n - 1]) / n
 
     cf = numba.cfunc(nb.lsoda_sig)(chain)
-    for n in (9, 20, 33):
+    for n in (9, 20, 33, 128):  # ... up to the largest system the warp kernels take
         u0n = 1.0 + 0.1 * np.arange(n)
         Pn = np.array([[2.0 * (1 + b), float(n)] for b in range(5)])
         ten = np.linspace(0.0, 5.0, 11)

@@ -392,6 +392,27 @@ def test_tensor_memory_matrix_strict_bitwise_and_same_as_shared_memory(n, monkey
     monkeypatch.delenv("B200ODE_LSODAW_TMEM", raising=False)
 
 
+@pytest.mark.parametrize("n", [65, 100, 128])
+def test_warp_kernel_largest_dense_systems_strict_bitwise(n):
+    """Above the tensor-memory kernel's 64 equations the dense matrix is back in shared memory
+    (n = 128: 132 KB, one trajectory per SM): the nonlinear chain and the column-interchanging
+    system, bit for bit the oracle."""
+    nb = _nb()
+    B = 5
+    te = np.linspace(0.0, 2.0, 6)
+    for rhs, u0, P, tol in (
+            (pr.upper_rhs, np.ones(n), np.array([[1000.0 * (1 + 0.1 * b), 5000.0, float(n)] for b in range(B)]),
+             (1e-6, 1e-9)),
+            (pr.chain_rhs, 1.0 + 0.1 * np.arange(n), np.array([[50.0 * (1 + b), float(n)] for b in range(B)]),
+             (1e-7, 1e-9))):
+        us, ok, cnt = nb.lsoda(rhs, u0, te, P, *tol, strict=True, counters=True)
+        ref, okr, cr = orc.solve_batch("lsoda", pr.cfunc_address(rhs), u0, te, P, *tol)
+        assert list(ok) == list(okr) and np.array_equal(cnt, cr) and np.array_equal(us, ref), (n, rhs.__name__)
+        us2, ok2 = nb.lsoda(rhs, u0, te, P, *tol)
+        err = np.abs(us2 - ref) / (tol[0] * np.abs(ref) + tol[1])
+        assert list(ok2) == list(okr) and err.max() < 50.0, (n, rhs.__name__, err.max())
+
+
 def test_data_record_passed_by_address():
     """Records of more than 16 doubles are not staged into registers: the RHS gets the
     record's device address (the kernels' `_ptr` entry points), as it would a C struct."""
