@@ -404,9 +404,14 @@ static int init_device_state(b200ode_rhs_t H, int device, PerDevice& P)
         if (H->solver == B200ODE_LSODA)
             CU(cuModuleGetFunction(&P.fn_band, P.mod, "b200ode_lsodaw_band_kernel"));
         if (H->solver == B200ODE_LSODA && H->neq > 32 && H->neq <= B200ODE_LSODAW_TMEM_NMAX) {
-            CU(cuModuleGetFunction(&P.fn_tmem, P.mod, "b200ode_lsodaw_tmem_kernel"));
-            CU(cuFuncSetAttribute(P.fn_tmem, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                  B200ODE_LSODAW_TMEM_WARPS * B200ODE_LSODAW_TMEM_DOUBLES(H->neq) * (int)sizeof(double)));
+            // (only if the eight warps' vectors fit the shared memory of a block)
+            const int need = B200ODE_LSODAW_TMEM_WARPS * B200ODE_LSODAW_TMEM_DOUBLES(H->neq) * (int)sizeof(double);
+            int optin = 0;
+            CU(cuDeviceGetAttribute(&optin, CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN, dev));
+            if (need + 2048 <= optin) {
+                CU(cuModuleGetFunction(&P.fn_tmem, P.mod, "b200ode_lsodaw_tmem_kernel"));
+                CU(cuFuncSetAttribute(P.fn_tmem, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, need));
+            }
         }
     } else
         CU(cuModuleGetFunction(&P.fn_ptr, P.mod,
