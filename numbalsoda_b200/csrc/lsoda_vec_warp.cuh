@@ -162,7 +162,9 @@ static inline void wv_tm_st1(unsigned, double) {}
 // At n = 64 the matrix is 32 KB of the 47 KB a trajectory needs, and shared memory holds four
 // trajectories per SM -- one warp per scheduler, nothing to hide latency with.  Tensor memory is
 // another 256 KB per SM that this kernel has no other use for: eight matrices, eight warps.
-template <bool TM>
+// BAND: 1 = the matrix is banded, 0 = dense, -1 = decided at run time by ml (host harness).  The
+// three kernels each compile one of the two paths only: they are bound by instruction fetch.
+template <bool TM, int BAND = -1>
 struct LsWarpVecT {
     unsigned tm;  // TM: tensor-memory address of this warp's 32 lanes x 256 columns
     double* fcopy;  // TM: right-hand sides of the perturbed copies (the matrix columns' staging)
@@ -212,7 +214,7 @@ struct LsWarpVecT {
                                                          : B200ODE_LSODAW_JCOLS) * ld);
         perm = ipvt + n;
     }
-    LS_MFN bool banded() const { return ml >= 0; }
+    LS_MFN bool banded() const { return BAND < 0 ? ml >= 0 : BAND == 1; }
     LS_MFN int jac_rhs_calls() const { return banded() && ml + mu + 1 < n ? ml + mu + 1 : n; }
     LS_MFN int size() const { return n; }
     LS_MFN void sync(unsigned) {}
@@ -992,7 +994,11 @@ struct LsWarpVecT {
     // travelling by shuffle -- one shuffle + one multiply-add per step on the critical path instead
     // of a shared-memory round trip and a barrier -- ran the C4 banded workload at 128 k traj/s
     // against 199 k: with 11 warps per SM the barriers' latency is hidden and the ~30
-    // select / shuffle instructions per step, executed by all 32 lanes, are not.)
+    // select / shuffle instructions per step, executed by all 32 lanes, are not.  Nor does a
+    // sliding window of b in registers with every lane running the same scalar recurrence -- no
+    // barrier, no shuffle, bit-identical on the host harness: 259 k against 264 k, strict mode
+    // 175 k against 209 k.  This solve is 40 % of the banded kernel's time
+    // (profiles/r2_lsodaw_band_v1.txt) and bound by the instructions of its 2 n steps.)
     LS_MFN void dgbsl(double* b) const
     {
         const int lda = 2 * ml + mu + 1, m = ml + mu;
@@ -1192,6 +1198,6 @@ struct LsWarpVecT {
         return dgefa() != 0 ? 1 : 0;
     }
 };
-typedef LsWarpVecT<false> LsWarpVec;
+typedef LsWarpVecT<false, -1> LsWarpVec;
 
 #endif

@@ -23,13 +23,13 @@
 
 __constant__ B200LsodaTables b200_lsoda_tables = B200_LSODA_TABLES_INIT;
 
-template <bool TM>
+template <bool TM, int BAND>
 __device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L, unsigned tm = 0)
 {
     extern __shared__ double b200_smem[];
     const B200LsodaTables* T = &b200_lsoda_tables;
     const int n = L.neq;
-    LsWarpVecT<TM> v;
+    LsWarpVecT<TM, BAND> v;
     if (TM) {
         // a block of independent warps: each its own slice of shared and of tensor memory
         v.tm = tm;
@@ -87,13 +87,13 @@ __device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L, unsigned
 extern "C" __global__ void __launch_bounds__(32, 8)
 b200ode_lsodaw_kernel(const B200OdeLaunch L)
 {
-    lsodaw_ensemble<false>(L);
+    lsodaw_ensemble<false, 0>(L);
 }
 
 extern "C" __global__ void __launch_bounds__(32, 12)
 b200ode_lsodaw_band_kernel(const B200OdeLaunch L)
 {
-    lsodaw_ensemble<false>(L);
+    lsodaw_ensemble<false, 1>(L);
 }
 
 // Dense matrix in tensor memory (lsoda_vec_warp.cuh), 32 < n <= 64: one block of eight warps per
@@ -113,7 +113,7 @@ b200ode_lsodaw_tmem_kernel(const B200OdeLaunch L)
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    lsodaw_ensemble<true>(L, tm_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 256u);
+    lsodaw_ensemble<true, 0>(L, tm_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 256u);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tm_base));
