@@ -998,7 +998,9 @@ struct LsWarpVecT {
     // sliding window of b in registers with every lane running the same scalar recurrence -- no
     // barrier, no shuffle, bit-identical on the host harness: 259 k against 264 k, strict mode
     // 175 k against 209 k.  This solve is 40 % of the banded kernel's time
-    // (profiles/r2_lsodaw_band_v1.txt) and bound by the instructions of its 2 n steps.)
+    // (profiles/r2_lsodaw_band_v1.txt) and bound by the instructions of its 2 n steps; multiplying
+    // by stored reciprocals of the diagonal in the throughput mode changes nothing either
+    // (280.2 k / 280.6 k against 280.6 k / 280.7 k, same box).)
     LS_MFN void dgbsl(double* b) const
     {
         const int lda = 2 * ml + mu + 1, m = ml + mu;

@@ -29,13 +29,16 @@ __device__ __forceinline__ void lsodaw_ensemble(const B200OdeLaunch& L, unsigned
     extern __shared__ double b200_smem[];
     const B200LsodaTables* T = &b200_lsoda_tables;
     const int n = L.neq;
+    // parallel triangular solves unless the handle was linked for bit parity: a link-time constant
+    // (link_flags.cu), so each linked image carries one of the two sets of sweeps only
+    const bool kFastSolves = (b200ode_link_flags() & 1u) == 0u;
     LsWarpVecT<TM, BAND> v;
     if (TM) {
         // a block of independent warps: each its own slice of shared and of tensor memory
         v.tm = tm;
-        v.attach(b200_smem + (size_t)(threadIdx.x >> 5) * B200ODE_LSODAW_TMEM_DOUBLES(n), n, L.strict == 0);
+        v.attach(b200_smem + (size_t)(threadIdx.x >> 5) * B200ODE_LSODAW_TMEM_DOUBLES(n), n, kFastSolves);
     } else {
-        v.attach(b200_smem, n, L.strict == 0,
+        v.attach(b200_smem, n, kFastSolves,
                  L.scratch ? L.scratch + (size_t)blockIdx.x * B200ODE_LSODAW_MATRIX(n) : nullptr, L.ml, L.mu);
     }
     const int nt = L.nt;
