@@ -31,6 +31,24 @@ def test_lsoda_and_dop853_shards_equal_the_whole():
                 assert np.array_equal(a, b)
 
 
+def test_warp_kernels_shards_equal_the_whole():
+    """n = 64: the dense path keeps its matrices in tensor memory (one block of eight warps per
+    SM allocates all 512 columns) and the banded path in shared memory; shards of one ensemble
+    run concurrently, on one device or several."""
+    import numbalsoda_b200 as nb
+    B = 37
+    P = pr.brusselator_sweep(B)
+    te = np.linspace(0.0, 10.0, 25)
+    for rhs, u0, kw in (("brusselator1d", pr.brusselator_u0(), {}),
+                        ("brusselator1d_il", pr.interleave(pr.brusselator_u0()), dict(ml=2, mu=2))):
+        whole = nb.lsoda(nb.builtin(rhs), u0, te, P, 1e-6, 1e-8, strict=True, counters=True, **kw)
+        assert whole[1].all()
+        for dev in _device_sets():
+            part = nb.lsoda(nb.builtin(rhs), u0, te, P, 1e-6, 1e-8, strict=True, counters=True, device=dev, **kw)
+            for a, b in zip(whole, part):
+                assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("mode", ["t_eval", "two_pass", "max_rows"])
 def test_solve_ivp_shards_equal_the_whole(mode):
     import numbalsoda_b200 as nb
