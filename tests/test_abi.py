@@ -99,7 +99,12 @@ def test_warp_kernels_do_not_spill(tmp_path, solver, mode):
     found = re.findall(r"Function (b200ode_\w+_kernel\w*):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", res)
     assert found, res
     if solver == "lsoda":
-        assert {k for k, *_ in found} >= {"b200ode_lsodaw_kernel", "b200ode_lsodaw_band_kernel"}
+        assert {k for k, *_ in found} >= {"b200ode_lsodaw_kernel", "b200ode_lsodaw_band_kernel",
+                                          "b200ode_lsodaw_tmem_kernel"}
+        # the tensor-memory kernel really is one: tcgen05 allocation, loads and stores in its SASS
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", "b200ode_lsodaw_tmem_kernel", str(f)],
+                              capture_output=True, text=True).stdout
+        assert "LDTM" in sass and "STTM" in sass and "UTCATOMSWS" in sass
     for name, regs, stack, local in found:
         assert int(stack) == 0 and int(local) == 0 and int(regs) <= 255, (name, regs, stack, local)
 
