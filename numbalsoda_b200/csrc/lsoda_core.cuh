@@ -87,7 +87,7 @@ struct LsLane {
     double told, pnorm, del, delp, rate, rh;
     int nq, nslp;
     int nst, nfe, nje;
-    int nqu : 16, icount : 16;  // (order of the last step; -1..20)
+    int nqu : 16, icount : 16;  // (order of the last step; 20 down to -1, where it stays)
     // The small state variables share one register (the kernel carries ~75 values per thread
     // across a pass; at 128 registers -- 16 warps per SM -- every word counts).  Ranges: meth 1-2,
     // mused 0-2, jcur 0-1, irflag 0-2, ipup 0 / 2 / 5 (miter), m 0-3 (LS_MAXCOR), phase LS_P_*,
@@ -749,7 +749,9 @@ LS_FN bool ls_advance_b(LsLane& s, LsRun& R, V& v, const B200LsodaTables* T, dou
         s.mused = s.meth;
         v.accept(l, &ELCO(s.nq, 0));  // yh[j] += el[j] * acor, j = 1..l
         s.flags |= LS_F_FINISH;
-        s.icount--;
+        // (the reference decrements on every step, LSODA.cpp:1203, and only asks for the sign; the
+        // 16-bit field stops at -1 instead of wrapping after 32 k steps without a method switch)
+        if (s.icount >= 0) s.icount--;
         bool switched = false;
         if (s.icount < 0) {
             ls_methodswitch(s, T, dsm, s.pnorm, pdh, s.rh);

@@ -4,6 +4,7 @@ Jacobian / switch counters must be identical bit for bit.  This validates the re
 control flow and storage scheme here, without a GPU; tests/test_gpu_lsoda.py then runs
 the same comparisons through the CUDA kernel."""
 import ctypes as ct
+import math
 import os
 import subprocess
 
@@ -74,6 +75,31 @@ def ocnt(st):
 
 def same(a, b):
     return np.array_equal(a, b, equal_nan=True)
+
+
+def _late_stiffness(t, u, du, p):
+    # a fast oscillation followed closely (non-stiff), then, from t = p[0] on, pulled to it hard
+    k = 1.0 if t < p[0] else 1.0e6
+    du[0] = -k * (u[0] - math.cos(20.0 * t)) - 20.0 * math.sin(20.0 * t)
+    du[1] = u[0] - u[1]
+
+
+def test_method_switch_is_still_considered_after_40k_steps():
+    """The reference decrements `icount` on every step (LSODA.cpp:1203) and consults methodswitch
+    while it is negative; the core keeps it in a 16-bit field that must stop at -1, not wrap.
+    More than 2^15 Adams steps, then the problem turns stiff: the switch to BDF has to come at
+    the reference's step."""
+    import numba
+    from numba import types
+    sig = types.void(types.double, types.CPointer(types.double), types.CPointer(types.double),
+                     types.CPointer(types.double))
+    cf = numba.cfunc(sig)(_late_stiffness)
+    u0, data = np.array([1.0, 0.0]), np.array([150.0])
+    te = np.array([0.0, 100.0, 149.0, 151.0, 160.0])
+    ref, okr, st = orc.lsoda(cf.address, u0, te, data, rtol=1e-10, atol=1e-12, mxstep=200000)
+    assert okr and st.nswitch >= 1 and st.meth == 2 and st.nst > 40000
+    us, ok, cnt = run_core(cf.address, u0, te, data, 1e-10, 1e-12, mxstep=200000)
+    assert ok and cnt == ocnt(st) and same(us, ref)
 
 
 @pytest.mark.parametrize("name", ["lv_test", "lv_readme", "robertson", "lorenz", "lorenz_short"])
