@@ -60,7 +60,8 @@ extern "C" {
                                 reference's by ~1e-7 relative.  Implied by STRICT_FP. */
 
 /* error codes */
-#define B200ODE_EINVAL -1  /* bad argument */
+#define B200ODE_EINVAL -1  /* bad argument (also: more than 2^31 - 1 trajectories in one device-resident
+                              launch -- the host-buffer entry points chunk the ensemble themselves) */
 #define B200ODE_ELINK -2   /* nvJitLink failed (message has the linker log) */
 #define B200ODE_ECUDA -3   /* CUDA driver error */
 #define B200ODE_ENODEV -4  /* no CUDA driver / device: there is NO CPU fallback */

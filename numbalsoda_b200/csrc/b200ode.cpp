@@ -630,6 +630,10 @@ static int check_args(b200ode_rhs_t H, int solver, long long B, int neq, const v
 static int launch(b200ode_rhs_t H, PerDevice* P, const B200OdeLaunch& args_in, CUstream stream)
 {
     if (args_in.B == 0) return 0;
+    // (the thread kernels keep a lane's trajectory index in 32 bits; the host-buffer path launches
+    // chunks far below this, a device-resident ensemble of more has to be split by the caller)
+    if (args_in.B > 0x7fffffffLL)
+        return fail(B200ODE_EINVAL, "B = %lld: at most 2^31 - 1 trajectories per launch", args_in.B);
     B200OdeLaunch args = args_in;
     unsigned slot = H->slot.fetch_add(1) % kCounterSlots;
     CUdeviceptr next = P->next + slot * sizeof(unsigned long long);
@@ -1142,6 +1146,8 @@ static int check_ivp(b200ode_rhs_t H, const b200ode_ivp_problem* p)
 
 static int launch_ivp(b200ode_rhs_t H, PerDevice* P, B200IvpLaunch args, CUstream stream)
 {
+    if (args.B > 0x7fffffffLL)
+        return fail(B200ODE_EINVAL, "B = %lld: at most 2^31 - 1 trajectories per launch", args.B);
     if (args.B == 0) return 0;
     unsigned slot = H->slot.fetch_add(1) % kCounterSlots;
     CUdeviceptr next = P->next + slot * sizeof(unsigned long long);
